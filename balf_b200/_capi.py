@@ -1,0 +1,244 @@
+"""ctypes binding of ``libbalf_b200.so`` (include/balf_b200.h) for the PyTorch-facing modules.
+
+PyTorch is plumbing here: it owns device memory and streams; every computation is a call into
+the C-ABI with raw device pointers.  The library must be present -- importing this module
+without it raises, and there is no CPU or eager fallback anywhere in the package.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbalf_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "balf_b200.h")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "balf_b200: %s is missing. Build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+        "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+_lib = ctypes.CDLL(LIB_PATH)
+
+c_int, c_void_p, c_size_t, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float
+
+
+class DetectorArch(ctypes.Structure):
+    _fields_ = [("dims", ctypes.c_int32 * 5), ("grid_h", ctypes.c_int32), ("grid_w", ctypes.c_int32),
+                ("block_h", ctypes.c_int32), ("block_w", ctypes.c_int32), ("grid_factor", ctypes.c_int32),
+                ("block_factor", ctypes.c_int32), ("proj_factor", ctypes.c_int32), ("reduction", ctypes.c_int32),
+                ("cell", ctypes.c_int32)]
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(_lib, name)
+    fn.restype, fn.argtypes = restype, list(argtypes)
+    return fn
+
+
+_P = c_void_p
+_arch_p = ctypes.POINTER(DetectorArch)
+_last_error = _sig("balf_last_error", ctypes.c_char_p)
+abi_version = _sig("balf_abi_version", c_int)
+launch_count = _sig("balf_launch_count", ctypes.c_ulonglong)
+_check_arch = _sig("balf_detector_check_arch", c_int, _arch_p)
+_raw_count = _sig("balf_detector_raw_weight_count", ctypes.c_int64, _arch_p)
+_packed_count = _sig("balf_detector_packed_weight_count", ctypes.c_int64, _arch_p)
+_pack = _sig("balf_detector_pack_weights", c_int, _arch_p, _P, _P, _P)
+_pad_geometry = _sig("balf_pad_geometry", c_int, c_int, c_int, c_int, *([ctypes.POINTER(c_int)] * 4))
+_preprocess = _sig("balf_preprocess_u8", c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P)
+_det_ws = _sig("balf_detector_workspace_bytes", c_size_t, _arch_p, c_int, c_int, c_int)
+_det_fwd = _sig("balf_detector_forward", c_int, _arch_p, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, c_int, _P)
+_pixel_shuffle = _sig("balf_pixel_shuffle", c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P)
+_nms_ws = _sig("balf_nms_workspace_bytes", c_size_t, c_int, c_int, c_int, c_int)
+_win_nms = _sig("balf_windowed_nms_topk", c_int, _P, *([c_int] * 10), _P, _P, _P, _P, c_size_t, _P)
+_greedy_nms = _sig("balf_greedy_nms_topk", c_int, _P, *([c_int] * 8), c_float, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                   c_size_t, _P)
+
+
+def declared_symbols():
+    """Every function the public header declares (tests check that the library exports them all)."""
+    return re.findall(r"\b(balf_[a-z0-9_]+)\s*\(", open(HEADER_PATH).read())
+
+
+class BalfError(RuntimeError):
+    pass
+
+
+def _ok(code):
+    if code != 0:
+        msg = (_last_error() or b"").decode()
+        raise (ValueError if code < 0 else BalfError)("balf_b200: %s (code %d)" % (msg, code))
+
+
+def _stream(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("balf_b200 has no CPU path: %s must be a CUDA tensor" % what)
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """grow-only scratch buffer per device (the C-ABI never allocates)."""
+    key = str(device)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------ detector
+def arch_struct(arch):
+    a = DetectorArch()
+    a.dims[:] = arch["dims"]
+    a.grid_h, a.grid_w = arch["grid"]
+    a.block_h, a.block_w = arch["block"]
+    a.grid_factor, a.block_factor, a.proj_factor = arch["gfac"], arch["bfac"], arch["proj"]
+    a.reduction, a.cell = arch["red"], arch["cell"]
+    return a
+
+
+def check_supported_arch(arch):
+    _ok(_check_arch(ctypes.byref(arch_struct(arch))))
+
+
+def detector_pack_weights(raw, arch):
+    _need_cuda(raw, "the weight blob")
+    a = arch_struct(arch)
+    n_raw, n_packed = _raw_count(ctypes.byref(a)), _packed_count(ctypes.byref(a))
+    if raw.numel() != n_raw or raw.dtype != torch.float32:
+        raise ValueError("weight blob has %d floats, the architecture needs %d" % (raw.numel(), n_raw))
+    raw = raw.contiguous()
+    packed = torch.empty(n_packed, dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        _ok(_pack(ctypes.byref(a), _ptr(raw), _ptr(packed), _stream(raw.device)))
+    return packed
+
+
+PRECISIONS = {"fp32": 0, "tf32": 1}
+
+
+def detector_forward(x, packed, arch, precision="fp32", want_logits=True):
+    _need_cuda(x, "the input")
+    a = arch_struct(arch)
+    x = x.contiguous().float()
+    B, _, H, W = x.shape
+    n_logit = arch["cell"] ** 2 + 1
+    logits = torch.empty(B, n_logit, H // arch["cell"], W // arch["cell"], dtype=torch.float32, device=x.device) \
+        if want_logits else None
+    prob = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+    nbytes = _det_ws(ctypes.byref(a), B, H, W)
+    ws = _workspace(x.device, nbytes)
+    with torch.cuda.device(x.device):
+        _ok(_det_fwd(ctypes.byref(a), _ptr(packed), _ptr(x), B, H, W, _ptr(logits), _ptr(prob), _ptr(ws), nbytes,
+                     PRECISIONS[precision], _stream(x.device)))
+    return logits, prob
+
+
+def pixel_shuffle(t, r):
+    _need_cuda(t, "the input")
+    t = t.contiguous().float()
+    n, c, h, w = t.shape
+    out = torch.empty(n, c // (r * r), h * r, w * r, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _ok(_pixel_shuffle(_ptr(t), _ptr(out), n, c, h, w, r, _stream(t.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ pre / post
+def pad_geometry(h, w, factor=64):
+    """-> (Hp, Wp, top, left) of make_shape_even + mod_padding_symmetric (pure host arithmetic)."""
+    out = [c_int() for _ in range(4)]
+    _ok(_pad_geometry(int(h), int(w), int(factor), *[ctypes.byref(o) for o in out]))
+    return tuple(o.value for o in out)
+
+
+def preprocess_u8(img, factor=64):
+    """img [B,H,W,C] uint8 CUDA -> (x [B,3,Hp,Wp] fp32, (top, left))."""
+    _need_cuda(img, "the image batch")
+    img = img.contiguous()
+    B, H, W, C = img.shape
+    Hp, Wp, top, left = pad_geometry(H, W, factor)
+    x = torch.empty(B, 3, Hp, Wp, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _ok(_preprocess(_ptr(img), B, H, W, C, _ptr(x), Hp, Wp, top, left, _stream(img.device)))
+    return x, (top, left)
+
+
+def _crop_args(score, crop):
+    _need_cuda(score, "the score map")
+    if score.dim() == 2:
+        score = score[None]
+    score = score.contiguous().float()
+    B, Hs, Ws = score.shape
+    top, left, H, W = crop if crop is not None else (0, 0, Hs, Ws)
+    return score, B, Hs, Ws, int(top), int(left), int(H), int(W)
+
+
+def windowed_nms_topk(score, k, border=15, nms_size=15, crop=None):
+    """score [B,Hs,Ws] CUDA -> (xy int32 [B,k,2], score fp32 [B,k], count int32 [B])."""
+    score, B, Hs, Ws, top, left, H, W = _crop_args(score, crop)
+    dev = score.device
+    xy = torch.zeros(B, k, 2, dtype=torch.int32, device=dev)
+    sc = torch.zeros(B, k, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    nbytes = _nms_ws(B, H, W, k)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _ok(_win_nms(_ptr(score), B, Hs, Ws, top, left, H, W, int(border), int(nms_size), int(k), _ptr(xy), _ptr(sc),
+                     _ptr(cnt), _ptr(ws), nbytes, _stream(dev)))
+    return xy, sc, cnt
+
+
+def greedy_nms_topk(score, k, border=15, thr=0.001, radius=15, subpixel_ps=0, crop=None):
+    """score [B,Hs,Ws] CUDA -> (xy int32 [B,k,2], score [B,k], dxdy fp32 [B,k,2] or None, count [B])."""
+    score, B, Hs, Ws, top, left, H, W = _crop_args(score, crop)
+    dev = score.device
+    xy = torch.zeros(B, k, 2, dtype=torch.int32, device=dev)
+    sc = torch.zeros(B, k, dtype=torch.float32, device=dev)
+    dxdy = torch.zeros(B, k, 2, dtype=torch.float32, device=dev) if subpixel_ps else None
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    nbytes = _nms_ws(B, H, W, k)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _ok(_greedy_nms(_ptr(score), B, Hs, Ws, top, left, H, W, int(border), float(thr), int(radius), int(k),
+                        int(subpixel_ps), _ptr(xy), _ptr(sc), _ptr(dxdy), _ptr(cnt), _ptr(ws), nbytes, _stream(dev)))
+    return xy, sc, dxdy, cnt
+
+
+_apply_nms_map = _sig("balf_apply_nms_map", c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P)
+_subpixel = _sig("balf_subpixel_refine", c_int, _P, *([c_int] * 8), _P, c_int, c_int, _P, _P)
+
+
+def apply_nms_map(score, nms_size, border=0):
+    """dense apply_nms: score [B,H,W] (or [H,W]) CUDA -> same shape."""
+    _need_cuda(score, "the score map")
+    squeeze = score.dim() == 2
+    s = (score[None] if squeeze else score).contiguous().float()
+    out = torch.empty_like(s)
+    with torch.cuda.device(s.device):
+        _ok(_apply_nms_map(_ptr(s), s.shape[0], s.shape[1], s.shape[2], int(border), int(nms_size), _ptr(out),
+                           _stream(s.device)))
+    return out[0] if squeeze else out
+
+
+def subpixel_refine(score, xy, ps, border=0, crop=None):
+    """score [B,Hs,Ws], xy int32 [B,n,2] -> dxdy fp32 [B,n,2] (offset to add, includes -ps//2)."""
+    score, B, Hs, Ws, top, left, H, W = _crop_args(score, crop)
+    xy = xy.contiguous().to(torch.int32)
+    n = xy.shape[1]
+    dxdy = torch.zeros(B, n, 2, dtype=torch.float32, device=score.device)
+    with torch.cuda.device(score.device):
+        _ok(_subpixel(_ptr(score), B, Hs, Ws, top, left, H, W, int(border), _ptr(xy), n, int(ps), _ptr(dxdy),
+                      _stream(score.device)))
+    return dxdy

@@ -1,0 +1,642 @@
+// Score-map post-processing for BALF on sm_100a: border mask, windowed NMS, greedy NMS,
+// threshold, k-th-value / top-k selection, sub-pixel refinement.
+//
+// Reference semantics (restated in oracle/postproc.py, bit-exact on indices):
+//   balf/utils/test_utils.py:34-47   remove_borders
+//   balf/utils/test_utils.py:50-54   apply_nms            (windowed max compare)
+//   balf/utils/test_utils.py:56-95   get_point_coordinates / find_index_higher_scores
+//   balf/utils/test_utils.py:97-128  get_points_direct_from_score_map (threshold)
+//   balf/utils/test_utils.py:130-168 nms_fast             (greedy, (2r+1)^2 exclusion box)
+//   balf/utils/test_utils.py:170-215 soft_argmax_points   (sub-pixel)
+//   demo/demo_match.py:38-57         un-pad crop, top-k by score
+//
+// All of this is HBM-bound byte/index work: the score map is read once (coalesced rows into a
+// shared-memory halo tile), the window maximum is separable (row pass with lanes on rows, column
+// pass with lanes on columns, log-step doubling networks in registers), survivors are compacted
+// as 64-bit (score, ~raster) keys, and one CTA per image does radix-select + bitonic sort.
+#include "common.cuh"
+#include "../../include/balf_b200.h"
+
+namespace balf {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------ keys
+// key = (sortable(score) << 32) | ~raster : descending key order == score desc, raster asc.
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(uint32_t s) {
+    uint32_t u = s ^ ((s >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ u64 make_key(float score, uint32_t raster) {
+    return ((u64)f2sortable(score) << 32) | (u64)(0xFFFFFFFFu - raster);
+}
+__device__ __forceinline__ uint32_t key_raster(u64 k) { return 0xFFFFFFFFu - (uint32_t)k; }
+__device__ __forceinline__ float key_score(u64 k) { return sortable2f((uint32_t)(k >> 32)); }
+
+struct MapView {
+    const float* score;   // [B, Hs, Ws]
+    int Hs, Ws, top, left, H, W, border;
+    // border-masked score of crop pixel (y, x), both in range  (remove_borders)
+    __device__ __forceinline__ float masked(int b, int y, int x) const {
+        bool in = (y >= border) & (y < H - border) & (x >= border) & (x < W - border);
+        return in ? __ldg(score + ((size_t)b * Hs + top + y) * Ws + left + x) : 0.0f;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ tile engine
+// Separable window maximum over a TH x TW output tile; the window of output i covers inputs
+// [i-LO, i+HI] clipped to the map (values outside the map never win: they load as the lowest T).
+template <int LO, int HI, typename T>
+struct Tile {
+    static constexpr int TH = 32, TW = 128, SEG = 8;
+    static constexpr int WIN = LO + HI + 1;
+    static constexpr int IH = TH + LO + HI;
+    static constexpr int NV = SEG + LO + HI;            // inputs feeding one 8-output segment
+    static constexpr int VEC = 16 / (int)sizeof(T);     // elements per 128-bit shared-memory access
+    static constexpr int NVV = (NV + VEC - 1) / VEC * VEC;
+    static constexpr int IW_MIN = TW - SEG + NVV;       // last segment's vector reads stay in the row
+    // row strides == 4 words (mod 32 banks): 128-bit accesses with lanes on rows are conflict-free
+    static constexpr int IWP = (IW_MIN - VEC + 8 * VEC - 1) / (8 * VEC) * (8 * VEC) + VEC;
+    static constexpr int TWP = TW + VEC;
+    static constexpr int P = WIN >= 16 ? 16 : WIN >= 8 ? 8 : WIN >= 4 ? 4 : WIN >= 2 ? 2 : 1;
+    static constexpr size_t smem_bytes = sizeof(T) * (size_t)IH * (IWP + TWP);
+};
+
+template <typename T> struct Vec128;
+template <> struct Vec128<float> { typedef float4 type; };
+template <> struct Vec128<unsigned long long> { typedef ulonglong2 type; };
+
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+
+// v[0..NV) -> v[i] = max(v[i..i+WIN-1]) for i < SEG   (log-step doubling, fully unrolled)
+template <int LO, int HI, typename T>
+__device__ __forceinline__ void window_reduce(T (&v)[Tile<LO, HI, T>::NVV]) {
+    using C = Tile<LO, HI, T>;
+#pragma unroll
+    for (int s = 1; s < C::P; s *= 2) {
+#pragma unroll
+        for (int i = 0; i + s < C::NV; ++i) v[i] = tmax(v[i], v[i + s]);
+    }
+#pragma unroll
+    for (int i = 0; i < C::SEG; ++i) v[i] = tmax(v[i], v[i + C::WIN - C::P]);
+}
+
+// Runs the tile at output origin (ty0, tx0).  load(y, x) returns the value at map position (y, x)
+// (any integer position; must return the lowest T outside the map).  emit(y, x, centre, wmax) is
+// called once per in-map output pixel.
+template <int LO, int HI, typename T, typename Load, typename Emit>
+__device__ __forceinline__ void run_tile(T* smem, int ty0, int tx0, int H, int W, Load load, Emit emit) {
+    using C = Tile<LO, HI, T>;
+    using V = typename Vec128<T>::type;
+    T* in = smem;                                   // [IH][IWP]
+    T* rm = smem + (size_t)C::IH * C::IWP;          // [IH][TWP] row maxima
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < C::IH * C::IWP; i += nt) {
+        int r = i / C::IWP, c = i - r * C::IWP;
+        in[i] = load(ty0 - LO + r, tx0 - LO + c);
+    }
+    __syncthreads();
+    // row pass: a warp owns a segment column, lanes run over rows
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    constexpr int NSEG = C::TW / C::SEG;
+    constexpr int RB = (C::IH + 31) / 32;
+    for (int task = warp; task < NSEG * RB; task += nwarp) {
+        int seg = task % NSEG, r = (task / NSEG) * 32 + lane;
+        if (r < C::IH) {
+            T v[C::NVV];
+            const V* src = reinterpret_cast<const V*>(in + (size_t)r * C::IWP + seg * C::SEG);
+#pragma unroll
+            for (int j = 0; j < C::NVV / C::VEC; ++j) *reinterpret_cast<V*>(&v[j * C::VEC]) = src[j];
+            window_reduce<LO, HI, T>(v);
+            V* dst = reinterpret_cast<V*>(rm + (size_t)r * C::TWP + seg * C::SEG);
+#pragma unroll
+            for (int j = 0; j < C::SEG / C::VEC; ++j) dst[j] = *reinterpret_cast<const V*>(&v[j * C::VEC]);
+        }
+    }
+    __syncthreads();
+    // column pass: lanes run over columns, a thread owns 8 consecutive output rows
+    constexpr int NRS = C::TH / C::SEG;
+    for (int task = tid; task < C::TW * NRS; task += nt) {
+        int c = task % C::TW, rs = task / C::TW;
+        T v[C::NVV];
+#pragma unroll
+        for (int j = 0; j < C::NVV; ++j) v[j] = j < C::NV ? rm[(size_t)(rs * C::SEG + j) * C::TWP + c] : T(0);
+        window_reduce<LO, HI, T>(v);
+        int x = tx0 + c;
+#pragma unroll
+        for (int j = 0; j < C::SEG; ++j) {
+            int y = ty0 + rs * C::SEG + j;
+            if (y < H && x < W) emit(y, x, in[(size_t)(rs * C::SEG + j + LO) * C::IWP + c + LO], v[j]);
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------ windowed NMS
+struct NmsWs {
+    int32_t* count;   // [B] candidates per image
+    int32_t* flags;   // [B] bit0 = candidate overflow
+    u64* keys;        // [B][cap]
+    float* alive;     // [B][H*W]  (greedy only)
+    size_t cap;
+};
+
+template <int LO, int HI>
+__global__ void __launch_bounds__(256) windowed_nms_kernel(MapView mv, NmsWs ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    using C = Tile<LO, HI, float>;
+    const int b = blockIdx.z, ty0 = blockIdx.y * C::TH, tx0 = blockIdx.x * C::TW;
+    auto load = [&](int y, int x) -> float {
+        return (y >= 0 && y < mv.H && x >= 0 && x < mv.W) ? mv.masked(b, y, x) : kNegInf;
+    };
+    auto emit = [&](int y, int x, float c, float m) {
+        if (c > 0.0f && c == m) {                    // survivor of apply_nms with a positive score
+            unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+            if (slot < ws.cap) ws.keys[(size_t)b * ws.cap + slot] = make_key(c, (uint32_t)(y * mv.W + x));
+            else atomicOr(ws.flags + b, 1);
+        }
+    };
+    run_tile<LO, HI, float>(smem, ty0, tx0, mv.H, mv.W, load, emit);
+}
+
+// any window size: one thread per pixel, window read through L1/L2 (small maps, unusual sizes)
+__global__ void windowed_nms_generic_kernel(MapView mv, NmsWs ws, int lo, int hi) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= mv.W) return;
+    float c = mv.masked(b, y, x);
+    if (!(c > 0.0f)) return;
+    int y0 = max(y - lo, 0), y1 = min(y + hi, mv.H - 1), x0 = max(x - lo, 0), x1 = min(x + hi, mv.W - 1);
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx)
+            if (mv.masked(b, yy, xx) > c) return;
+    unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+    if (slot < ws.cap) ws.keys[(size_t)b * ws.cap + slot] = make_key(c, (uint32_t)(y * mv.W + x));
+    else atomicOr(ws.flags + b, 1);
+}
+
+// ------------------------------------------------------------------------------------------ greedy NMS
+// One CTA per image.  Rounds: every alive pixel whose 64-bit key is the maximum of the alive keys in
+// its (2r+1)^2 window is kept; everything alive within r of a kept pixel dies; repeat until nothing
+// is alive.  Equal to the sequential walk of nms_fast.
+__global__ void greedy_init_kernel(MapView mv, NmsWs ws, float thr) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= mv.W) return;
+    float s = mv.masked(b, y, x);
+    ws.alive[(size_t)b * mv.H * mv.W + (size_t)y * mv.W + x] = (s >= thr) ? s : kNegInf;
+}
+
+template <int R>
+__device__ __forceinline__ void greedy_round_tiles(u64* smem, float* alive, int H, int W, u64* kept, int cap,
+                                                   int* n_kept, int* n_new, int* sh_new, int sh_cap) {
+    using C = Tile<R, R, u64>;
+    const int tiles_x = (W + C::TW - 1) / C::TW, tiles_y = (H + C::TH - 1) / C::TH;
+    for (int t = 0; t < tiles_x * tiles_y; ++t) {
+        int ty0 = (t / tiles_x) * C::TH, tx0 = (t % tiles_x) * C::TW;
+        auto load = [&](int y, int x) -> u64 {
+            if (y < 0 || y >= H || x < 0 || x >= W) return 0ull;
+            float a = alive[(size_t)y * W + x];
+            return a > kNegInf ? make_key(a, (uint32_t)(y * W + x)) : 0ull;
+        };
+        auto emit = [&](int y, int x, u64 c, u64 m) {
+            if (c != 0ull && c == m) {
+                int slot = atomicAdd(n_kept, 1);
+                if (slot < cap) kept[slot] = c;
+                int s2 = atomicAdd(n_new, 1);
+                if (s2 < sh_cap) sh_new[s2] = y * W + x;
+            }
+        };
+        run_tile<R, R, u64>(smem, ty0, tx0, H, W, load, emit);
+    }
+}
+
+__device__ __forceinline__ void greedy_round_generic(float* alive, int H, int W, int r, u64* kept, int cap,
+                                                     int* n_kept, int* n_new, int* sh_new, int sh_cap) {
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        float a = alive[i];
+        if (!(a > kNegInf)) continue;
+        int y = i / W, x = i - y * W;
+        u64 me = make_key(a, (uint32_t)i);
+        int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+        bool top = true;
+        for (int yy = y0; yy <= y1 && top; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) {
+                float q = alive[(size_t)yy * W + xx];
+                if (q > kNegInf && make_key(q, (uint32_t)(yy * W + xx)) > me) { top = false; break; }
+            }
+        if (top) {
+            int slot = atomicAdd(n_kept, 1);
+            if (slot < cap) kept[slot] = me;
+            int s2 = atomicAdd(n_new, 1);
+            if (s2 < sh_cap) sh_new[s2] = i;
+        }
+    }
+}
+
+constexpr int kGreedyNewCap = 4096;   // kept pixels per round staged in shared memory
+
+template <int R>   // R > 0: tile engine with radius R;  R == 0: generic radius r
+__global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W, int r) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int n_kept, n_new;
+    __shared__ int sh_new[kGreedyNewCap];
+    const int b = blockIdx.x;
+    float* alive = ws.alive + (size_t)b * H * W;
+    u64* kept = ws.keys + (size_t)b * ws.cap;
+    if (threadIdx.x == 0) n_kept = 0;
+    __syncthreads();
+    for (int round = 0; round < (1 << 20); ++round) {      // bounded: every round keeps >= 1 pixel or ends
+        if (threadIdx.x == 0) n_new = 0;
+        __syncthreads();
+        if constexpr (R > 0) greedy_round_tiles<(R > 0 ? R : 1)>(reinterpret_cast<u64*>(smem_raw), alive, H, W, kept, (int)ws.cap,
+                                                       &n_kept, &n_new, sh_new, kGreedyNewCap);
+        else greedy_round_generic(alive, H, W, r, kept, (int)ws.cap, &n_kept, &n_new, sh_new, kGreedyNewCap);
+        __syncthreads();
+        const int nn = n_new;
+        if (nn == 0) break;
+        if (nn <= kGreedyNewCap) {
+            // suppression: one warp clears the (2r+1)^2 box of each newly kept pixel
+            for (int i = threadIdx.x >> 5; i < nn; i += blockDim.x >> 5) {
+                int p = sh_new[i], y = p / W, x = p - y * W;
+                int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+                for (int yy = y0; yy <= y1; ++yy)
+                    for (int xx = x0 + (threadIdx.x & 31); xx <= x1; xx += 32) alive[(size_t)yy * W + xx] = kNegInf;
+            }
+        } else {
+            // more new keeps than the staging list holds (tiny radius): re-derive them from the
+            // kept list itself -- the last nn entries were appended this round.
+            const int total = min(n_kept, (int)ws.cap);
+            for (int i = total - nn + (threadIdx.x >> 5); i < total; i += blockDim.x >> 5) {
+                if (i < 0) continue;
+                int p = (int)key_raster(kept[i]), y = p / W, x = p - y * W;
+                int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+                for (int yy = y0; yy <= y1; ++yy)
+                    for (int xx = x0 + (threadIdx.x & 31); xx <= x1; xx += 32) alive[(size_t)yy * W + xx] = kNegInf;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ws.count[b] = min(n_kept, (int)ws.cap);
+        if (n_kept > (int)ws.cap) ws.flags[b] |= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ select + sort
+// k-th largest value of field(key) among keys satisfying pred -- MSB-first byte-wise radix select.
+template <typename Pred, typename Field>
+__device__ u64 radix_select(const u64* keys, int n, int kth, int nbytes, Pred pred, Field field, unsigned* hist,
+                            unsigned* xch) {
+    u64 prefix = 0, mask = 0;
+    int remaining = kth;
+    for (int shift = (nbytes - 1) * 8; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 k = keys[i];
+            if (pred(k)) {
+                u64 f = field(k);
+                if ((f & mask) == prefix) atomicAdd(&hist[(unsigned)(f >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, bin = 255;
+            for (; bin > 0; --bin) {
+                int h = (int)hist[bin];
+                if (cum + h >= remaining) break;
+                cum += h;
+            }
+            xch[0] = (unsigned)bin;
+            xch[1] = (unsigned)(remaining - cum);
+        }
+        __syncthreads();
+        prefix |= (u64)xch[0] << shift;
+        mask |= (u64)255 << shift;
+        remaining = (int)xch[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// soft_argmax_points (test_utils.py:170-215): ps x ps window of the border-masked map zero-padded by
+// ps/2 -> normalise by the sum (+1e-6) -> negatives to 1e-6 -> log -> spatial soft-argmax
+// (torchgeometry: e = exp(l - max l), centroid = sum(pos * e) / (sum e + 1e-6)) -> minus ps/2.
+__global__ void subpixel_kernel(MapView mv, const int32_t* __restrict__ xy, const int32_t* __restrict__ count,
+                                int n_max, int ps, float* __restrict__ dxdy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= n_max || (count && i >= count[b])) return;
+    const int x = xy[((size_t)b * n_max + i) * 2], y = xy[((size_t)b * n_max + i) * 2 + 1];
+    const int half = ps / 2, H = mv.H, W = mv.W;
+    auto at = [&](int j) -> float {
+        int yy = y - half + j / ps, xx = x - half + j % ps;
+        return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? mv.masked(b, yy, xx) : 0.f;
+    };
+    float sum = 0.f;
+    for (int j = 0; j < ps * ps; ++j) sum += at(j);
+    const float inv = sum + 1e-6f;
+    float mx = kNegInf;
+    for (int j = 0; j < ps * ps; ++j) {
+        float qv = at(j) / inv;
+        if (qv < 0.f) qv = 1e-6f;
+        mx = fmaxf(mx, logf(qv));
+    }
+    float se = 0.f, sx = 0.f, sy = 0.f;
+    for (int j = 0; j < ps * ps; ++j) {
+        float qv = at(j) / inv;
+        if (qv < 0.f) qv = 1e-6f;
+        float e = expf(logf(qv) - mx);
+        se += e;
+        sx += e * (float)(j % ps);
+        sy += e * (float)(j / ps);
+    }
+    const float w = 1.0f / (se + 1e-6f);
+    dxdy[((size_t)b * n_max + i) * 2] = sx * w - (float)half;
+    dxdy[((size_t)b * n_max + i) * 2 + 1] = sy * w - (float)half;
+}
+
+// dense apply_nms output: out = score * (score == window max)
+template <int LO, int HI>
+__global__ void __launch_bounds__(256) nms_map_kernel(MapView mv, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using C = Tile<LO, HI, float>;
+    const int b = blockIdx.z;
+    auto load = [&](int y, int x) -> float {
+        return (y >= 0 && y < mv.H && x >= 0 && x < mv.W) ? mv.masked(b, y, x) : kNegInf;
+    };
+    auto emit = [&](int y, int x, float c, float m) {
+        out[((size_t)b * mv.H + y) * mv.W + x] = (c == m) ? c : c * 0.0f;
+    };
+    run_tile<LO, HI, float>(reinterpret_cast<float*>(smem_raw), blockIdx.y * C::TH, blockIdx.x * C::TW, mv.H, mv.W, load, emit);
+}
+__global__ void nms_map_generic_kernel(MapView mv, float* __restrict__ out, int lo, int hi) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= mv.W) return;
+    float c = mv.masked(b, y, x), m = c;
+    int y0 = max(y - lo, 0), y1 = min(y + hi, mv.H - 1), x0 = max(x - lo, 0), x1 = min(x + hi, mv.W - 1);
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) m = fmaxf(m, mv.masked(b, yy, xx));
+    out[((size_t)b * mv.H + y) * mv.W + x] = (c == m) ? c : c * 0.0f;
+}
+
+// mode 0: windowed (find_index_higher_scores semantics), mode 1: greedy (plain top-k by key)
+__global__ void __launch_bounds__(1024) select_sort_kernel(NmsWs ws, int mode, int k, int npow2, int H, int W,
+                                                           int32_t* xy, float* out_score, int32_t* out_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* sel = reinterpret_cast<u64*>(smem_raw);          // [npow2]
+    __shared__ unsigned hist[256];
+    __shared__ unsigned xch[2];
+    __shared__ int n_sel, c_gt, c_eq;
+    const int b = blockIdx.x;
+    const u64* keys = ws.keys + (size_t)b * ws.cap;
+    const int n = min(ws.count[b], (int)ws.cap);
+    int32_t* oxy = xy + (size_t)b * k * 2;
+    float* osc = out_score + (size_t)b * k;
+
+    if (mode == 0 && n == 0) {
+        // all-zero NMS map: threshold 0.0 selects the first k raster pixels (test_utils.py:85-93)
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            oxy[2 * i] = i % W;
+            oxy[2 * i + 1] = i / W;
+            osc[i] = 0.0f;
+        }
+        if (threadIdx.x == 0) out_count[b] = k;
+        return;
+    }
+    if (threadIdx.x == 0) { n_sel = 0; c_gt = 0; c_eq = 0; }
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) sel[i] = 0ull;
+    __syncthreads();
+
+    auto all = [](u64) { return true; };
+    if (n <= k) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sel[i] = keys[i];
+        if (threadIdx.x == 0) n_sel = n;
+    } else if (mode == 1) {
+        u64 kth = radix_select(keys, n, k, 8, all, [](u64 q) { return q; }, hist, xch);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 q = keys[i];
+            if (q >= kth) sel[atomicAdd(&n_sel, 1)] = q;      // keys are unique -> exactly k
+        }
+    } else {
+        // t = k-th largest score; keep score >= t, and if ties at t overflow k keep the k
+        // raster-first of them (even over higher scores) -- quirk (i) of find_index_higher_scores
+        u64 t = radix_select(keys, n, k, 4, all, [](u64 q) { return q >> 32; }, hist, xch);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 s = keys[i] >> 32;
+            if (s > t) atomicAdd(&c_gt, 1);
+            else if (s == t) atomicAdd(&c_eq, 1);
+        }
+        __syncthreads();
+        u64 low = 0;
+        if (c_gt + c_eq > k)
+            low = radix_select(keys, n, k, 4, [t](u64 q) { return (q >> 32) >= t; },
+                               [](u64 q) { return q & 0xFFFFFFFFull; }, hist, xch);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 q = keys[i];
+            if ((q >> 32) >= t && (q & 0xFFFFFFFFull) >= low) sel[atomicAdd(&n_sel, 1)] = q;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int size = 2; size <= npow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < npow2 / 2; i += blockDim.x) {
+                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                bool desc = (lo & size) == 0;
+                u64 a = sel[lo], c = sel[hi];
+                if ((a < c) == desc) { sel[lo] = c; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int m = min(n_sel, k);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        u64 q = sel[i];
+        int p = (int)key_raster(q), y = p / W, x = p - y * W;
+        oxy[2 * i] = x;
+        oxy[2 * i + 1] = y;
+        osc[i] = key_score(q);
+    }
+    if (threadIdx.x == 0) out_count[b] = m;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static size_t nms_ws_layout(int B, int H, int W, NmsWs* ws, void* base) {
+    size_t off = 0;
+    char* p = static_cast<char*>(base);
+    size_t cap = (size_t)H * W;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_count = take(sizeof(int32_t) * B), o_flags = take(sizeof(int32_t) * B);
+    size_t o_keys = take(sizeof(u64) * cap * B), o_alive = take(sizeof(float) * cap * B);
+    if (ws) {
+        ws->count = reinterpret_cast<int32_t*>(p + o_count);
+        ws->flags = reinterpret_cast<int32_t*>(p + o_flags);
+        ws->keys = reinterpret_cast<u64*>(p + o_keys);
+        ws->alive = reinterpret_cast<float*>(p + o_alive);
+        ws->cap = cap;
+    }
+    return off;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <int LO, int HI>
+static int launch_windowed(const MapView& mv, const NmsWs& ws, int B, cudaStream_t st) {
+    using C = Tile<LO, HI, float>;
+    size_t smem = C::smem_bytes;
+    BALF_CUDA_OK(cudaFuncSetAttribute(windowed_nms_kernel<LO, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(mv.W, C::TW), cdiv(mv.H, C::TH), B);
+    windowed_nms_kernel<LO, HI><<<grid, 256, smem, st>>>(mv, ws);
+    BALF_COUNT_LAUNCH(1);
+    return 0;
+}
+
+template <int R>
+static int launch_greedy(const NmsWs& ws, int B, int H, int W, int r, cudaStream_t st) {
+    size_t smem = R > 0 ? Tile<(R > 0 ? R : 1), (R > 0 ? R : 1), u64>::smem_bytes : 0;
+    if (smem > 48 * 1024)
+        BALF_CUDA_OK(cudaFuncSetAttribute(greedy_nms_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    greedy_nms_kernel<R><<<B, 256, smem, st>>>(ws, H, W, r);
+    BALF_COUNT_LAUNCH(1);
+    return 0;
+}
+
+static int check_common(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W, int border,
+                        int k, const void* xy, const void* sc, const void* cnt, void* wsp, size_t wsb) {
+    BALF_REQUIRE(score && xy && sc && cnt && wsp, "null pointer argument");
+    BALF_REQUIRE(B > 0 && H > 0 && W > 0 && k > 0, "B, H, W, k must be positive (B=%d H=%d W=%d k=%d)", B, H, W, k);
+    BALF_REQUIRE(top >= 0 && left >= 0 && top + H <= Hs && left + W <= Ws, "crop [%d+%d, %d+%d] exceeds map %dx%d",
+                 top, H, left, W, Hs, Ws);
+    BALF_REQUIRE(border >= 0, "border must be >= 0");
+    BALF_REQUIRE(k <= 16384, "k = %d exceeds the supported maximum of 16384", k);
+    BALF_REQUIRE((size_t)H * W < 0x7FFFFFFFull, "map too large");
+    BALF_REQUIRE(wsb >= nms_ws_layout(B, H, W, nullptr, nullptr), "workspace too small: %zu < %zu", wsb,
+                 nms_ws_layout(B, H, W, nullptr, nullptr));
+    return 0;
+}
+
+static int run_select(const NmsWs& ws, int mode, int B, int H, int W, int k, int32_t* xy, float* sc, int32_t* cnt,
+                      cudaStream_t st) {
+    int np2 = next_pow2(k < 2 ? 2 : k);
+    size_t smem = sizeof(u64) * (size_t)np2;
+    if (smem > 48 * 1024)
+        BALF_CUDA_OK(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_sort_kernel<<<B, 1024, smem, st>>>(ws, mode, k, np2, H, W, xy, sc, cnt);
+    BALF_COUNT_LAUNCH(1);
+    BALF_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace balf
+
+using namespace balf;
+
+extern "C" size_t balf_nms_workspace_bytes(int B, int H, int W, int k) {
+    (void)k;
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return nms_ws_layout(B, H, W, nullptr, nullptr);
+}
+
+extern "C" int balf_windowed_nms_topk(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                                      int border, int nms_size, int k, int32_t* xy, float* out_score,
+                                      int32_t* count, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int e = check_common(score, B, Hs, Ws, top, left, H, W, border, k, xy, out_score, count, workspace, workspace_bytes)) return e;
+    BALF_REQUIRE(nms_size >= 1, "nms_size must be >= 1");
+    BALF_REQUIRE((long long)H * W >= k, "score map has fewer than k = %d elements (the reference raises IndexError)", k);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    NmsWs ws;
+    nms_ws_layout(B, H, W, &ws, workspace);
+    MapView mv{score, Hs, Ws, top, left, H, W, border};
+    BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
+    const int lo = nms_size / 2, hi = (nms_size - 1) / 2;
+    int e = 0;
+    if (nms_size == 15) e = launch_windowed<7, 7>(mv, ws, B, st);
+    else if (nms_size == 31) e = launch_windowed<15, 15>(mv, ws, B, st);
+    else {
+        dim3 grid(cdiv(W, 128), H, B);
+        windowed_nms_generic_kernel<<<grid, 128, 0, st>>>(mv, ws, lo, hi);
+        BALF_COUNT_LAUNCH(1);
+    }
+    if (e) return e;
+    BALF_LAUNCH_OK();
+    return run_select(ws, 0, B, H, W, k, xy, out_score, count, st);
+}
+
+extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                                    int border, float thr, int radius, int k, int subpixel_ps, int32_t* xy,
+                                    float* out_score, float* dxdy, int32_t* count, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (int e = check_common(score, B, Hs, Ws, top, left, H, W, border, k, xy, out_score, count, workspace, workspace_bytes)) return e;
+    BALF_REQUIRE(radius >= 0, "radius must be >= 0");
+    BALF_REQUIRE(subpixel_ps >= 0 && subpixel_ps <= 15, "sub-pixel patch size must be in [0, 15]");
+    BALF_REQUIRE(subpixel_ps == 0 || dxdy != nullptr, "dxdy must be given when sub-pixel refinement is on");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    NmsWs ws;
+    nms_ws_layout(B, H, W, &ws, workspace);
+    MapView mv{score, Hs, Ws, top, left, H, W, border};
+    BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
+    {
+        dim3 grid(cdiv(W, 128), H, B);
+        greedy_init_kernel<<<grid, 128, 0, st>>>(mv, ws, thr);
+        BALF_COUNT_LAUNCH(1);
+        BALF_LAUNCH_OK();
+    }
+    int e = radius == 15 ? launch_greedy<15>(ws, B, H, W, radius, st) : launch_greedy<0>(ws, B, H, W, radius, st);
+    if (e) return e;
+    BALF_LAUNCH_OK();
+    if (int e2 = run_select(ws, 1, B, H, W, k, xy, out_score, count, st)) return e2;
+    if (subpixel_ps > 0) {
+        dim3 grid(cdiv(k, 128), B);
+        subpixel_kernel<<<grid, 128, 0, st>>>(mv, xy, count, k, subpixel_ps, dxdy);
+        BALF_COUNT_LAUNCH(1);
+        BALF_LAUNCH_OK();
+    }
+    return 0;
+}
+
+extern "C" int balf_subpixel_refine(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                                    int border, const int32_t* xy, int n, int ps, float* dxdy, void* stream) {
+    BALF_REQUIRE(score && xy && dxdy, "null pointer argument");
+    BALF_REQUIRE(B > 0 && n >= 0 && ps >= 1 && ps <= 15, "bad sub-pixel arguments (n=%d ps=%d)", n, ps);
+    BALF_REQUIRE(top >= 0 && left >= 0 && top + H <= Hs && left + W <= Ws && border >= 0, "bad crop");
+    if (n == 0) return 0;
+    MapView mv{score, Hs, Ws, top, left, H, W, border};
+    dim3 grid(cdiv(n, 128), B);
+    subpixel_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(mv, xy, nullptr, n, ps, dxdy);
+    BALF_COUNT_LAUNCH(1);
+    BALF_LAUNCH_OK();
+    return 0;
+}
+
+template <int LO, int HI>
+static int launch_nms_map(const MapView& mv, float* out, int B, cudaStream_t st) {
+    using C = Tile<LO, HI, float>;
+    BALF_CUDA_OK(cudaFuncSetAttribute(nms_map_kernel<LO, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
+    dim3 grid(cdiv(mv.W, C::TW), cdiv(mv.H, C::TH), B);
+    nms_map_kernel<LO, HI><<<grid, 256, C::smem_bytes, st>>>(mv, out);
+    BALF_COUNT_LAUNCH(1);
+    return 0;
+}
+
+extern "C" int balf_apply_nms_map(const float* score, int B, int H, int W, int border, int nms_size, float* out,
+                                  void* stream) {
+    BALF_REQUIRE(score && out, "null pointer argument");
+    BALF_REQUIRE(B > 0 && H > 0 && W > 0 && border >= 0 && nms_size >= 1, "bad apply_nms arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MapView mv{score, H, W, 0, 0, H, W, border};
+    int e = 0;
+    if (nms_size == 15) e = launch_nms_map<7, 7>(mv, out, B, st);
+    else if (nms_size == 31) e = launch_nms_map<15, 15>(mv, out, B, st);
+    else {
+        dim3 grid(cdiv(W, 128), H, B);
+        nms_map_generic_kernel<<<grid, 128, 0, st>>>(mv, out, nms_size / 2, (nms_size - 1) / 2);
+        BALF_COUNT_LAUNCH(1);
+    }
+    if (e) return e;
+    BALF_LAUNCH_OK();
+    return 0;
+}

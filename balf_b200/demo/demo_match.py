@@ -1,0 +1,69 @@
+"""Drop-in for the reference's ``demo/demo_match.py`` library functions.
+
+``detect`` (:21-57), ``extract_features`` (:59-95) and ``extract_matches`` (:97-112) keep their
+signatures and return layouts.  Each one is a short chain of C-ABI calls on device-resident
+buffers; the image goes host->device once as uint8 and only the keypoint / descriptor / match
+lists come back (the reference crosses the boundary four times per image with fp32 maps).
+``load_im`` / ``draw_matches`` (PIL / cv2 I/O) are out of scope.
+"""
+import numpy as np
+import torch
+
+from .. import _capi
+from ..utils import test_utils
+
+
+def _detect_device(args, im, detector, device):
+    """image -> device-resident (xy int32 [K,2], dxdy fp32 [K,2] | None, score [K], K)."""
+    dev = torch.device(device)
+    if im.dtype == np.uint8:
+        u8 = torch.from_numpy(np.ascontiguousarray(im)).to(dev, non_blocking=True)[None]
+        x, (top, left) = _capi.preprocess_u8(u8)
+    else:                                   # non-uint8 input: the reference's float64 arithmetic, on the host
+        pad = test_utils.mod_padding_symmetric(test_utils.make_shape_even(im / 255.), factor=64)
+        x = torch.tensor(pad, dtype=torch.float32).permute(2, 0, 1).unsqueeze(0).contiguous().to(dev)
+        _, _, top, left = _capi.pad_geometry(im.shape[0], im.shape[1], 64)
+    with torch.inference_mode():
+        prob = detector(x)["prob"]
+    h, w = im.shape[0], im.shape[1]
+    xy, sc, dxdy, cnt = _capi.greedy_nms_topk(
+        prob, args.num_features, border=args.border_size, thr=args.heatmap_confidence_threshold,
+        radius=args.nms_size, subpixel_ps=args.patch_size if args.sub_pixel else 0, crop=(top, left, h, w))
+    return xy[0], (dxdy[0] if dxdy is not None else None), sc[0], int(cnt[0])
+
+
+def detect(args, im, detector, device):
+    """-> [K,3] float64 rows (x, y, 1.0), score-descending, K <= args.num_features."""
+    xy, dxdy, _, n = _detect_device(args, im, detector, device)
+    if n == 0:
+        return np.zeros([0, 3]), np.zeros([0, 1])          # (sic) the reference returns this pair
+    pts = xy[:n].cpu().numpy().astype(np.float64)
+    if dxdy is not None:
+        pts = pts + dxdy[:n].cpu().numpy().astype(np.float64)
+    if args.order_coord == 'yxsr':
+        pts = pts[:, ::-1]
+    return np.concatenate([pts, np.ones((n, 1))], axis=1)
+
+
+def extract_features(args, im_rgb, im_gray, detector, descriptor, device):
+    """-> (kpts [K,2] float64, descs [K,128] float32)."""
+    kpts_np = detect(args, im_rgb, detector, device)
+    dev = torch.device(device)
+    kp = torch.from_numpy(np.ascontiguousarray(kpts_np[:, 0:2])).float().to(dev)
+    gray = torch.from_numpy(np.ascontiguousarray(im_gray)).to(dev)
+    patches = _capi.extract_patches(gray, kp, float(args.s_mult), 32)
+    if patches.shape[0] == 0:
+        return kpts_np[:, 0:2], np.array([])
+    with torch.inference_mode():
+        descs = descriptor(patches)
+    return kpts_np[:, 0:2], descs.cpu().numpy()
+
+
+def extract_matches(args, im_rgb1, im_gray1, im_rgb2, im_gray2, detector, descriptor, device):
+    """-> (points1 [M,2], points2 [M,2]) of the SMNN(0.99) matches, ordered by the first index."""
+    kpts1, desc1 = extract_features(args, im_rgb1, im_gray1, detector, descriptor, device)
+    kpts2, desc2 = extract_features(args, im_rgb2, im_gray2, detector, descriptor, device)
+    dev = torch.device(device)
+    ids = _capi.match_smnn(torch.from_numpy(desc1).to(dev), torch.from_numpy(desc2).to(dev), 0.99)[1]
+    ids = ids.cpu().numpy()
+    return kpts1[ids[:, 0], :2], kpts2[ids[:, 1], :2]

@@ -1,0 +1,116 @@
+"""B200-native drop-in for the reference's ``balf/model/mlp_ma_decoder.py``.
+
+Same constructor (``MLP_MA_DECODER(model_cfg)`` with the eight keys read at
+mlp_ma_decoder.py:249-256), same ``forward(x) -> {'logits', 'prob'}`` contract
+(mlp_ma_decoder.py:278-285, decoder.py:16-30) and the same 167-entry ``state_dict`` layout
+(SURVEY.md appendix A), but the module owns *parameters only*: the whole forward is one call
+into the C-ABI library (``balf_detector_forward``, include/balf_b200.h), which runs
+hand-written sm_100a kernels.  There is no eager / CPU path -- a CPU tensor raises.
+
+The parameter tree is created leaf by leaf in the reference's construction order, so
+``torch.manual_seed(s); MLP_MA_DECODER(cfg)`` yields bit-identical initial weights to the
+reference (checked in tests/test_boundary.py).
+"""
+import torch
+import torch.nn as nn
+
+from .. import _capi
+from .decoder import DetectorHead
+
+_P = "residual_split_head_multi_axis_gmlp_layer"
+_R = "residual_channel_attention_block"
+
+
+def down_layout(cin, c, cells, block_px, proj=2, gfac=2, bfac=2, red=4):
+    """Leaves of one ``Down`` stage in reference registration order:
+    (dotted name, kind, out_features, in_features).  kind 'ln' has (C,) weight and bias."""
+    g, b = _P + ".grid_gmlp_layer", _P + ".block_gmlp_layer"
+    return (
+        ("conv.0", "linear", c, cin),
+        (_P + ".norm", "ln", c, c),
+        (_P + ".dense1", "linear", c * proj, c),
+        (g + ".norm", "ln", c, c),
+        (g + ".dense1", "linear", c * gfac, c),
+        (g + ".grid_gating_unit.norm", "ln", c, c),
+        (g + ".grid_gating_unit.dense", "linear", cells, cells),
+        (g + ".dense2", "linear", c, c),
+        (b + ".norm", "ln", c, c),
+        (b + ".dense1", "linear", c * bfac, c),
+        (b + ".block_gating_unit.norm", "ln", c, c),
+        (b + ".block_gating_unit.dense", "linear", block_px, block_px),
+        (b + ".dense2", "linear", c, c),
+        (_P + ".dense2", "linear", c, c * proj),
+        (_R + ".norm", "ln", c, c),
+        (_R + ".conv1", "linear", c, c),
+        (_R + ".conv2", "linear", c, c),
+        (_R + ".calayer.excite.0", "linear", c // red, c),
+        (_R + ".calayer.excite.2", "linear", c, c // red),
+        ("conv2", "linear", c, c),
+    )
+
+
+class _Scope(nn.Module):
+    """Pure name-space node of the parameter tree (no behaviour)."""
+
+    def put(self, dotted, leaf):
+        node = self
+        *path, last = dotted.split(".")
+        for name in path:
+            if name not in node._modules:
+                node.add_module(name, _Scope())
+            node = node._modules[name]
+        node.add_module(last, leaf)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter scope only; the forward lives in balf_detector_forward (CUDA)")
+
+
+class Down(_Scope):
+    """One encoder stage (reference: mlp_ma_decoder.py:201-244) -- parameters only."""
+
+    def __init__(self, in_ch, out_ch, grid_size, block_size, grid_gmlp_factor=2, block_gmlp_factor=2,
+                 input_proj_factor=2, channels_reduction=4, downsample=True):
+        super().__init__()
+        self.downsample = downsample
+        self.dims = (in_ch, out_ch)
+        for name, kind, n_out, n_in in down_layout(in_ch, out_ch, grid_size[0] * grid_size[1],
+                                                   block_size[0] * block_size[1], input_proj_factor,
+                                                   grid_gmlp_factor, block_gmlp_factor, channels_reduction):
+            self.put(name, nn.LayerNorm(n_out) if kind == "ln" else nn.Linear(n_in, n_out))
+
+
+class MLP_MA_DECODER(nn.Module):
+    def __init__(self, model_cfg):
+        super().__init__()
+        dims = list(model_cfg["en_embed_dims"])
+        self.arch = dict(
+            dims=dims, grid=tuple(model_cfg["grid_size"]), block=tuple(model_cfg["block_size"]),
+            gfac=model_cfg["grid_gmlp_factor"], bfac=model_cfg["block_gmlp_factor"],
+            proj=model_cfg["input_proj_factor"], red=model_cfg["channels_reduction"], cell=model_cfg["cell_size"])
+        _capi.check_supported_arch(self.arch)
+        for i in range(4):
+            self.add_module("down%d" % (i + 1), Down(
+                dims[i], dims[i + 1], self.arch["grid"], self.arch["block"], self.arch["gfac"], self.arch["bfac"],
+                self.arch["proj"], self.arch["red"], downsample=i < 3))
+        self.detector_head = DetectorHead(input_channel=dims[4], cell_size=self.arch["cell"])
+        self._packed = None          # (key, device weight blob) cache, see _weights()
+        self.precision = "fp32"      # 'fp32' (FFMA, exact-class) or 'tf32' (tcgen05), see DESIGN.md
+
+    # -- weight blob: every floating tensor of the state_dict, concatenated in state_dict order
+    def _weights(self, device):
+        tensors = [t for t in self.state_dict(keep_vars=True).values() if t.is_floating_point()]
+        key = (str(device), self.precision) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._packed is None or self._packed[0] != key:
+            raw = torch.cat([t.detach().reshape(-1).to(device=device, dtype=torch.float32) for t in tensors])
+            self._packed = (key, _capi.detector_pack_weights(raw, self.arch))
+        return self._packed[1]
+
+    def forward(self, x):
+        if self.training:
+            raise RuntimeError("balf_b200 implements the inference path only: call .eval() first")
+        if not x.is_cuda:
+            raise RuntimeError("balf_b200 has no CPU path: move the model and the input to a CUDA device")
+        if x.dim() != 4 or x.shape[1] != self.arch["dims"][0]:
+            raise ValueError("expected input [B, %d, H, W], got %s" % (self.arch["dims"][0], tuple(x.shape)))
+        logits, prob = _capi.detector_forward(x, self._weights(x.device), self.arch, self.precision)
+        return {"logits": logits, "prob": prob}

@@ -1,0 +1,125 @@
+/* balf_b200 -- C-ABI of the B200-native BALF inference hot path (libbalf_b200.so).
+ *
+ * The reference (ericzzj1989/BALF) is pure Python and has no FFI; its drop-in boundary is the
+ * Python call surface listed in SURVEY.md section 8b.  The PyTorch-facing modules under
+ * balf_b200/ keep that surface and forward into the entry points below, one per stage of
+ * demo/demo_match.py::extract_matches.  Each declaration cites the reference code it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host";
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream, never
+ *    allocate, never synchronise (exception: functions documented as "host-synchronous");
+ *  - return 0 on success, <0 for an argument / shape error, >0 = cudaError_t; the message is
+ *    available from balf_last_error() (thread-local);
+ *  - scratch memory is caller-provided: query *_workspace_bytes() first;
+ *  - the library fails loudly: there is no CPU fallback anywhere.
+ */
+#ifndef BALF_B200_H_
+#define BALF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BALF_B200_ABI_VERSION 1
+#define BALF_API __attribute__((visibility("default")))
+
+BALF_API const char* balf_last_error(void);
+BALF_API int balf_abi_version(void);
+/* number of kernels this library has launched since load (bench.py: "gpu_launches") */
+BALF_API unsigned long long balf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * D3  detector architecture + weights
+ *     replaces: balf/model/mlp_ma_decoder.py:246-276 (MLP_MA_DECODER.__init__),
+ *               balf/model/get_model.py:88-90 (load_model)
+ * `raw` is every floating-point tensor of the reference state_dict, flattened and concatenated
+ * in state_dict order (4 x 40 Down tensors, then detector_head.dense.
+ * {weight,bias}, detector_head.norm.{weight,bias,running_mean,running_var}).
+ * balf_detector_pack_weights() lays them out for the kernels (transposes, BatchNorm folding). */
+typedef struct balf_detector_arch {
+    int32_t dims[5];        /* en_embed_dims, e.g. {3,32,64,128,256}                           */
+    int32_t grid_h, grid_w; /* grid_size  (cells per image side; the kernels require 8 x 8)    */
+    int32_t block_h, block_w; /* block_size (pixels per block side; the kernels require 8 x 8) */
+    int32_t grid_factor, block_factor, proj_factor; /* all 2                                   */
+    int32_t reduction;      /* channels_reduction (squeeze-excite), 4                          */
+    int32_t cell;           /* cell_size of the head (8 -> 65 logits)                          */
+} balf_detector_arch;
+
+BALF_API int balf_detector_check_arch(const balf_detector_arch* arch);
+BALF_API int64_t balf_detector_raw_weight_count(const balf_detector_arch* arch);
+BALF_API int64_t balf_detector_packed_weight_count(const balf_detector_arch* arch);
+BALF_API int balf_detector_pack_weights(const balf_detector_arch* arch, const float* raw, float* packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * D0  image -> network input
+ *     replaces: demo/demo_match.py:22-29 + balf/utils/test_utils.py:16-32
+ *               (/255., make_shape_even, mod_padding_symmetric(factor), HWC->CHW)
+ * balf_pad_geometry (host, pure arithmetic): padded size and the offset of the image inside it
+ * (also the un-pad crop origin of demo_match.py:38-43).
+ * balf_preprocess_u8: img [B,H,W,C] uint8 (C = 1 or 3; C = 1 is replicated to 3 planes)
+ *     -> x [B,3,Hp,Wp] fp32 = float(u8)/255.f, zeros in the padding. */
+BALF_API int balf_pad_geometry(int H, int W, int factor, int* Hp, int* Wp, int* top, int* left);
+BALF_API int balf_preprocess_u8(const uint8_t* img, int B, int H, int W, int C, float* x, int Hp, int Wp, int top,
+                       int left, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * D1 + D2  detector forward
+ *     replaces: balf/model/mlp_ma_decoder.py:278-285 (MLP_MA_DECODER.forward: 4 x Down,
+ *               :201-244) and balf/model/decoder.py:16-30 (DetectorHead.forward) with
+ *               balf/utils/tensor_op.py:1-27 (pixel_shuffle) fused in.
+ * x [B,dims[0],Hp,Wp] fp32 NCHW, Hp and Wp multiples of 64.
+ * logits [B,cell^2+1,Hp/8,Wp/8] (may be NULL), prob [B,Hp,Wp].
+ * precision: 0 = fp32 FFMA (bit-level class of the reference's fp32 path),
+ *            1 = TF32 tensor-core operands with fp32 accumulate (tcgen05). */
+BALF_API size_t balf_detector_workspace_bytes(const balf_detector_arch* arch, int B, int Hp, int Wp);
+BALF_API int balf_detector_forward(const balf_detector_arch* arch, const float* packed, const float* x, int B, int Hp,
+                          int Wp, float* logits, float* prob, void* workspace, size_t workspace_bytes,
+                          int precision, void* stream);
+/* stand-alone depth-to-space (balf/utils/tensor_op.py:1-27): in [N,C,H,W] -> out [N,C/r^2,H*r,W*r] */
+BALF_API int balf_pixel_shuffle(const float* in, float* out, int N, int C, int H, int W, int r, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P1-P8  score map -> keypoints.  The score map is the (padded) `prob` of the detector:
+ * score [B, Hs, Ws] with the image occupying rows [top, top+H) and columns [left, left+W)
+ * (un-pad crop, demo_match.py:38-43, fused).  Scores must be >= 0 (softmax probabilities).
+ * Output per image (capacity k): xy int32 [B,k,2] = (x, y) in crop coordinates, score fp32
+ * [B,k], count int32 [B]; rows are ordered score-descending with ties broken by raster index
+ * y*W+x ascending (the canonical tie rule).
+ *
+ * balf_windowed_nms_topk  replaces test_utils.py:34-47 (remove_borders), :50-54 (apply_nms:
+ *     size x size maximum filter, plateau ties all survive), :56-95 (get_point_coordinates /
+ *     find_index_higher_scores: k-th value threshold with the raster-order truncation quirks)
+ *     and the caller's argsort, balf/utils/train_utils.py:446-452.  Requires H*W >= k
+ *     (the reference raises IndexError otherwise).
+ * balf_greedy_nms_topk    replaces test_utils.py:34-47, :97-128 (get_points_direct_from_score_map:
+ *     fp32 threshold `>= thr`), :130-168 (nms_fast: greedy, (2r+1)^2 exclusion box), :170-215
+ *     (sub-pixel soft-argmax over a ps x ps window, ps = 0 disables) and demo_match.py:51-57
+ *     (top-k by score).  dxdy fp32 [B,k,2] (may be NULL when ps = 0) holds the sub-pixel offset
+ *     to ADD to (x, y) (already includes the "- ps/2" of test_utils.py:179). */
+BALF_API size_t balf_nms_workspace_bytes(int B, int H, int W, int k);
+BALF_API int balf_windowed_nms_topk(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                           int border, int nms_size, int k, int32_t* xy, float* out_score, int32_t* count,
+                           void* workspace, size_t workspace_bytes, void* stream);
+BALF_API int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                         int border, float thr, int radius, int k, int subpixel_ps, int32_t* xy,
+                         float* out_score, float* dxdy, int32_t* count, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* stand-alone pieces of the above, for callers that use the reference helpers one by one:
+ * balf_apply_nms_map   test_utils.py:50-54 on a dense map [B,H,W] (border = 0 reproduces apply_nms;
+ *                      border > 0 fuses remove_borders first): out = s * (s == max_filter(s, size)).
+ * balf_subpixel_refine test_utils.py:170-215 for n given integer points per image (xy int32 [B,n,2])
+ *                      -> dxdy fp32 [B,n,2]. */
+BALF_API int balf_apply_nms_map(const float* score, int B, int H, int W, int border, int nms_size, float* out,
+                                void* stream);
+BALF_API int balf_subpixel_refine(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
+                                  int border, const int32_t* xy, int n, int ps, float* dxdy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BALF_B200_H_ */

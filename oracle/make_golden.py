@@ -1,0 +1,199 @@
+"""Generate ``tests/golden/*.npz`` by running the REFERENCE's own Python modules.
+
+TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference, which does not
+exist on the GPU box):   python -m oracle.make_golden
+
+What is pinned by these vectors: detector forward (balf/model), HardNet
+(third_party/hardnet), and every NumPy helper of balf/utils/test_utils.py that the hot path
+touches.  The reference is run unmodified except for two shims, both recorded in the files:
+
+* ``np.argsort`` is forced to ``kind='stable'`` while reference code runs, so that its four
+  unstable sorts become deterministic (tie order = input order).  See oracle/postproc.py.
+* ``torchgeometry`` (un-vendored) is replaced by ``oracle.thirdparty.spatial_soft_argmax2d``
+  and ``kornia`` by an empty stub (only its import is needed by demo_match.detect), so the
+  sub-pixel columns of the ``*_subpix`` arrays are NOT reference-pinned (key
+  ``unpinned_subpixel`` = 1 in the file).
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+import yaml
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _install_shims():
+    from oracle import thirdparty
+
+    class _SoftArgmax:
+        def __init__(self, normalized_coordinates=True):
+            assert not normalized_coordinates
+
+        def __call__(self, patches):                       # [N,1,ps,ps] -> [N,1,2]
+            n, _, ps, _ = patches.shape
+            return torch.from_numpy(thirdparty.spatial_soft_argmax2d(patches.reshape(n, ps, ps))).view(n, 1, 2)
+
+    tgm = types.ModuleType("torchgeometry")
+    tgm.contrib = types.SimpleNamespace(SpatialSoftArgmax2d=_SoftArgmax)
+    sys.modules["torchgeometry"] = tgm
+    kornia = types.ModuleType("kornia")
+    kornia.feature = types.SimpleNamespace()
+    sys.modules["kornia"] = kornia
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))
+
+
+class stable_argsort:
+    def __enter__(self):
+        self._orig = np.argsort
+        np.argsort = lambda a, *x, **k: self._orig(a, *x, **{**k, "kind": "stable"})
+
+    def __exit__(self, *e):
+        np.argsort = self._orig
+
+
+def ref_modules():
+    sys.path.insert(0, REF)
+    _install_shims()
+    warnings.filterwarnings("ignore")
+    from balf.model import get_model
+    from balf.utils import test_utils
+    from third_party.hardnet.hardnet_pytorch import HardNet
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from demo import demo_match
+    finally:
+        os.chdir(cwd)
+    cfg = yaml.safe_load(open(os.path.join(REF, "balf/configs/test.yaml")))
+    return get_model, test_utils, HardNet, demo_match, cfg
+
+
+def weight_digest(sd):
+    """order-independent digest of a state_dict: (sum, sum of squares) in float64."""
+    s = sum(float(v.double().sum()) for v in sd.values())
+    q = sum(float((v.double() ** 2).sum()) for v in sd.values())
+    return np.array([s, q, float(len(sd))])
+
+
+def synth_image_u8(h, w, seed, channels=1):
+    """seeded uint8 image, gray plane replicated to 3 channels."""
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (channels, h, w), generator=g, dtype=torch.uint8)
+    return u8.permute(1, 2, 0).expand(h, w, 3).contiguous().numpy() if channels == 1 else \
+        u8.permute(1, 2, 0).contiguous().numpy()
+
+
+def main():
+    get_model, tu, HardNet, demo_match, cfg = ref_modules()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+
+    # ------------------------------------------------------------------ detector
+    torch.manual_seed(0)
+    det = get_model.load_model(cfg["model"]).eval()
+    sd = det.state_dict()
+    x = torch.rand(1, 3, 128, 192, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        o = det(x)
+    # batch-2 non-square case with a different seed (checks per-image SE pooling / grid cells)
+    x2 = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(77))
+    with torch.inference_mode():
+        o2 = det(x2)
+    xb = torch.rand(1, 3, 512, 640, generator=torch.Generator().manual_seed(1234))
+    with torch.inference_mode():
+        ob = det(xb)
+    pb = ob["prob"][0].numpy()
+    np.savez(os.path.join(OUT, "detector.npz"),
+             weight_digest=weight_digest(sd),
+             first_weight=sd["down1.conv.0.weight"].numpy(),
+             head_bias=sd["detector_head.dense.bias"].numpy(),
+             prob_128x192=o["prob"][0].numpy(), logits_128x192=o["logits"][0].numpy(),
+             prob_b2_64x128=o2["prob"].numpy(), logits_b2_64x128=o2["logits"].numpy(),
+             prob_512x640_sub8=pb[::8, ::8].copy(), prob_512x640_row255=pb[255].copy(),
+             prob_512x640_stats=np.array([pb.astype(np.float64).sum(), pb.min(), pb.max(), pb.mean()]),
+             logits_512x640_stats=np.array([ob["logits"].double().sum().item(), ob["logits"].abs().max().item()]))
+
+    # ------------------------------------------------------------------ post-processing on the reference's own score map
+    score = pb[16:496].copy()                                  # un-pad crop of a 480x640 image (P1)
+    g = {"score_480x640": score, "unpinned_subpixel": np.array(1)}
+    with stable_argsort():
+        rb = tu.remove_borders(score, 15)
+        g["apply_nms15_idx"] = np.flatnonzero(tu.apply_nms(rb, 15)).astype(np.int32)
+        g["apply_nms4_idx"] = np.flatnonzero(tu.apply_nms(rb, 4)).astype(np.int32)
+        nmsmap = tu.apply_nms(rb, 15)
+        for k in (2048, 500, 5000):
+            g["kth_topk%d" % k] = tu.get_point_coordinates(nmsmap, num_points=k)
+        for name, thr in (("thr001", 0.001), ("thr015", 0.015)):
+            g["greedy_" + name] = tu.get_points_direct_from_score_map(rb, thr, 15, False, 4)
+        g["greedy_thr001_r4"] = tu.get_points_direct_from_score_map(rb, 0.001, 4, False, 4)
+        g["greedy_thr001_subpix4"] = tu.get_points_direct_from_score_map(rb, 0.001, 15, True, 4)
+        g["greedy_thr015_subpix5"] = tu.get_points_direct_from_score_map(rb, 0.015, 15, True, 5)
+        ys, xs = np.where(rb >= np.float32(0.001))
+        pts = np.stack([xs, ys, rb[ys, xs]]).astype(np.float64)
+        out, inds = tu.nms_fast(pts, 480, 640, 15)
+        g["nms_fast_out"], g["nms_fast_inds"] = out, inds.astype(np.int64)
+    np.savez(os.path.join(OUT, "postproc_480x640.npz"), **g)
+
+    # ------------------------------------------------------------------ small synthetic maps: ties, plateaus, zeros, edge cases
+    rng = np.random.default_rng(7)
+    small = {}
+    maps = {
+        "rand": rng.random((96, 128), dtype=np.float32),
+        "quant": (rng.integers(0, 12, (96, 128)) / 16.0).astype(np.float32),          # heavy ties + plateaus
+        "sparse": (rng.random((96, 128), dtype=np.float32) * (rng.random((96, 128)) > 0.97)).astype(np.float32),
+        "zeros": np.zeros((96, 128), np.float32),
+        "odd": rng.random((75, 101), dtype=np.float32),
+        "one": np.zeros((64, 64), np.float32),
+    }
+    maps["one"][40, 21] = 0.5
+    with stable_argsort():
+        for name, m in maps.items():
+            small["map_" + name] = m
+            b = 15 if name != "rand" else 4
+            rb = tu.remove_borders(m, b)
+            small["rb_" + name] = np.array(b)
+            for size in (15, 4, 3):
+                small["nms%d_%s" % (size, name)] = np.flatnonzero(tu.apply_nms(rb, size)).astype(np.int32)
+            nm = tu.apply_nms(rb, 15)
+            for k in (1, 50, 2048):
+                small["kth%d_%s" % (k, name)] = tu.find_index_higher_scores(nm, num_points=k).astype(np.int32)
+                small["kthraw%d_%s" % (k, name)] = tu.find_index_higher_scores(rb, num_points=k).astype(np.int32)
+            for r in (15, 4, 1):
+                small["greedy%d_%s" % (r, name)] = tu.get_points_direct_from_score_map(rb, 0.015, r, False, 4)
+    np.savez(os.path.join(OUT, "postproc_small.npz"), **small)
+
+    # ------------------------------------------------------------------ D0: pad geometry + full detect() of the reference on synthetic u8 images
+    d = {}
+    args = types.SimpleNamespace(border_size=15, nms_size=15, num_features=2048, s_mult=60, order_coord="xysr",
+                                 heatmap_confidence_threshold=0.001, sub_pixel=False, patch_size=4)
+    for (h, w, seed) in ((480, 640, 1234), (121, 187, 5), (128, 192, 6)):
+        im = synth_image_u8(h, w, seed)
+        pad = tu.mod_padding_symmetric(tu.make_shape_even(im / 255.0), 64)
+        d["pad_shape_%dx%d" % (h, w)] = np.array(pad.shape)
+        d["pad_sum_%dx%d" % (h, w)] = np.array([pad.astype(np.float32).astype(np.float64).sum()])
+        if h < 480:
+            d["pad_%dx%d" % (h, w)] = pad.astype(np.float32)
+            with stable_argsort():
+                d["detect_%dx%d" % (h, w)] = demo_match.detect(args, im, det, "cpu")
+    np.savez(os.path.join(OUT, "detect.npz"), **d)
+
+    # ------------------------------------------------------------------ HardNet
+    torch.manual_seed(0)
+    hn = HardNet().eval()
+    xh = torch.rand(8, 1, 32, 32, generator=torch.Generator().manual_seed(4321))
+    with torch.inference_mode():
+        oh = hn(xh)
+    np.savez(os.path.join(OUT, "hardnet.npz"), weight_digest=weight_digest(hn.state_dict()),
+             first_weight=hn.state_dict()["features.0.weight"].numpy(), out=oh.numpy())
+    print("golden vectors written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  %-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+"""Parity of the CUDA post-processing (balf_b200/csrc/nms.cu, through the C-ABI) with the oracle.
+Bit-exact on indices and scores; sub-pixel offsets within a stated fp32 tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import postproc, postproc_c
+
+pytestmark = pytest.mark.gpu
+SUBPIX_ATOL = 2e-5      # fp32 exp/log/sum-order differences of the 16..25-tap soft-argmax
+
+
+def capi():
+    import balf_b200._capi as c
+    return c
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def gpu_windowed(score, k, border, size, crop=None):
+    xy, sc, cnt = capi().windowed_nms_topk(torch.as_tensor(score).to(dev()), k, border=border, nms_size=size, crop=crop)
+    xy, sc, cnt = xy.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+    return [np.concatenate([xy[b, :cnt[b]].astype(np.float64), np.ones((cnt[b], 1)), sc[b, :cnt[b], None].astype(np.float64)], 1)
+            for b in range(len(cnt))]
+
+
+def gpu_greedy(score, k, border, thr, r, ps=0, crop=None):
+    xy, sc, dxdy, cnt = capi().greedy_nms_topk(torch.as_tensor(score).to(dev()), k, border=border, thr=thr, radius=r,
+                                               subpixel_ps=ps, crop=crop)
+    xy, sc, cnt = xy.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+    out = []
+    for b in range(len(cnt)):
+        p = xy[b, :cnt[b]].astype(np.float64)
+        if ps:
+            p = p + dxdy[b, :cnt[b]].cpu().numpy().astype(np.float64)
+        out.append(np.concatenate([p, np.ones((cnt[b], 1)), sc[b, :cnt[b], None].astype(np.float64)], 1))
+    return out
+
+
+def oracle_greedy(score, border, thr, r, k, ps=0, fast=True):
+    rb = postproc.remove_borders(score, border)
+    pts = postproc.get_points_direct_from_score_map(rb, thr, r, ps > 0, ps if ps else 4,
+                                                    nms=postproc_c.greedy_nms if fast else postproc.greedy_nms)
+    return pts[np.argsort(-pts[:, 3], kind="stable")][:k] if len(pts) else pts.reshape(0, 4)
+
+
+def test_windowed_golden_map():
+    g = load_golden("postproc_480x640.npz")
+    score = g["score_480x640"]
+    for k in (2048, 500, 5000):
+        want = postproc.windowed_detect(score, 15, 15, k)
+        got = gpu_windowed(score, k, 15, 15)[0]
+        np.testing.assert_array_equal(got, want)
+        ref = g["kth_topk%d" % k]                                # the reference's own raster-ordered rows
+        np.testing.assert_array_equal(got[np.lexsort((got[:, 0], got[:, 1]))], ref)
+
+
+def test_greedy_golden_map():
+    g = load_golden("postproc_480x640.npz")
+    score = g["score_480x640"]
+    for name, thr, r in (("greedy_thr001", 0.001, 15), ("greedy_thr015", 0.015, 15), ("greedy_thr001_r4", 0.001, 4)):
+        got = gpu_greedy(score, 8192, 15, thr, r)[0]
+        want = oracle_greedy(score, 15, thr, r, 8192)
+        np.testing.assert_array_equal(got, want)
+        ref = g[name]
+        canon = lambda p: p[np.lexsort((p[:, 0], p[:, 1], -p[:, 3]))]
+        np.testing.assert_array_equal(canon(got), canon(ref))
+    got = gpu_greedy(score, 2048, 15, 0.001, 15)[0]
+    assert len(got) == 800
+    np.testing.assert_allclose(got[0], [28, 42, 1.0, 0.0226866342], rtol=1e-7)
+
+
+def test_greedy_topk_binds():
+    g = load_golden("postproc_480x640.npz")
+    score = g["score_480x640"]
+    for k in (1, 100, 777):
+        np.testing.assert_array_equal(gpu_greedy(score, k, 15, 0.001, 15)[0], oracle_greedy(score, 15, 0.001, 15, k))
+    k = 300                                                       # r = 4 keeps thousands: radix-select path
+    np.testing.assert_array_equal(gpu_greedy(score, k, 15, 0.001, 4)[0], oracle_greedy(score, 15, 0.001, 4, k))
+
+
+def test_subpixel():
+    g = load_golden("postproc_480x640.npz")
+    score = g["score_480x640"]
+    for thr, ps in ((0.001, 4), (0.015, 5), (0.001, 3)):
+        got = gpu_greedy(score, 2048, 15, thr, 15, ps)[0]
+        want = oracle_greedy(score, 15, thr, 15, 2048, ps)
+        np.testing.assert_array_equal(got[:, 2:], want[:, 2:])
+        np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=0, atol=SUBPIX_ATOL)
+        assert np.abs(got[:, :2] - np.round(want[:, :2])).max() > 0.01     # offsets are really applied
+
+
+@pytest.mark.parametrize("name", ["rand", "quant", "sparse", "zeros", "odd", "one"])
+def test_small_maps(name):
+    g = load_golden("postproc_small.npz")
+    m = g["map_" + name]
+    b = int(g["rb_" + name])
+    for size in (15, 4, 3, 31, 1):
+        for k in (1, 50, 2048):
+            want = postproc.windowed_detect(m, b, size, k)
+            got = gpu_windowed(m, k, b, size)[0]
+            np.testing.assert_array_equal(got, want, err_msg="windowed %s size %d k %d" % (name, size, k))
+    for r in (15, 4, 1, 0, 7):
+        for thr in (0.015, 0.0, 0.5):
+            want = oracle_greedy(m, b, thr, r, 4096)
+            got = gpu_greedy(m, 4096, b, thr, r)[0]
+            np.testing.assert_array_equal(got, want, err_msg="greedy %s r %d thr %g" % (name, r, thr))
+
+
+def test_dense_apply_nms_and_helpers():
+    from balf_b200.utils import test_utils as tu
+    g = load_golden("postproc_small.npz")
+    for name in ("rand", "quant", "odd"):
+        m = g["map_" + name]
+        for size in (15, 4, 3, 31):
+            np.testing.assert_array_equal(tu.apply_nms(m, size), postproc.apply_nms(m, size))
+        rb = tu.remove_borders(m, 5)
+        np.testing.assert_array_equal(rb, postproc.remove_borders(m, 5))
+        nm = postproc.apply_nms(rb, 15)
+        for k in (1, 50, 2048):
+            np.testing.assert_array_equal(tu.find_index_higher_scores(nm, k), postproc.find_index_higher_scores(nm, k))
+            np.testing.assert_array_equal(tu.get_point_coordinates(nm, num_points=k), postproc.get_point_coordinates(nm, num_points=k))
+        got = tu.get_points_direct_from_score_map(rb, 0.015, 4, False, 4)
+        want = postproc.get_points_direct_from_score_map(rb, 0.015, 4, False, 4)
+        np.testing.assert_array_equal(got, want)
+        got = tu.get_points_direct_from_score_map(rb, 0.015, 4, True, 5)
+        want = postproc.get_points_direct_from_score_map(rb, 0.015, 4, True, 5)
+        np.testing.assert_allclose(got, want, rtol=0, atol=SUBPIX_ATOL)
+        ys, xs = np.nonzero(rb >= np.float32(0.3))
+        pts = np.stack([xs, ys, rb[ys, xs]]).astype(np.float64)
+        out, inds = tu.nms_fast(pts, m.shape[0], m.shape[1], 4)
+        keep = postproc.greedy_nms(xs, ys, pts[2], m.shape[0], m.shape[1], 4)
+        np.testing.assert_array_equal(inds, keep)
+        np.testing.assert_array_equal(out, pts[:, keep])
+    with pytest.raises(IndexError):
+        tu.find_index_higher_scores(np.ones((4, 4), np.float32), 17)
+    assert tu.get_points_direct_from_score_map(np.zeros((64, 64), np.float32), 0.015, 15, True, 5).shape == (0, 4)
+    assert tu.make_shape_even(np.zeros((5, 7, 3))).shape == (6, 8, 3)
+    assert tu.mod_padding_symmetric(np.zeros((480, 640, 3))).shape == (512, 640, 3)
+    assert tu.mod_padding_symmetric(np.zeros((900, 1200, 3))).shape == (960, 1216, 3)
+    assert tu.mod_padding_symmetric(np.zeros((128, 192, 3))).shape == (128, 192, 3)
+
+
+def test_errors():
+    c = capi()
+    s = torch.rand(1, 16, 16, device=dev())
+    with pytest.raises(ValueError):
+        c.windowed_nms_topk(s, 257)                              # fewer than k elements (IndexError in the reference)
+    with pytest.raises(ValueError):
+        c.windowed_nms_topk(s, 4, crop=(8, 8, 16, 16))           # crop outside the map
+    with pytest.raises(ValueError):
+        c.greedy_nms_topk(s, 20000)                              # k above the supported maximum
+    with pytest.raises(RuntimeError):
+        c.windowed_nms_topk(s.cpu(), 4)                          # no CPU path
+
+
+def test_batched_crop_full_size():
+    """config-2 shape: batch of padded 512x640 maps, crop 480x640 at row 16; every image against the
+    C oracle, plus size-independent properties."""
+    B = 6
+    rng = np.random.default_rng(11)
+    maps = (rng.random((B, 512, 640), dtype=np.float32) * 0.02 + 0.005).astype(np.float32)
+    maps[1] = np.round(maps[1] * 2000) / 2000                    # heavy ties / plateaus
+    maps[2, 16:496] *= (rng.random((480, 640)) > 0.999)         # almost empty: fewer than k survivors
+    maps[3] = 0                                                  # all-zero map quirk
+    crop = (16, 0, 480, 640)
+    got_w = gpu_windowed(maps, 2048, 15, 15, crop)
+    got_g = gpu_greedy(maps, 2048, 15, 0.001, 15, 0, crop)
+    for b in range(B):
+        s = maps[b, 16:496]
+        want = postproc.windowed_detect(s, 15, 15, 2048)
+        np.testing.assert_array_equal(got_w[b], want, err_msg="windowed image %d" % b)
+        want = oracle_greedy(s, 15, 0.001, 15, 2048)
+        np.testing.assert_array_equal(got_g[b], want, err_msg="greedy image %d" % b)
+        p = got_g[b]
+        if len(p) > 1:
+            assert np.all(np.diff(p[:, 3]) <= 0)                 # sorted by score
+            d = np.maximum(np.abs(p[:, None, 0] - p[None, :, 0]), np.abs(p[:, None, 1] - p[None, :, 1]))
+            np.fill_diagonal(d, 1e9)
+            assert d.min() > 15                                  # exclusion box respected
+            assert p[:, 0].min() >= 15 and p[:, 0].max() < 640 - 15 and p[:, 1].min() >= 15 and p[:, 1].max() < 480 - 15
+    assert len(got_w[3]) == 2048 and np.all(got_w[3][:, 3] == 0)  # zero-map quirk: first k raster pixels
+    assert len(got_g[3]) == 0
+
+
+def test_large_map_1200x900_topk_binds():
+    rng = np.random.default_rng(5)
+    s = (rng.random((900, 1200), dtype=np.float32) * 0.02).astype(np.float32)
+    got = gpu_greedy(s, 2048, 15, 0.001, 15)[0]
+    want = oracle_greedy(s, 15, 0.001, 15, 2048)
+    assert len(want) == 2048
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(gpu_windowed(s, 8192, 15, 15)[0], postproc.windowed_detect(s, 15, 15, 8192))
