@@ -83,7 +83,7 @@ def test_rejects_bad_input(det_gpu, detector):
 def test_weight_reload_invalidates_cache(det_gpu):
     x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(9))
     _, p0 = run(det_gpu, x)
-    sd = det_gpu.state_dict()
+    sd = {k: v.detach().clone() for k, v in det_gpu.state_dict().items()}
     sd2 = {k: (v * 1.5 if k == "detector_head.dense.weight" else v) for k, v in sd.items()}
     det_gpu.load_state_dict(sd2)
     _, p1 = run(det_gpu, x)
