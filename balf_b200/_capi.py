@@ -56,6 +56,25 @@ _greedy_nms = _sig("balf_greedy_nms_topk", c_int, _P, *([c_int] * 8), c_float, c
                    c_size_t, _P)
 
 
+_prof_enable = _sig("balf_profile_enable", c_int, c_int)
+_prof_report = _sig("balf_profile_report", c_int, ctypes.c_char_p, c_size_t, c_int)
+
+
+def profile_enable(on):
+    _ok(_prof_enable(1 if on else 0))
+
+
+def profile_report(reset=True):
+    """host-synchronous -> {kernel name: (launches, total_ms)} since the last reset."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _ok(_prof_report(buf, len(buf), 1 if reset else 0))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out
+
+
 def declared_symbols():
     """Every function the public header declares (tests check that the library exports them all)."""
     return re.findall(r"\b(balf_[a-z0-9_]+)\s*\(", open(HEADER_PATH).read())

@@ -3,7 +3,9 @@
 #include "common.cuh"
 #include "../../include/balf_b200.h"
 
+#include <string.h>
 #include <string>
+#include <vector>
 
 namespace balf {
 
@@ -20,6 +22,24 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 const char* last_error() { return g_error.c_str(); }
+
+// ---- per-kernel event timing
+bool g_prof_on = false;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(const char* name, cudaStream_t st) {
+    ProfRec r{name, prof_event(), prof_event()};
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 
 // D0: demo_match.py:22-29.  float(u8) / 255.f is bit-identical to the reference's float64
 // division followed by the fp32 cast for all 256 inputs.
@@ -61,6 +81,42 @@ extern "C" const char* balf_last_error(void) { return last_error(); }
 extern "C" int balf_abi_version(void) { return BALF_B200_ABI_VERSION; }
 extern "C" unsigned long long balf_launch_count(void) { return g_launches; }
 
+extern "C" int balf_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+
+// host-synchronous: waits for every recorded event, then writes "name count total_ms\n" lines
+extern "C" int balf_profile_report(char* buf, size_t cap, int reset) {
+    struct Agg { const char* name; long n; double ms; };
+    std::vector<Agg> agg;
+    for (ProfRec& r : g_prof) {
+        BALF_CUDA_OK(cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        BALF_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        Agg* a = nullptr;
+        for (Agg& q : agg) if (q.name == r.name || std::string(q.name) == r.name) { a = &q; break; }
+        if (!a) { agg.push_back(Agg{r.name, 0, 0.0}); a = &agg.back(); }
+        a->n += 1;
+        a->ms += ms;
+    }
+    std::string out;
+    char line[256];
+    for (Agg& q : agg) {
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", q.name, q.n, q.ms);
+        out += line;
+    }
+    if (buf && cap) {
+        BALF_REQUIRE(out.size() + 1 <= cap, "profile report needs %zu bytes", out.size() + 1);
+        memcpy(buf, out.c_str(), out.size() + 1);
+    }
+    if (reset) {
+        for (ProfRec& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+        g_prof.clear();
+    }
+    return (int)out.size() + 1 > 0 ? 0 : 0;
+}
+
 extern "C" int balf_pad_geometry(int H, int W, int factor, int* Hp, int* Wp, int* top, int* left) {
     BALF_REQUIRE(H > 0 && W > 0 && factor > 0, "H, W, factor must be positive");
     // make_shape_even (test_utils.py:16-21) then mod_padding_symmetric (test_utils.py:23-32)
@@ -81,7 +137,10 @@ extern "C" int balf_preprocess_u8(const uint8_t* img, int B, int H, int W, int C
     BALF_REQUIRE(B > 0 && H > 0 && W > 0 && top >= 0 && left >= 0 && top + H <= Hp && left + W <= Wp,
                  "image %dx%d at (%d,%d) does not fit the padded size %dx%d", H, W, top, left, Hp, Wp);
     dim3 grid(cdiv(Wp, 128), Hp, B);
-    preprocess_u8_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(img, H, W, C, x, Hp, Wp, top, left);
+    {
+        ProfScope p("preprocess_u8", static_cast<cudaStream_t>(stream));
+        preprocess_u8_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(img, H, W, C, x, Hp, Wp, top, left);
+    }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
     return 0;

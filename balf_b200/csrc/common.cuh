@@ -33,6 +33,18 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 extern unsigned long long g_launches;
 #define BALF_COUNT_LAUNCH(n) (::balf::g_launches += (n))
 
+// per-kernel CUDA-event timing (bench.py's roofline leg): off by default; when on, every launch
+// wrapped in a ProfScope is bracketed by two events on the launching stream.
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+extern bool g_prof_on;
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(const char* name, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin(name, s); }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
 constexpr float kNegInf = -__builtin_huge_valf();
 
 __device__ __forceinline__ float warp_sum(float v) {

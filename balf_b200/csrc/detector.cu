@@ -529,11 +529,23 @@ static int run_level(const float* xin, bool nchw, const DownW& w, int Bc, int h,
     if (int e = set_smem(branch_kernel<CIN, C, MB, 1>, BranchSmem<CIN, C, MB>::bytes)) return e;
     if (int e = set_smem(merge_kernel<CIN, C, MM>, MergeSmem<CIN, C, MM>::bytes)) return e;
     dim3 gb(npix / MB, Bc);
-    branch_kernel<CIN, C, MB, 0><<<gb, NT, BranchSmem<CIN, C, MB>::bytes, st>>>(xin, nchw, w, g, ws.u);
-    branch_kernel<CIN, C, MB, 1><<<gb, NT, BranchSmem<CIN, C, MB>::bytes, st>>>(xin, nchw, w, g, ws.v);
+    {
+        ProfScope p(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
+        branch_kernel<CIN, C, MB, 0><<<gb, NT, BranchSmem<CIN, C, MB>::bytes, st>>>(xin, nchw, w, g, ws.u);
+    }
+    {
+        ProfScope p(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
+        branch_kernel<CIN, C, MB, 1><<<gb, NT, BranchSmem<CIN, C, MB>::bytes, st>>>(xin, nchw, w, g, ws.v);
+    }
     dim3 gm(npix / MM, Bc);
-    merge_kernel<CIN, C, MM><<<gm, NT, MergeSmem<CIN, C, MM>::bytes, st>>>(xin, nchw, w, g, ws.u, ws.v, ws.r, ws.q, ws.partial);
-    se_kernel<C><<<Bc, C, 0, st>>>(ws.partial, npix / MM, 1.0f / (float)npix, w, ws.scale);
+    {
+        ProfScope p(C == 32 ? "det_merge_c32" : C == 64 ? "det_merge_c64" : C == 128 ? "det_merge_c128" : "det_merge_c256", st);
+        merge_kernel<CIN, C, MM><<<gm, NT, MergeSmem<CIN, C, MM>::bytes, st>>>(xin, nchw, w, g, ws.u, ws.v, ws.r, ws.q, ws.partial);
+    }
+    {
+        ProfScope p("det_se", st);
+        se_kernel<C><<<Bc, C, 0, st>>>(ws.partial, npix / MM, 1.0f / (float)npix, w, ws.scale);
+    }
     BALF_COUNT_LAUNCH(4);
     BALF_LAUNCH_OK();
     *merge_tiles = npix / MM;
@@ -543,7 +555,10 @@ static int run_level(const float* xin, bool nchw, const DownW& w, int Bc, int h,
 template <int C>
 static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st) {
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
-    pool_kernel<C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+    {
+        ProfScope p("det_pool", st);
+        pool_kernel<C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+    }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
     return 0;
@@ -651,9 +666,12 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
         if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st)) return e;
         if (int e = run_level<128, 256, 64, 32>(ws.pooled[2], false, w.down[3], Bc, hc, wc, ws, st, &tiles)) return e;
         dim3 gh(hc * wc / 32, Bc);
-        head_kernel<256, 32><<<gh, NT, HeadSmem<256, 32>::bytes, st>>>(
-            ws.r, ws.q, ws.scale, w.down[3], w.head, hc, wc, a.cell,
-            logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp);
+        {
+            ProfScope p("det_head", st);
+            head_kernel<256, 32><<<gh, NT, HeadSmem<256, 32>::bytes, st>>>(
+                ws.r, ws.q, ws.scale, w.down[3], w.head, hc, wc, a.cell,
+                logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp);
+        }
         BALF_COUNT_LAUNCH(1);
         BALF_LAUNCH_OK();
     }

@@ -490,7 +490,10 @@ static int launch_windowed(const MapView& mv, const NmsWs& ws, int B, cudaStream
     size_t smem = C::smem_bytes;
     BALF_CUDA_OK(cudaFuncSetAttribute(windowed_nms_kernel<LO, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(mv.W, C::TW), cdiv(mv.H, C::TH), B);
-    windowed_nms_kernel<LO, HI><<<grid, 256, smem, st>>>(mv, ws);
+    {
+        ProfScope p("nms_windowed", st);
+        windowed_nms_kernel<LO, HI><<<grid, 256, smem, st>>>(mv, ws);
+    }
     BALF_COUNT_LAUNCH(1);
     return 0;
 }
@@ -500,7 +503,10 @@ static int launch_greedy(const NmsWs& ws, int B, int H, int W, int r, cudaStream
     size_t smem = R > 0 ? Tile<(R > 0 ? R : 1), (R > 0 ? R : 1), u64>::smem_bytes : 0;
     if (smem > 48 * 1024)
         BALF_CUDA_OK(cudaFuncSetAttribute(greedy_nms_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    greedy_nms_kernel<R><<<B, 256, smem, st>>>(ws, H, W, r);
+    {
+        ProfScope p("nms_greedy_rounds", st);
+        greedy_nms_kernel<R><<<B, 256, smem, st>>>(ws, H, W, r);
+    }
     BALF_COUNT_LAUNCH(1);
     return 0;
 }
@@ -525,7 +531,10 @@ static int run_select(const NmsWs& ws, int mode, int B, int H, int W, int k, int
     size_t smem = sizeof(u64) * (size_t)np2;
     if (smem > 48 * 1024)
         BALF_CUDA_OK(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    select_sort_kernel<<<B, 1024, smem, st>>>(ws, mode, k, np2, H, W, xy, sc, cnt);
+    {
+        ProfScope p("nms_select_sort", st);
+        select_sort_kernel<<<B, 1024, smem, st>>>(ws, mode, k, np2, H, W, xy, sc, cnt);
+    }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
     return 0;
@@ -558,6 +567,7 @@ extern "C" int balf_windowed_nms_topk(const float* score, int B, int Hs, int Ws,
     else if (nms_size == 31) e = launch_windowed<15, 15>(mv, ws, B, st);
     else {
         dim3 grid(cdiv(W, 128), H, B);
+        ProfScope p("nms_windowed_generic", st);
         windowed_nms_generic_kernel<<<grid, 128, 0, st>>>(mv, ws, lo, hi);
         BALF_COUNT_LAUNCH(1);
     }
@@ -581,6 +591,7 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
     BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
     {
         dim3 grid(cdiv(W, 128), H, B);
+        ProfScope p("nms_greedy_init", st);
         greedy_init_kernel<<<grid, 128, 0, st>>>(mv, ws, thr);
         BALF_COUNT_LAUNCH(1);
         BALF_LAUNCH_OK();
@@ -591,6 +602,7 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
     if (int e2 = run_select(ws, 1, B, H, W, k, xy, out_score, count, st)) return e2;
     if (subpixel_ps > 0) {
         dim3 grid(cdiv(k, 128), B);
+        ProfScope p("nms_subpixel", st);
         subpixel_kernel<<<grid, 128, 0, st>>>(mv, xy, count, k, subpixel_ps, dxdy);
         BALF_COUNT_LAUNCH(1);
         BALF_LAUNCH_OK();

@@ -32,6 +32,35 @@ def _detect_device(args, im, detector, device):
     return xy[0], (dxdy[0] if dxdy is not None else None), sc[0], int(cnt[0])
 
 
+def detect_batch_device(args, u8, detector, nms="greedy"):
+    """Batched device-resident detect: u8 [B,H,W,C] uint8 CUDA -> (xy int32 [B,K,2], score fp32
+    [B,K], dxdy fp32 [B,K,2] | None, count int32 [B]) on the device.  ``nms`` selects the demo
+    path ('greedy': demo_match.py:44-57) or the validation path ('windowed':
+    balf/utils/train_utils.py:446-452)."""
+    B, h, w, _ = u8.shape
+    x, (top, left) = _capi.preprocess_u8(u8)
+    with torch.inference_mode():
+        prob = detector(x)["prob"]
+    if nms == "windowed":
+        xy, sc, cnt = _capi.windowed_nms_topk(prob, args.num_features, border=args.border_size,
+                                              nms_size=args.nms_size, crop=(top, left, h, w))
+        return xy, sc, None, cnt
+    return _capi.greedy_nms_topk(
+        prob, args.num_features, border=args.border_size, thr=args.heatmap_confidence_threshold,
+        radius=args.nms_size, subpixel_ps=args.patch_size if args.sub_pixel else 0, crop=(top, left, h, w))
+
+
+def detect_batch(args, images, detector, device, nms="greedy"):
+    """Batched ``detect`` with HOST buffers in and out: images [B,H,W,C] uint8 (NumPy array or
+    torch CPU tensor, pinned for an asynchronous copy) -> (xy int32 [B,K,2], score fp32 [B,K],
+    count int32 [B]) NumPy arrays; rows beyond count[b] are zero.  One H2D copy of the uint8
+    batch, one D2H copy of the keypoint records."""
+    dev = torch.device(device)
+    t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+    xy, sc, dxdy, cnt = detect_batch_device(args, t.to(dev, non_blocking=True), detector, nms)
+    return xy.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+
+
 def detect(args, im, detector, device):
     """-> [K,3] float64 rows (x, y, 1.0), score-descending, K <= args.num_features."""
     xy, dxdy, _, n = _detect_device(args, im, detector, device)

@@ -1,0 +1,62 @@
+"""Image-batch sharding across the GPUs of one box.
+
+The reference is strictly batch-1 and single-device (demo/demo_match.py:29); every image is
+independent, so the batch is partitioned contiguously over ranks, each rank runs the whole
+pipeline locally, and ONE collective gathers the fixed-size keypoint records.  There is no
+exchange inside the network (the squeeze-excite mean and the grid gate are per image).
+
+``torch.distributed`` is the plumbing: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous [start, end) of rank's share of n_items (the first n_items % world ranks get one more)."""
+    base, extra = divmod(int(n_items), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def pack_records(xy, score, count):
+    """xy int32 [B,K,2], score fp32 [B,K], count int32 [B] -> one int32 buffer [B, 3K+1]."""
+    b, k, _ = xy.shape
+    buf = torch.empty(b, 3 * k + 1, dtype=torch.int32, device=xy.device)
+    buf[:, :2 * k] = xy.reshape(b, 2 * k)
+    buf[:, 2 * k:3 * k] = score.contiguous().view(torch.int32)
+    buf[:, 3 * k] = count
+    return buf
+
+
+def unpack_records(buf):
+    b, n = buf.shape
+    k = (n - 1) // 3
+    xy = buf[:, :2 * k].reshape(b, k, 2)
+    score = buf[:, 2 * k:3 * k].contiguous().view(torch.float32)
+    return xy, score, buf[:, 3 * k].contiguous()
+
+
+def gather_keypoints(xy, score, count, group=None):
+    """All-gather the per-rank keypoint records (equal local batch on every rank) with a single
+    collective -> (xy [B_total,K,2], score [B_total,K], count [B_total]) in rank order."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return xy, score, count
+    world = dist.get_world_size(group)
+    local = pack_records(xy, score, count)
+    out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return unpack_records(out)
+
+
+def gather_matches(ids, n_matches, group=None):
+    """ids int32 [P,Mmax,2], n_matches int32 [P] (pairs handled by this rank) -> gathered over ranks."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return ids, n_matches
+    world = dist.get_world_size(group)
+    p, m, _ = ids.shape
+    local = torch.empty(p, 2 * m + 1, dtype=torch.int32, device=ids.device)
+    local[:, :2 * m] = ids.reshape(p, 2 * m)
+    local[:, 2 * m] = n_matches
+    out = torch.empty((world * p, 2 * m + 1), dtype=torch.int32, device=ids.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out[:, :2 * m].reshape(world * p, m, 2), out[:, 2 * m].contiguous()

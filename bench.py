@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of record for the BALF inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch 64] [--nms windowed]
+
+One "step" = one pass of the hot path over one batch of synthetic input on every rank:
+uint8 images -> /255 + pad (D0) -> detector forward (D1-D3) -> border mask + NMS + top-2048
+(P1-P8) -> keypoint records (and, for N > 1, one NCCL all-gather of the records).
+Workload = BASELINE.json configs[1]: batch 64 synthetic grayscale 640x480 per GPU.
+
+Prints ONE JSON line (rank 0).  ``value`` = whole-job images/s with the uint8 batch already in
+HBM; ``e2e`` = the same metric through the public host-buffer API (``demo_match.detect_batch``:
+pinned host uint8 in, keypoint records back on the host, copies inside the timed region).
+``--impl reference`` times the reference's CPU algorithm (the oracle restatement; the reference
+itself cannot travel to the GPU box) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+H, W, K_FEATURES = 480, 640, 2048
+METRIC = "images/sec detect+NMS+top-k @640x480"
+FLOP_PER_PADDED_PIXEL = 119496          # SURVEY.md 8d (Linear / matmul MACs x 2 only)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    p.add_argument("--nms", default="windowed", choices=["windowed", "greedy"])
+    p.add_argument("--precision", default=None, help="detector precision (default: the module's)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return ("configs[1]: batch %d synthetic grayscale 640x480 per GPU, detector + %s NMS + top-%d"
+            % (a.batch, a.nms, K_FEATURES))
+
+
+def synth_batch(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (batch, H, W, 1), generator=g, dtype=torch.uint8)
+
+
+def model_cfg():
+    from balf_b200.configs import config
+    from balf_b200.utils import test_utils
+    return test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)["model"]
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_pipeline(a):
+    """-> callable(image index) running the reference algorithm (oracle port) on one image."""
+    from oracle import pipeline, postproc, detector as odet          # the CPU arm only
+    from balf_b200.model import get_model                             # weights only (same init as the reference)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in get_model.load_model(model_cfg()).state_dict().items()}
+    args = pipeline.default_args(sub_pixel=False)
+    imgs = synth_batch(8, 1234).expand(8, H, W, 3).contiguous().numpy()
+
+    def one(i):
+        im = imgs[i % len(imgs)]
+        score = pipeline.score_map(sd, im)
+        if a.nms == "windowed":
+            return postproc.windowed_detect(score, args.border_size, args.nms_size, K_FEATURES)
+        return pipeline.detect_from_score_map(args, score)[0]
+    return one
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one = cpu_pipeline(a)
+    per_step = 2
+    for i in range(a.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        for j in range(per_step):
+            one(s * per_step + j)
+    dt = time.perf_counter() - t0
+    v = a.steps * per_step / dt
+    sample = "%d images per step, batch 1 each (the reference's own batching), %d steps" % (per_step, a.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "nms": a.nms, "k": K_FEATURES},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def cpu_baseline(a):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one = cpu_pipeline(a)
+    one(0)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 32):
+        one(n)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d images of the same workload, batch 1 each, %.1f s" % (n, dt)}
+
+
+# ------------------------------------------------------------------------------------------ roofline
+def level_dims():
+    hp, wp = 512, 640
+    return [(3, 32, hp * wp), (32, 64, hp * wp // 4), (64, 128, hp * wp // 16), (128, 256, hp * wp // 64)]
+
+
+def kernel_work(name, images):
+    """Algorithmic work of ONE step's launches of kernel `name`: ("tensor", flops) or ("hbm", bytes).
+    Detector kernels count Linear / token-mixing MACs x 2 once (recomputation is not credited);
+    SURVEY.md 8d.  NMS counts 4*H*W + 16*K bytes per image."""
+    lv = {32: 0, 64: 1, 128: 2, 256: 3}
+    if name.startswith("det_"):
+        tail = name.rsplit("_c", 1)
+        c = int(tail[1]) if len(tail) == 2 and tail[1].isdigit() else None
+        if c in lv:
+            cin, ch, px = level_dims()[lv[c]]
+            if "branch" in name:                       # half of dense1, branch dense1, token mix, dense2
+                return "tensor", images * px * (2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch)
+            if "merge" in name:                        # conv.0, dense2 (2C->C), conv1, conv2
+                return "tensor", images * px * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch)
+            if "level" in name:                        # a whole Down stage in one kernel
+                return "tensor", images * px * (2 * cin * ch + 24 * ch * ch + 256 * ch)
+        if name == "det_head":
+            return "tensor", images * level_dims()[3][2] * (2 * 256 * 256 + 2 * 256 * 65)
+        return "tensor", 0
+    if name.startswith("nms_windowed"):
+        return "hbm", images * (4 * H * W)
+    if name == "nms_select_sort":
+        return "hbm", images * 16 * K_FEATURES
+    if name == "preprocess_u8":
+        return "hbm", images * (H * W + 12 * 512 * 640)
+    return "hbm", 0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor": p["bf16_tflops_sustained"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def roofline_of(name, launches, total_ms, steps, images, pk, traffic=None):
+    kind, work = kernel_work(name, images)
+    per_launch_ms = total_ms / max(launches, 1)
+    work_per_launch = work * steps / max(launches, 1)
+    if kind == "tensor":
+        achieved = work_per_launch / (per_launch_ms * 1e-3) / 1e12
+        unit = "TFLOP/s"
+    else:
+        achieved = work_per_launch / (per_launch_ms * 1e-3) / 1e9
+        unit = "GB/s"
+    return {"kernel": name, "bound": kind, "achieved": achieved, "peak": pk[kind], "unit": unit,
+            "frac": achieved / pk[kind], "traffic": traffic, "launch_ms": per_launch_ms,
+            "launches_per_step": launches / steps, "peak_source": pk["src"]}
+
+
+# ------------------------------------------------------------------------------------------ main arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import balf_b200._capi as capi
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.model import get_model
+    from balf_b200.sharding import gather_keypoints
+
+    torch.manual_seed(0)
+    det = get_model.load_model(model_cfg()).eval().to(dev)
+    if a.precision:
+        det.precision = a.precision
+    args = config.default_test_args(sub_pixel=False, num_features=K_FEATURES)
+    host = synth_batch(a.batch, 1234 + rank).pin_memory()
+    u8 = host.to(dev)
+
+    def step_device():
+        xy, sc, _, cnt = demo_match.detect_batch_device(args, u8, det, a.nms)
+        if world > 1:
+            return gather_keypoints(xy, sc, cnt)
+        return xy, sc, cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    capi.profile_enable(True)
+    capi.profile_report(reset=True)
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count() - l0
+    prof = capi.profile_report(reset=True)
+    capi.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the host-buffer API
+    def step_host():
+        xy, sc, cnt = demo_match.detect_batch(args, host, det, dev, a.nms)
+        return xy, sc, cnt
+    for _ in range(2):
+        res = step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = step_host()
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) * 1e3
+    d2h = sum(int(r.nbytes) for r in res)
+
+    t = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    images = a.batch * world
+    pk = peaks()
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    kernels = {k: {"launches_per_step": v[0] / a.steps, "ms_per_step": v[1] / a.steps,
+                   "share": v[1] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    roof = roofline_of(top[0], top[1][0], top[1][1], a.steps, a.batch, pk)
+    nms_name = "nms_windowed" if a.nms == "windowed" else "nms_greedy_rounds"
+    roof_nms = roofline_of(nms_name, prof[nms_name][0], prof[nms_name][1], a.steps, a.batch, pk) if nms_name in prof else None
+    det_ms = sum(v[1] for k, v in prof.items() if k.startswith("det_")) / a.steps
+    line = {
+        "metric": METRIC, "value": images * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": det.precision, "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "nms": a.nms, "k": K_FEATURES,
+                   "padded": "512x640", "weights": "random-init torch.manual_seed(0)",
+                   "l2": "no explicit flush: each step streams >2 GB of activations per GPU, far above the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": images * a.steps / (t_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "roofline_nms": roof_nms,
+        "detector": {"ms_per_step": det_ms, "tflops": a.batch * 512 * 640 * FLOP_PER_PADDED_PIXEL / (det_ms * 1e-3) / 1e12
+                     if det_ms else None},
+        "kernels": kernels,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,14 @@ BALF_API int balf_abi_version(void);
 /* number of kernels this library has launched since load (bench.py: "gpu_launches") */
 BALF_API unsigned long long balf_launch_count(void);
 
+/* Per-kernel timing for the roofline report (bench.py): while enabled, every kernel launch of the
+ * library is bracketed by two CUDA events on the launching stream.  balf_profile_report is
+ * host-synchronous: it waits for the events and writes one "name launches total_ms" line per
+ * kernel name into `buf` (host).  No reference counterpart (the reference has no profiler hooks,
+ * SURVEY.md section 5). */
+BALF_API int balf_profile_enable(int on);
+BALF_API int balf_profile_report(char* buf, size_t cap, int reset);
+
 /* ------------------------------------------------------------------------------------------
  * D3  detector architecture + weights
  *     replaces: balf/model/mlp_ma_decoder.py:246-276 (MLP_MA_DECODER.__init__),

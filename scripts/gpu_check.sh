@@ -1,0 +1,20 @@
+#!/bin/bash
+# Run on the B200 box through gpurun: GPU parity tests, bench of record, ncu launch list,
+# one full ncu capture of the dominant kernel.  Outputs land in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/smi.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+tail -c 3000 gpurun_out/bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
+cat gpurun_out/bench_ref.json
+if [ "${NCU:-1}" = "1" ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-branch_kernel}" -s 8 -c 3 \
+    -f -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out
+fi

@@ -1,0 +1,95 @@
+"""Turn gpurun_out/{launches.csv, prof.ncu-rep, bench.json} into committed summaries under profiles/.
+
+    python scripts/summarize_profiles.py <tag>      # e.g. r01a -> profiles/r01a_*.{md,csv,json}
+"""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+KEYS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "smsp__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg")
+
+
+def launches(tag):
+    path = os.path.join(OUT, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = [l for l in open(path) if l.startswith('"')]
+    agg = OrderedDict()
+    for r in csv.DictReader(io.StringIO("".join(rows))):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = r["Kernel Name"].split("(")[0]
+        full = r["Kernel Name"]
+        if "<" in full and "balf::" in full:
+            name = full.split("(")[0]
+        ns = float(r["Metric Value"].replace(",", ""))
+        if r.get("Metric Unit") == "us":
+            ns *= 1e3
+        elif r.get("Metric Unit") == "ms":
+            ns *= 1e6
+        a = agg.setdefault(name, [0, 0.0, r["Grid Size"], r["Block Size"]])
+        a[0] += 1
+        a[1] += ns
+    total = sum(a[1] for a in agg.values())
+    with open(os.path.join(PROF, tag + "_launches.md"), "w") as f:
+        f.write("# %s -- ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n" % tag)
+        f.write("| kernel | launches | total us | share | grid | block |\n|---|---:|---:|---:|---|---|\n")
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| `%s` | %d | %.1f | %.1f%% | %s | %s |\n" % (name[:110], a[0], a[1] / 1e3, 100 * a[1] / total, a[2], a[3]))
+    print("wrote", tag + "_launches.md")
+
+
+def full(tag):
+    rep = os.path.join(OUT, "prof.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        print("no rows in report")
+        return
+    head, units = rows[0], rows[1]
+    with open(os.path.join(PROF, tag + "_ncu_full.md"), "w") as f:
+        f.write("# %s -- `ncu --set full --clock-control none` of the dominant kernel (one row per captured launch)\n\n" % tag)
+        for r in rows[2:]:
+            d = dict(zip(head, r))
+            f.write("## %s  grid %s block %s\n\n| metric | value | unit |\n|---|---:|---|\n" % (
+                d.get("Kernel Name", "?")[:120], d.get("Grid Size", "?"), d.get("Block Size", "?")))
+            for i, h in enumerate(head):
+                if any(h.startswith(k) for k in KEYS):
+                    f.write("| %s | %s | %s |\n" % (h, r[i], units[i]))
+            f.write("\n")
+    print("wrote", tag + "_ncu_full.md")
+
+
+def bench(tag):
+    for name in ("bench.json", "bench_ref.json"):
+        p = os.path.join(OUT, name)
+        if os.path.exists(p):
+            txt = [l for l in open(p).read().splitlines() if l.startswith("{")]
+            if txt:
+                json.dump(json.loads(txt[-1]), open(os.path.join(PROF, tag + "_" + name), "w"), indent=1)
+                print("wrote", tag + "_" + name)
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    os.makedirs(PROF, exist_ok=True)
+    launches(tag)
+    full(tag)
+    bench(tag)
