@@ -261,3 +261,94 @@ def subpixel_refine(score, xy, ps, border=0, crop=None):
         _ok(_subpixel(_ptr(score), B, Hs, Ws, top, left, H, W, int(border), _ptr(xy), n, int(ps), _ptr(dxdy),
                       _stream(score.device)))
     return dxdy
+
+
+# ------------------------------------------------------------------------------------------ patches / HardNet / matching
+_patch_level = _sig("balf_patch_pyramid_level", c_int, c_int, c_int, c_float, c_int)
+_patch_ws = _sig("balf_patches_workspace_bytes", c_size_t, c_int, c_int, c_int)
+_patches = _sig("balf_extract_patches_u8", c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P, c_size_t, _P)
+_hn_raw = _sig("balf_hardnet_raw_weight_count", ctypes.c_int64)
+_hn_packed = _sig("balf_hardnet_packed_weight_count", ctypes.c_int64)
+_hn_pack = _sig("balf_hardnet_pack_weights", c_int, _P, _P, _P)
+_hn_ws = _sig("balf_hardnet_workspace_bytes", c_size_t, c_int)
+_hn_fwd = _sig("balf_hardnet_forward", c_int, _P, _P, c_int, _P, _P, c_size_t, _P)
+_match_ws = _sig("balf_match_workspace_bytes", c_size_t, c_int, c_int)
+_match = _sig("balf_match_smnn", c_int, _P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_size_t, _P)
+
+
+def patch_pyramid_level(h, w, s_mult, ps=32):
+    return int(_patch_level(int(h), int(w), float(s_mult), int(ps)))
+
+
+def extract_patches_batch(gray, kpts, count, s_mult, ps=32):
+    """gray [B,H,W] uint8 CUDA, kpts fp32 [B,K,2] (x, y), count int32 [B] or None -> patches fp32 [B,K,ps,ps]
+    (rows beyond count[b] are zero)."""
+    _need_cuda(gray, "the gray image batch")
+    if gray.dtype != torch.uint8:
+        raise ValueError("gray images must be uint8 (the /255 is fused into the sampling kernels)")
+    gray, kpts = gray.contiguous(), kpts.contiguous().float()
+    B, H, W = gray.shape
+    K = kpts.shape[1]
+    patches = torch.zeros(B, K, ps, ps, dtype=torch.float32, device=gray.device)
+    if K == 0:
+        return patches
+    nbytes = _patch_ws(B, H, W)
+    ws = _workspace(gray.device, nbytes)
+    with torch.cuda.device(gray.device):
+        _ok(_patches(_ptr(gray), B, H, W, _ptr(kpts), _ptr(count), K, float(s_mult), int(ps), _ptr(patches), _ptr(ws),
+                     nbytes, _stream(gray.device)))
+    return patches
+
+
+def extract_patches(gray, kpts, s_mult, ps=32):
+    """gray [H,W] uint8 CUDA, kpts fp32 [K,2] -> patches [K,1,ps,ps]  (demo_match.py:62-69)."""
+    out = extract_patches_batch(gray[None], kpts[None], None, s_mult, ps)
+    return out[0].unsqueeze(1)
+
+
+def hardnet_pack_weights(raw):
+    _need_cuda(raw, "the weight blob")
+    if raw.numel() != _hn_raw() or raw.dtype != torch.float32:
+        raise ValueError("HardNet weight blob has %d floats, expected %d" % (raw.numel(), _hn_raw()))
+    raw = raw.contiguous()
+    packed = torch.empty(_hn_packed(), dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        _ok(_hn_pack(_ptr(raw), _ptr(packed), _stream(raw.device)))
+    return packed
+
+
+def hardnet_forward(patches, packed):
+    """patches fp32 [N,1,32,32] CUDA -> descriptors fp32 [N,128]."""
+    _need_cuda(patches, "the patches")
+    patches = patches.contiguous().float()
+    n = patches.shape[0]
+    desc = torch.empty(n, 128, dtype=torch.float32, device=patches.device)
+    if n == 0:
+        return desc
+    nbytes = _hn_ws(n)
+    ws = _workspace(patches.device, nbytes)
+    with torch.cuda.device(patches.device):
+        _ok(_hn_fwd(_ptr(packed), _ptr(patches), n, _ptr(desc), _ptr(ws), nbytes, _stream(patches.device)))
+    return desc
+
+
+def match_smnn(d1, d2, th=0.99, want_dm=False):
+    """d1 [n1,128], d2 [n2,128] CUDA -> (dists fp32 [M,1], ids int64 [M,2]) like kornia.feature.match_smnn
+    (ids ascending in the first index).  want_dm=True also returns the fp32 distance matrix used."""
+    _need_cuda(d1, "the descriptors")
+    d1, d2 = d1.contiguous().float(), d2.contiguous().float()
+    n1, n2 = d1.shape[0], d2.shape[0]
+    dev = d1.device
+    ids = torch.zeros(max(n1, 1), 2, dtype=torch.int32, device=dev)
+    dist = torch.zeros(max(n1, 1), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    dm = torch.empty(n1, n2, dtype=torch.float32, device=dev) if want_dm else None
+    nbytes = _match_ws(n1, n2)
+    ws = _workspace(dev, nbytes)
+    dim = d1.shape[1] if d1.dim() == 2 and n1 else 128
+    with torch.cuda.device(dev):
+        _ok(_match(_ptr(d1), n1, _ptr(d2), n2, int(dim), float(th), _ptr(ids), _ptr(dist), _ptr(cnt), _ptr(dm), _ptr(ws),
+                   nbytes, _stream(dev)))
+    m = int(cnt[0])
+    out = (dist[:m].reshape(m, 1), ids[:m].long())
+    return out + (dm,) if want_dm else out

@@ -127,6 +127,48 @@ BALF_API int balf_apply_nms_map(const float* score, int B, int H, int W, int bor
 BALF_API int balf_subpixel_refine(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
                                   int border, const int32_t* xy, int n, int ps, float* dxdy, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * F1  keypoints -> descriptor patches
+ *     replaces: demo/demo_match.py:62-69 (kornia laf_from_center_scale_ori with scale s_mult and angle
+ *               0, then extract_patches_from_pyramid(gray / 255., lafs, PS)) -- kornia 0.7.4 is not
+ *               vendored by the reference: PARITY UNPINNED (oracle/thirdparty.py restates it).
+ * gray [B,H,W] uint8, kpts fp32 [B,K,2] = (x, y) in pixels, count int32 [B] (NULL: K valid rows per
+ * image) -> patches fp32 [B,K,PS,PS]; rows beyond count[b] are left untouched.
+ * balf_patch_pyramid_level (host): the pyramid level every keypoint samples (1 for 60 / 32). */
+BALF_API int balf_patch_pyramid_level(int H, int W, float s_mult, int PS);
+BALF_API size_t balf_patches_workspace_bytes(int B, int H, int W);
+BALF_API int balf_extract_patches_u8(const uint8_t* gray, int B, int H, int W, const float* kpts, const int32_t* count,
+                                     int K, float s_mult, int PS, float* patches, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * H1  HardNet descriptor
+ *     replaces: third_party/hardnet/hardnet_pytorch.py:29-72 (HardNet.forward: input_norm, 7 conv +
+ *               BatchNorm(affine=False, eval) (+ ReLU), L2Norm) and the 1000-patch chunk loop of
+ *               demo/demo_match.py:71-93.
+ * `raw` = every floating tensor of the HardNet state_dict concatenated in state_dict order
+ * (features.{0,3,6,9,12,15,19}.weight each followed by its BatchNorm running_mean, running_var).
+ * patches fp32 [N,1,32,32] -> desc fp32 [N,128]. */
+BALF_API int64_t balf_hardnet_raw_weight_count(void);
+BALF_API int64_t balf_hardnet_packed_weight_count(void);
+BALF_API int balf_hardnet_pack_weights(const float* raw, float* packed, void* stream);
+BALF_API size_t balf_hardnet_workspace_bytes(int n_patches);
+BALF_API int balf_hardnet_forward(const float* packed, const float* patches, int n_patches, float* desc, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * M1  SMNN matching
+ *     replaces: demo/demo_match.py:104-108 (kornia match_smnn(desc1, desc2, 0.99)) -- kornia 0.7.4 is
+ *               not vendored by the reference: PARITY UNPINNED (oracle/thirdparty.py restates it).
+ * d1 fp32 [n1,dim], d2 fp32 [n2,dim], dim = 128 -> ids int32 [<=n1,2] = (index in d1, index in d2)
+ * ascending in the first index, dist fp32 [<=n1] = max of the two Lowe ratios, count int32 [1].
+ * dm_out (may be NULL) receives the fp32 distance matrix [n1,n2] the decisions were taken on.
+ * Exactly equal distances resolve to the lower index. */
+BALF_API size_t balf_match_workspace_bytes(int n1, int n2);
+BALF_API int balf_match_smnn(const float* d1, int n1, const float* d2, int n2, int dim, float th, int32_t* ids,
+                             float* dist, int32_t* count, float* dm_out, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
