@@ -75,6 +75,9 @@ def profile_report(reset=True):
     return out
 
 
+debug_set = _sig("balf_debug_set", c_int, c_int, c_int)
+
+
 def declared_symbols():
     """Every function the public header declares (tests check that the library exports them all)."""
     return re.findall(r"\b(balf_[a-z0-9_]+)\s*\(", open(HEADER_PATH).read())

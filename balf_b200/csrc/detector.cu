@@ -501,7 +501,7 @@ static size_t ws_layout(const balf_detector_arch& a, int Bc, int Hp, int Wp, voi
     size_t o[9];
     for (int i = 0; i < 4; ++i) o[i] = take(big);
     for (int l = 0; l < 3; ++l) o[4 + l] = take((size_t)Bc * (px >> (2 * (l + 1))) * a.dims[l + 1]);
-    o[7] = take((size_t)Bc * (px / 128) * a.dims[1]);      // partial sums: tiles * C is largest at level 1
+    o[7] = take((size_t)Bc * (px / 64) * a.dims[1]);       // partial sums: (64-pixel units) * C is largest at level 1
     o[8] = take((size_t)Bc * a.dims[4]);
     if (ws) {
         ws->u = reinterpret_cast<float*>(p + o[0]); ws->v = reinterpret_cast<float*>(p + o[1]);
@@ -512,6 +512,8 @@ static size_t ws_layout(const balf_detector_arch& a, int Bc, int Hp, int Wp, voi
     }
     return off;
 }
+
+int g_tc_mask = 0x1F;              // debug hook (balf_debug_set key 0): bit l = stage l on the tensor-core path, bit 4 = head
 
 constexpr int kChunkImages = 8;   // images per internal pass: bounds the workspace, keeps stage outputs near L2
 
@@ -553,6 +555,17 @@ static int run_level(const float* xin, bool nchw, const DownW& w, int Bc, int h,
 }
 
 template <int C>
+static int run_se(const Workspace& ws, const DownW& w, int Bc, int npix, int parts, cudaStream_t st) {
+    {
+        ProfScope p("det_se", st);
+        se_kernel<C><<<Bc, C, 0, st>>>(ws.partial, parts, 1.0f / (float)npix, w, ws.scale);
+    }
+    BALF_COUNT_LAUNCH(1);
+    BALF_LAUNCH_OK();
+    return 0;
+}
+
+template <int C>
 static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st) {
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
     {
@@ -568,6 +581,12 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
 
 using namespace balf;
 
+extern "C" int balf_debug_set(int key, int value) {
+    BALF_REQUIRE(key == 0, "unknown debug key %d", key);
+    g_tc_mask = value & 0x1F;
+    return 0;
+}
+
 extern "C" int balf_detector_check_arch(const balf_detector_arch* arch) { return check_arch(arch); }
 
 extern "C" int64_t balf_detector_raw_weight_count(const balf_detector_arch* arch) {
@@ -577,7 +596,7 @@ extern "C" int64_t balf_detector_raw_weight_count(const balf_detector_arch* arch
 
 extern "C" int64_t balf_detector_packed_weight_count(const balf_detector_arch* arch) {
     if (check_arch(arch)) return -1;
-    return (int64_t)walk_packed(*arch, nullptr, nullptr);
+    return (int64_t)(walk_packed(*arch, nullptr, nullptr) + tc_blob_floats(*arch));
 }
 
 extern "C" int balf_detector_pack_weights(const balf_detector_arch* arch, const float* raw, float* packed, void* stream) {
@@ -627,7 +646,7 @@ extern "C" int balf_detector_pack_weights(const balf_detector_arch* arch, const 
     src += 4 * nl;
     BALF_LAUNCH_OK();
     BALF_REQUIRE(src - raw == raw_count(a), "internal: raw weight walk mismatch");
-    return 0;
+    return tc_pack_weights(a, w, packed + total, st);       // second half of the blob: tensor-core operand images
 }
 
 extern "C" size_t balf_detector_workspace_bytes(const balf_detector_arch* arch, int B, int Hp, int Wp) {
@@ -643,13 +662,13 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
     BALF_REQUIRE(B > 0 && Hp > 0 && Wp > 0, "B, Hp, Wp must be positive");
     BALF_REQUIRE(Hp % 64 == 0 && Wp % 64 == 0, "input %dx%d: height and width must be multiples of 64 "
                  "(3 max-pools x 8x8 grid/block tokens; pad with mod_padding_symmetric)", Hp, Wp);
-    BALF_REQUIRE(precision == 0, "precision %d is not built in this library (0 = fp32)", precision);
+    BALF_REQUIRE(precision == 0 || precision == 1, "precision %d is not built in this library (0 = fp32, 1 = tf32)", precision);
     const balf_detector_arch& a = *arch;
     const int chunk = B < kChunkImages ? B : kChunkImages;
     BALF_REQUIRE(workspace_bytes >= ws_layout(a, chunk, Hp, Wp, nullptr, nullptr), "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DetW w;
-    walk_packed(a, packed, &w);
+    const float* tc_blob = packed + walk_packed(a, packed, &w);
     Workspace ws;
     ws_layout(a, chunk, Hp, Wp, workspace, &ws);
     const int nl = a.cell * a.cell + 1, hc = Hp / 8, wc = Wp / 8;
@@ -657,14 +676,35 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int Bc = B - b0 < chunk ? B - b0 : chunk;
         const float* xb = x + (size_t)b0 * 3 * Hp * Wp;
+        // precision 1: tensor-core kernels (detector_tc.cu); g_tc_mask (debug hook) can send single
+        // stages back to the fp32 kernels -- both paths share the workspace formats.
+        const int tcm = precision == 1 ? g_tc_mask : 0;
+        const DownW* d = w.down;
         int tiles = 0;
-        if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
+        if (tcm & 1) {
+            if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = run_se<32>(ws, d[0], Bc, Hp * Wp, Hp * Wp / 64, st)) return e;
+        } else if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
         if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st)) return e;
-        if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
+        if (tcm & 2) {
+            if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;
+        } else if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
         if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st)) return e;
-        if (int e = run_level<64, 128, 64, 64>(ws.pooled[1], false, w.down[2], Bc, Hp / 4, Wp / 4, ws, st, &tiles)) return e;
+        if (tcm & 4) {
+            if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = run_se<128>(ws, d[2], Bc, Hp * Wp / 16, Hp * Wp / 1024, st)) return e;
+        } else if (int e = run_level<64, 128, 64, 64>(ws.pooled[1], false, w.down[2], Bc, Hp / 4, Wp / 4, ws, st, &tiles)) return e;
         if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st)) return e;
-        if (int e = run_level<128, 256, 64, 32>(ws.pooled[2], false, w.down[3], Bc, hc, wc, ws, st, &tiles)) return e;
+        if (tcm & 8) {
+            if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = run_se<256>(ws, d[3], Bc, hc * wc, hc * wc / 64, st)) return e;
+        } else if (int e = run_level<128, 256, 64, 32>(ws.pooled[2], false, w.down[3], Bc, hc, wc, ws, st, &tiles)) return e;
+        if (tcm & 16) {
+            if (int e = tc_run_head(ws.r, ws.q, ws.scale, d[3], w.head, a, tc_blob, Bc, hc, wc,
+                                    logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp, st)) return e;
+            continue;
+        }
         dim3 gh(hc * wc / 32, Bc);
         {
             ProfScope p("det_head", st);

@@ -87,6 +87,9 @@ BALF_API size_t balf_detector_workspace_bytes(const balf_detector_arch* arch, in
 BALF_API int balf_detector_forward(const balf_detector_arch* arch, const float* packed, const float* x, int B, int Hp,
                           int Wp, float* logits, float* prob, void* workspace, size_t workspace_bytes,
                           int precision, void* stream);
+/* development hook, no reference counterpart: key 0 = bit mask of detector stages that run on the tensor-core
+ * kernels when precision = 1 (bits 0-3: the four Down stages, bit 4: the head; default all). */
+BALF_API int balf_debug_set(int key, int value);
 /* stand-alone depth-to-space (balf/utils/tensor_op.py:1-27): in [N,C,H,W] -> out [N,C/r^2,H*r,W*r] */
 BALF_API int balf_pixel_shuffle(const float* in, float* out, int N, int C, int H, int W, int r, void* stream);
 
