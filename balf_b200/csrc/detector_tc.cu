@@ -204,7 +204,7 @@ __device__ __forceinline__ void epi_ln_to_a(uint32_t taddr, float mean, float rs
             o.y = (v[4 * j + 1] - mean) * rstd * __ldg(gam + c0 + 4 * j + 1) + __ldg(bet + c0 + 4 * j + 1);
             o.z = (v[4 * j + 2] - mean) * rstd * __ldg(gam + c0 + 4 * j + 2) + __ldg(bet + c0 + 4 * j + 2);
             o.w = (v[4 * j + 3] - mean) * rstd * __ldg(gam + c0 + 4 * j + 3) + __ldg(bet + c0 + 4 * j + 3);
-            *reinterpret_cast<float4*>(dst + ((size_t)(c0 / 4 + j) * TM + row) * 4) = o;
+            *reinterpret_cast<float4*>(dst + ((size_t)(c0 / 4 + j) * TM + row) * 4) = to_tf32(o);
         }
     }
 }
@@ -293,14 +293,14 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, bo
         float v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = (valid && c < CIN) ? __ldg(xin + (img * CIN + c) * npix + pix) : 0.f;
-        *reinterpret_cast<float4*>(dst + ((size_t)0 * TM + row) * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(dst + ((size_t)1 * TM + row) * 4) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4*>(dst + ((size_t)0 * TM + row) * 4) = to_tf32(make_float4(v[0], v[1], v[2], v[3]));
+        *reinterpret_cast<float4*>(dst + ((size_t)1 * TM + row) * 4) = to_tf32(make_float4(v[4], v[5], v[6], v[7]));
     } else {
         (void)nchw;
         const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN);
 #pragma unroll 4
         for (int j = 0; j < KIN / 4; ++j)
-            *reinterpret_cast<float4*>(dst + ((size_t)j * TM + row) * 4) = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + ((size_t)j * TM + row) * 4) = valid ? to_tf32(__ldg(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(TM, 1) tc_branch_kernel(const float* __restric
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    yt[(size_t)(c0 + i) * 4] = (v[i] - mean) * rstd * __ldg(br.gn_w + c0 + i) + __ldg(br.gn_b + c0 + i);
+                    yt[(size_t)(c0 + i) * 4] = to_tf32((v[i] - mean) * rstd * __ldg(br.gn_w + c0 + i) + __ldg(br.gn_b + c0 + i));
             }
         }
         sync_for_mma();
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(TM, 1) tc_branch_kernel(const float* __restric
                 o.y = y1[4 * j + 1] * (y2[4 * j + 1] + mix_bias + 1.0f);
                 o.z = y1[4 * j + 2] * (y2[4 * j + 2] + mix_bias + 1.0f);
                 o.w = y1[4 * j + 3] * (y2[4 * j + 3] + mix_bias + 1.0f);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = o;
+                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
             }
         }
         sync_for_mma();
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(TM, 1) tc_merge_kernel(const float* __restrict
                 o.y = tc_act<3>(a[4 * j + 1] + __ldg(w.rc1_b + c0 + 4 * j + 1));
                 o.z = tc_act<3>(a[4 * j + 2] + __ldg(w.rc1_b + c0 + 4 * j + 2));
                 o.w = tc_act<3>(a[4 * j + 3] + __ldg(w.rc1_b + c0 + 4 * j + 3));
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = o;
+                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
             }
         }
         sync_for_mma();
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(TM, 1) tc_head_kernel(const float* __restrict_
                 const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C) + j);
                 o = make_float4(rv.x * sv.x + qv.x, rv.y * sv.y + qv.y, rv.z * sv.z + qv.z, rv.w * sv.w + qv.w);
             }
-            *reinterpret_cast<float4*>(s.region + ((size_t)j * TM + tid) * 4) = o;
+            *reinterpret_cast<float4*>(s.region + ((size_t)j * TM + tid) * 4) = to_tf32(o);
         }
         sync_for_mma();
         if (tid == 0) { issue_linear(ring, plan, HG_C2, region_addr, TM, tm, true); commit(s.done); }
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(TM, 1) tc_head_kernel(const float* __restrict_
                 o.y = fmaxf(a[4 * j + 1] + __ldg(w.c2_b + c0 + 4 * j + 1), 0.f);
                 o.z = fmaxf(a[4 * j + 2] + __ldg(w.c2_b + c0 + 4 * j + 2), 0.f);
                 o.w = fmaxf(a[4 * j + 3] + __ldg(w.c2_b + c0 + 4 * j + 3), 0.f);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = o;
+                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
             }
         }
         sync_for_mma();
@@ -692,7 +692,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ wT, int ld, int n0, int
     if (i >= rows * k_pad) return;
     const int k = i / rows, n = i - k * rows;
     const int b = k / kb, kk = k - b * kb;
-    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = k < k_real ? wT[(size_t)k * ld + n0 + n] : 0.f;
+    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = k < k_real ? to_tf32(wT[(size_t)k * ld + n0 + n]) : 0.f;
 }
 
 struct TcPlans {
@@ -801,12 +801,19 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// persistent grid: one CTA per resident slot.  Resident CTAs per SM = min over shared memory (227 KB usable,
+// 1 KB reserved per CTA), registers (64 K per SM) and TMEM columns (512 per SM).
 template <typename K>
-static int tc_launch_cfg(K kernel, size_t smem, int ntiles, int* grid) {
+static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* grid) {
     BALF_REQUIRE(smem <= 227 * 1024, "internal: tc kernel needs %zu bytes of shared memory", smem);
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    BALF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TM, smem));
+    BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cudaFuncAttributes fa;
+    BALF_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * TM;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (regs_per_cta > 0 && 65536 / regs_per_cta < per_sm) per_sm = 65536 / regs_per_cta;
+    if (512 / tmem_cols < per_sm) per_sm = 512 / tmem_cols;
     if (per_sm < 1) per_sm = 1;
     const int cap = num_sms() * per_sm;
     *grid = ntiles < cap ? ntiles : cap;
@@ -823,11 +830,11 @@ static int tc_run_level(const float* xin, bool nchw, const DownW& w, const TcPla
         const TcPlan& p = P.branch[level][b];
         const size_t smem = BranchCfg<C>::region + tc_weight_bytes(p.resident, p.bytes) + kTcTail;
         if (b == 0) {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, ntiles, &grid)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
             tc_branch_kernel<CIN, C, 0><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, u);
         } else {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, ntiles, &grid)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
             tc_branch_kernel<CIN, C, 1><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, v);
         }
@@ -835,7 +842,7 @@ static int tc_run_level(const float* xin, bool nchw, const DownW& w, const TcPla
     {
         const TcPlan& p = P.merge[level];
         const size_t smem = MergeCfg<C>::region + tc_weight_bytes(p.resident, p.bytes) + kTcTail;
-        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, ntiles, &grid)) return e;
+        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, MergeCfg<C>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 32 ? "det_merge_c32" : C == 64 ? "det_merge_c64" : C == 128 ? "det_merge_c128" : "det_merge_c256", st);
         tc_merge_kernel<CIN, C><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, u, v, r, q, partial);
     }
@@ -864,7 +871,7 @@ int tc_run_head(const float* r, const float* q, const float* scale, const DownW&
     const int ntiles = (g.total_units + 1) / 2;
     const size_t smem = (size_t)TM * 256 * 4 + tc_weight_bytes(false, 0) + kTcTail;
     int grid = 0;
-    if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, ntiles, &grid)) return e;
+    if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
     {
         ProfScope ps("det_head", st);
         tc_head_kernel<256><<<grid, TM, smem, st>>>(r, q, scale, w, hw, P.head, g, a.cell, logits, prob);

@@ -145,6 +145,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// fp32 -> tf32 with round-to-nearest (the tensor core itself truncates the low 13 mantissa bits; rounding the
+// operands first halves the worst-case error and removes the towards-zero bias)
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
+
 // chunk-major operand addressing (see the file comment): float offset of element (r, k)
 __host__ __device__ constexpr int cm_off(int rows, int r, int k) { return (k >> 2) * rows * 4 + r * 4 + (k & 3); }
 

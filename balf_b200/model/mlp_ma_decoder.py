@@ -94,7 +94,10 @@ class MLP_MA_DECODER(nn.Module):
                 self.arch["proj"], self.arch["red"], downsample=i < 3))
         self.detector_head = DetectorHead(input_channel=dims[4], cell_size=self.arch["cell"])
         self._packed = None          # (key, device weight blob) cache, see _weights()
-        self.precision = "fp32"      # 'fp32' (FFMA, exact-class) or 'tf32' (tcgen05), see DESIGN.md
+        # 'tf32': tcgen05 tensor-core kernels, tf32 operands (round-to-nearest) with fp32 accumulation -- score maps
+        #         within rel 1e-3 of the reference (the product path);
+        # 'fp32': FFMA kernels, bit-level class of the reference's own fp32 arithmetic (rel ~2e-6).  See DESIGN.md.
+        self.precision = "tf32"
 
     # -- weight blob: every floating tensor of the state_dict, concatenated in state_dict order
     def _weights(self, device):

@@ -17,7 +17,9 @@ FP32_RTOL = 2e-5
 @pytest.fixture(scope="module")
 def det_gpu(detector):
     import copy
-    return copy.deepcopy(detector).to("cuda:0").eval()
+    d = copy.deepcopy(detector).to("cuda:0").eval()
+    d.precision = "fp32"
+    return d
 
 
 def run(det_gpu, x):

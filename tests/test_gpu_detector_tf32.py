@@ -1,0 +1,98 @@
+"""Parity of the tensor-core detector path (precision 'tf32': balf_b200/csrc/detector_tc.cu, tcgen05
+kind::tf32 with fp32 accumulation in TMEM) with the reference's golden vectors and the CPU oracle.
+
+Bound (BASELINE.json north_star): score maps within rel <= 1e-3 for fp32-accumulate paths, and
+>= 99 % keypoint agreement end to end."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, synth_u8
+from oracle import detector as odet
+from oracle import pipeline, postproc_c
+
+pytestmark = pytest.mark.gpu
+TF32_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def det_tc(detector):
+    d = copy.deepcopy(detector).to("cuda:0").eval()
+    d.precision = "tf32"
+    return d
+
+
+def run(det, x):
+    with torch.inference_mode():
+        o = det(x.to("cuda:0"))
+    torch.cuda.synchronize()
+    return o["logits"].cpu(), o["prob"].cpu()
+
+
+def test_golden_small(det_tc):
+    g = load_golden("detector.npz")
+    x = torch.rand(1, 3, 128, 192, generator=torch.Generator().manual_seed(1234))
+    logits, prob = run(det_tc, x)
+    np.testing.assert_allclose(prob[0].numpy(), g["prob_128x192"], rtol=TF32_RTOL)
+    np.testing.assert_allclose(logits[0].numpy(), g["logits_128x192"], atol=1.5e-3)
+    x2 = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(77))
+    logits, prob = run(det_tc, x2)
+    np.testing.assert_allclose(prob.numpy(), g["prob_b2_64x128"], rtol=TF32_RTOL)
+
+
+def test_golden_512x640(det_tc):
+    g = load_golden("detector.npz")
+    x = torch.rand(1, 3, 512, 640, generator=torch.Generator().manual_seed(1234))
+    logits, prob = run(det_tc, x)
+    p = prob[0].numpy()
+    np.testing.assert_allclose(p[::8, ::8], g["prob_512x640_sub8"], rtol=TF32_RTOL)
+    np.testing.assert_allclose(p[255], g["prob_512x640_row255"], rtol=TF32_RTOL)
+    assert abs(p.astype(np.float64).sum() - 5044.952016152) < 0.05
+
+
+def test_batches_units_and_determinism(det_tc, detector_sd):
+    # odd unit counts (64x64 -> a single 64-token unit at the last stage), batches that cross the
+    # internal chunk of 8 images, per-image independence and run-to-run bit reproducibility
+    xb = torch.rand(11, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    _, pb = run(det_tc, xb)
+    _, pb2 = run(det_tc, xb)
+    np.testing.assert_array_equal(pb.numpy(), pb2.numpy())
+    for i in (0, 7, 8, 10):
+        _, pi = run(det_tc, xb[i:i + 1])
+        np.testing.assert_array_equal(pb[i].numpy(), pi[0].numpy())
+    with torch.inference_mode():
+        o = odet.detector_forward(detector_sd, xb)
+    np.testing.assert_allclose(pb.numpy(), o["prob"].numpy(), rtol=TF32_RTOL)
+    x3 = torch.rand(3, 3, 192, 64, generator=torch.Generator().manual_seed(4))
+    _, p3 = run(det_tc, x3)
+    with torch.inference_mode():
+        o3 = odet.detector_forward(detector_sd, x3)
+    np.testing.assert_allclose(p3.numpy(), o3["prob"].numpy(), rtol=TF32_RTOL)
+
+
+def test_keypoint_agreement(det_tc, detector_sd):
+    """each side on its own score map: >= 99 % of the oracle's keypoints (integer coordinates)."""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    g = load_golden("detect.npz")
+    args = config.default_test_args(sub_pixel=False)
+    for h, w, seed in ((121, 187, 5), (128, 192, 6)):
+        im = synth_u8(h, w, seed)
+        got = demo_match.detect(args, im, det_tc, "cuda:0")
+        ref = g["detect_%dx%d" % (h, w)]                     # the reference's own detect() output
+        inter = set(map(tuple, got[:, :2])) & set(map(tuple, ref[:, :2]))
+        assert len(inter) >= 0.99 * len(ref), (len(inter), len(ref))
+    im = synth_u8(480, 640, 1234)
+    got = demo_match.detect(args, im, det_tc, "cuda:0")
+    want = pipeline.detect(args, detector_sd, im, nms=postproc_c.greedy_nms)
+    inter = set(map(tuple, got[:, :2])) & set(map(tuple, want[:, :2]))
+    assert len(inter) >= 0.99 * len(want), (len(inter), len(want))
+    # windowed path (validation extraction), top-2048
+    xy, sc, _, cnt = demo_match.detect_batch_device(config.default_test_args(sub_pixel=False), torch.from_numpy(im[None, :, :, :1].copy()).to("cuda:0"),
+                                                    det_tc, nms="windowed")
+    wantw = pipeline.detect_windowed(detector_sd, im, 15, 15, 2048)
+    gotw = set(map(tuple, xy[0, :int(cnt[0])].cpu().numpy().tolist()))
+    ww = set(map(tuple, wantw[:, :2].astype(int).tolist()))
+    assert len(gotw & ww) >= 0.99 * len(ww), (len(gotw & ww), len(ww))
