@@ -8,26 +8,35 @@
 //
 //   shared memory (A operand, chunk-major) --tcgen05.mma--> TMEM accumulator --tcgen05.ld--> registers
 //        ^                                                                          |
-//        +---- bias / activation / LayerNorm / gating, one thread per pixel row <---+
+//        +---- activation / LayerNorm / gating, two threads per pixel row  <--------+
 //
 // A tile is 128 pixels = 2 "units" of 64 tokens (grid branch: the 64 cells of one in-cell offset;
-// block branch: one 8x8 block; merge / head: 64 consecutive pixels).  One thread owns one pixel row:
-// TMEM lane == thread, so LayerNorm, GELU, softmax and the gating multiply are thread-local.
+// block branch: one 8x8 block; merge / head: 64 consecutive pixels).  A CTA has 256 threads: thread
+// (row = tid % 128, half = tid / 128) owns one half of the channels of pixel row `row`; TMEM lane ==
+// row, so GELU, gating and softmax are thread-local and LayerNorm needs one (sum, sum of squares)
+// exchange between the two halves of a row through shared memory.
+//
+// What the epilogues do NOT do: biases ride in the GEMM (one extra K = 8 MMA whose A operand is a
+// constant [1 1 0 ...] column block and whose B rows hold the bias split into tf32 hi + lo parts), and
+// the LayerNorm affine parameters that feed a Linear layer are folded into that layer's weights and bias
+// when the weights are packed (W' = W diag(gamma), b' = b + W beta).  GELU is the exact erf form,
+// evaluated as v * Phi(v) with erfc(t) = exp2(t * P(t)) (degree-6 fit, |err| < 3e-7, scripts/fit_gelu.py).
+//
 // The 64x64 token mixing runs as two M=64 MMAs (A = mixing matrix, B = the unit's activations stored
 // [channel][token]); their accumulators interleave in the two 16-lane halves of every 32-lane TMEM
 // quadrant, which fixes the lane <-> pixel mapping of the branch kernels:
 //        unit g = (lane % 32) / 16,   token = (lane / 32) * 16 + lane % 16.
 // Weights are pre-packed into the exact shared-memory image of the B operands and brought in by TMA
 // bulk copies (cp.async.bulk + mbarrier) -- once per CTA when the whole set fits next to the operand
-// region (level 1), otherwise through a ring of 32 KB slots that runs ahead of the MMAs.
+// region (level 1), otherwise through a 2-slot ring that runs ahead of the MMAs.
 #include "detector.cuh"
 #include "umma.cuh"
 
 namespace balf {
 using namespace umma;
 
-constexpr int TM = 128;                 // pixels per tile == threads per CTA
-constexpr int kSlotBytes = 32768;
+constexpr int TM = 128;                 // pixel rows per tile
+constexpr int NT2 = 256;                // threads per CTA (two per row)
 constexpr int kNSlot = 2;
 constexpr int kMaxGemm = 6;
 
@@ -36,7 +45,7 @@ struct TcGemm {
     uint16_t nblk;        // K blocks
     uint16_t rows;        // rows of the packed operand (N of a Linear layer, 64 for a mixing matrix)
     uint16_t kb;          // K columns per block
-    uint16_t pad;
+    uint16_t bias;        // 1: the last block carries 8 extra K columns (bias hi, bias lo, 0 ...)
 };
 struct TcPlan {
     const float* base;
@@ -44,6 +53,7 @@ struct TcPlan {
     int ngemm;
     int resident;         // all blocks stay in shared memory for the life of the CTA
     uint32_t bytes;       // total bytes of all blocks (resident footprint)
+    uint32_t slot_bytes;  // ring slot size (largest block, 128-byte multiple)
 };
 
 enum { BG_CONV0 = 0, BG_PD1, BG_D1A, BG_D1B, BG_WM, BG_D2, BG_COUNT };
@@ -52,13 +62,17 @@ enum { HG_C2 = 0, HG_DENSE, HG_COUNT };
 constexpr int kHeadN = 80;              // 65 logits padded to a legal UMMA N (multiple of 16)
 
 __host__ __device__ constexpr int tc_kin(int cin) { return cin < 8 ? 8 : cin; }
-// K columns per streamed block: the largest power-of-two divisor of K (>= 8) whose block fits a slot
+// K columns per streamed block: the largest power-of-two divisor of K (>= 8) whose block is <= 32 KB
 __host__ __device__ constexpr int tc_kb(int rows, int K) {
     int kb = K;
-    while (kb > 8 && (kb * rows * 4 > kSlotBytes || K % kb != 0)) kb /= 2;
+    while (kb > 8 && (kb * rows * 4 > 32768 || K % kb != 0)) kb /= 2;
     return kb;
 }
 __host__ __device__ constexpr int tc_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+__host__ __device__ inline uint32_t gemm_block_bytes(const TcGemm& g, uint32_t b) {
+    return (uint32_t)g.rows * (g.kb + ((g.bias && b + 1 == g.nblk) ? 8u : 0u)) * 4u;
+}
+__host__ __device__ inline uint32_t gemm_bytes(const TcGemm& g) { return (uint32_t)g.rows * ((uint32_t)g.kb * g.nblk + (g.bias ? 8u : 0u)) * 4u; }
 
 // ------------------------------------------------------------------------------------------ weight ring (thread 0)
 struct Ring {
@@ -70,15 +84,17 @@ struct Ring {
     uint32_t to_load;      // blocks still to be requested over the life of the CTA
 };
 
+__device__ __forceinline__ void bulk_load(uint32_t dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void ring_load_one(Ring& r, const TcPlan& p) {
     const TcGemm& g = p.g[r.pg];
-    const uint32_t bytes = (uint32_t)g.rows * g.kb * 4u;
+    const uint32_t bytes = gemm_block_bytes(g, r.pb);
     const uint32_t slot = r.pcnt % kNSlot, use = r.pcnt / kNSlot;
     if (use > 0) mbar_wait(&r.empty[slot], (use - 1) & 1);
     mbar_expect_tx(&r.full[slot], bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(r.wsm + slot * kSlotBytes), "l"(p.base + g.goff + (size_t)r.pb * g.rows * g.kb), "r"(bytes),
-                    "r"(smem_u32(&r.full[slot])) : "memory");
+    bulk_load(r.wsm + slot * p.slot_bytes, p.base + g.goff + (size_t)r.pb * g.rows * g.kb, bytes, &r.full[slot]);
     ++r.pcnt;
     --r.to_load;
     if (++r.pb == g.nblk) { r.pb = 0; if (++r.pg == (uint32_t)p.ngemm) r.pg = 0; }
@@ -86,27 +102,26 @@ __device__ __forceinline__ void ring_load_one(Ring& r, const TcPlan& p) {
 __device__ __forceinline__ void ring_top_up(Ring& r, const TcPlan& p) {
     while (r.to_load > 0 && r.pcnt < r.ccnt + kNSlot) ring_load_one(r, p);
 }
-// resident mode: every block of every gemm, once
+// resident mode: every gemm, once
 __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
     mbar_expect_tx(&r.full[0], p.bytes);
     uint32_t off = 0;
     for (int gi = 0; gi < p.ngemm; ++gi) {
-        const uint32_t bytes = (uint32_t)p.g[gi].rows * p.g[gi].kb * 4u * p.g[gi].nblk;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(r.wsm + off), "l"(p.base + p.g[gi].goff), "r"(bytes), "r"(smem_u32(&r.full[0])) : "memory");
+        const uint32_t bytes = gemm_bytes(p.g[gi]);
+        bulk_load(r.wsm + off, p.base + p.g[gi].goff, bytes, &r.full[0]);
         off += bytes;
     }
 }
 __device__ __forceinline__ uint32_t resident_off(const TcPlan& p, int gi) {
     uint32_t off = 0;
-    for (int i = 0; i < gi; ++i) off += (uint32_t)p.g[i].rows * p.g[i].kb * 4u * p.g[i].nblk;
+    for (int i = 0; i < gi; ++i) off += gemm_bytes(p.g[i]);
     return off;
 }
 
-// Thread 0: D[128 x N] (+)= A[128 x K] * W^T.  A: chunk-major at shared address a_addr with a_rows
-// physical rows; W: gemm gi of the plan (rows == N).  `first` = overwrite the accumulator.
+// Thread 0: D[128 x N] (+)= A[128 x K] * W^T (+ bias).  A: chunk-major at shared address a_addr with
+// a_rows physical rows; W: gemm gi of the plan (rows == N); ones_addr: the constant [1 1 0 ..] operand.
 __device__ __forceinline__ void issue_linear(Ring& r, const TcPlan& p, int gi, uint32_t a_addr, uint32_t a_rows,
-                                             uint32_t d_tmem, bool first) {
+                                             uint32_t ones_addr, uint32_t d_tmem, bool first) {
     const TcGemm& g = p.g[gi];
     const uint32_t idesc = make_idesc_tf32(128, g.rows);
     const uint32_t a_lbo = a_rows * 16u, b_lbo = (uint32_t)g.rows * 16u;
@@ -119,7 +134,7 @@ __device__ __forceinline__ void issue_linear(Ring& r, const TcPlan& p, int gi, u
             ring_top_up(r, p);
             slot = r.ccnt % kNSlot;
             mbar_wait(&r.full[slot], (r.ccnt / kNSlot) & 1);
-            w_addr = r.wsm + slot * kSlotBytes;
+            w_addr = r.wsm + slot * p.slot_bytes;
         }
         fence_after_sync();
         for (uint32_t k8 = 0; k8 < (uint32_t)g.kb / 8u; ++k8) {
@@ -127,6 +142,8 @@ __device__ __forceinline__ void issue_linear(Ring& r, const TcPlan& p, int gi, u
             mma_tf32(d_tmem, make_desc(a_addr + kchunk * a_lbo, a_lbo, 128), make_desc(w_addr + k8 * 2u * b_lbo, b_lbo, 128),
                      idesc, !(first && b == 0 && k8 == 0));
         }
+        if (g.bias && b + 1 == g.nblk)
+            mma_tf32(d_tmem, make_desc(ones_addr, TM * 16u, 128), make_desc(w_addr + ((uint32_t)g.kb / 4u) * b_lbo, b_lbo, 128), idesc, true);
         if (!p.resident) { commit(&r.empty[slot]); ++r.ccnt; }
     }
 }
@@ -142,7 +159,7 @@ __device__ __forceinline__ void issue_mix(Ring& r, const TcPlan& p, int gi, uint
         ring_top_up(r, p);
         slot = r.ccnt % kNSlot;
         mbar_wait(&r.full[slot], (r.ccnt / kNSlot) & 1);
-        w_addr = r.wsm + slot * kSlotBytes;
+        w_addr = r.wsm + slot * p.slot_bytes;
     }
     fence_after_sync();
     const uint32_t idesc = make_idesc_tf32(64, C);
@@ -155,82 +172,102 @@ __device__ __forceinline__ void issue_mix(Ring& r, const TcPlan& p, int gi, uint
 }
 
 // ------------------------------------------------------------------------------------------ epilogue pieces
-template <int ACT> __device__ __forceinline__ float tc_act(float v) {
-    if (ACT == 1) return fmaxf(v, 0.0f);
-    if (ACT == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-    if (ACT == 3) return v > 0.0f ? v : 0.2f * v;
-    return v;
+// exact-erf GELU: v * Phi(v), erfc(t) = exp2(t * P(t)) on t = |v| / sqrt(2) in [0, 4]
+__device__ __forceinline__ float gelu_erf(float v) {
+    const float t = fminf(fabsf(v) * 0.70710678118654752440f, 4.0f);
+    float p = 2.576425322e-04f;
+    p = fmaf(p, t, -4.260182846e-03f);
+    p = fmaf(p, t, 3.200358897e-02f);
+    p = fmaf(p, t, -1.506087184e-01f);
+    p = fmaf(p, t, -9.178448915e-01f);
+    p = fmaf(p, t, -1.627962232e+00f);
+    const float h = (0.5f * v) * exp2f(p * t);        // 0.5 v erfc(t), carries the sign of v
+    return fmaxf(v, 0.0f) - fabsf(h);                 // v < 0: h;  v >= 0: v - h
 }
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
 
-// v = act(acc + bias) for C columns starting at taddr; optionally parked back in TMEM; returns sum / sum of squares
-template <int C, int ACT, bool PARK>
-__device__ __forceinline__ void epi_act(uint32_t taddr, const float* __restrict__ bias, float& sum, float& sq) {
-    sum = 0.f; sq = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
+// CH consecutive accumulator columns of this thread's row -> registers (tcgen05.ld is warp-collective)
+template <int CH>
+__device__ __forceinline__ void ld_row(uint32_t taddr, float (&v)[CH]) {
+    if constexpr (CH == 16) {
+        tmem_ld16(taddr, v);
+    } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            v[i] = tc_act<ACT>(v[i] + __ldg(bias + c0 + i));
-            sum += v[i];
-            sq = fmaf(v[i], v[i], sq);
-        }
-        if (PARK) tmem_st32(taddr + c0, v);
+        for (int c0 = 0; c0 < CH; c0 += 32) tmem_ld32(taddr + c0, *reinterpret_cast<float (*)[32]>(&v[c0]));
     }
-    if (PARK) tmem_st_wait();
+    tmem_ld_wait();
+}
+template <int CH>
+__device__ __forceinline__ void st_row(uint32_t taddr, const float (&v)[CH]) {
+    if constexpr (CH == 16) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+            :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+               "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+               "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+            : "memory");
+    } else {
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += 32) tmem_st32(taddr + c0, *reinterpret_cast<const float (*)[32]>(&v[c0]));
+    }
+    tmem_st_wait();
 }
 
-__device__ __forceinline__ void ln_stats(float sum, float sq, int C, float& mean, float& rstd) {
-    mean = sum / (float)C;
-    const float var = fmaxf(sq / (float)C - mean * mean, 0.f);
+// this thread's CH values -> A operand (chunk-major, 128 rows), columns [col0, col0 + CH), tf32-rounded
+template <int CH>
+__device__ __forceinline__ void row_to_a(const float (&v)[CH], float* region, int row, int col0) {
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j)
+        *reinterpret_cast<float4*>(region + ((size_t)(col0 / 4 + j) * TM + row) * 4) =
+            to_tf32(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+}
+
+// LayerNorm statistics of a row whose two halves live in two threads: exchange (sum, sum of squares)
+__device__ __forceinline__ void row_stats(float sum, float sq, float2* xch, int row, int half, int C, float& rstd, float& shift) {
+    xch[half * TM + row] = make_float2(sum, sq);
+    __syncthreads();
+    const float2 o = xch[(half ^ 1) * TM + row];
+    const float mean = (sum + o.x) / (float)C;
+    const float var = fmaxf((sq + o.y) / (float)C - mean * mean, 0.f);
     rstd = 1.0f / sqrtf(var + 1e-5f);
-}
-
-// LayerNorm of the parked row -> A operand (chunk-major, 128 rows) at `dst`, row `row`
-template <int C>
-__device__ __forceinline__ void epi_ln_to_a(uint32_t taddr, float mean, float rstd, const float* __restrict__ gam,
-                                            const float* __restrict__ bet, float* dst, int row) {
-#pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = (v[4 * j + 0] - mean) * rstd * __ldg(gam + c0 + 4 * j + 0) + __ldg(bet + c0 + 4 * j + 0);
-            o.y = (v[4 * j + 1] - mean) * rstd * __ldg(gam + c0 + 4 * j + 1) + __ldg(bet + c0 + 4 * j + 1);
-            o.z = (v[4 * j + 2] - mean) * rstd * __ldg(gam + c0 + 4 * j + 2) + __ldg(bet + c0 + 4 * j + 2);
-            o.w = (v[4 * j + 3] - mean) * rstd * __ldg(gam + c0 + 4 * j + 3) + __ldg(bet + c0 + 4 * j + 3);
-            *reinterpret_cast<float4*>(dst + ((size_t)(c0 / 4 + j) * TM + row) * 4) = to_tf32(o);
-        }
-    }
+    shift = -mean * rstd;                              // normalised value = v * rstd + shift
 }
 
 // ------------------------------------------------------------------------------------------ shared memory carve-up
 struct TcShared {
     float* region;         // operand region
     uint32_t wsm;          // weight area (shared address)
+    float* ones;           // [2 chunks][128 rows][4]: (1 1 0 0), (0 0 0 0)
+    float2* xch;           // [2 buffers][2 halves][128 rows]
+    float* vec;            // small per-kernel vectors (gating LayerNorm affine)
     uint64_t* full;
     uint64_t* empty;
     uint64_t* done;
     uint32_t* tmem_slot;
 };
-__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, uint32_t weight_bytes) {
+constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kTcTail = 128;
+__host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
+    return p.resident ? (p.bytes + 127u) / 128u * 128u : kNSlot * p.slot_bytes;
+}
+__host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p) {
+    return region + tc_weight_bytes(p) + kOnesBytes + kXchBytes + kVecBytes + kTcTail;
+}
+__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p) {
     TcShared s;
-    s.region = reinterpret_cast<float*>(smem);
-    s.wsm = smem_u32(smem + region_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + region_bytes + weight_bytes);
+    unsigned char* q = smem;
+    s.region = reinterpret_cast<float*>(q); q += region_bytes;
+    s.wsm = smem_u32(q); q += tc_weight_bytes(p);
+    s.ones = reinterpret_cast<float*>(q); q += kOnesBytes;
+    s.xch = reinterpret_cast<float2*>(q); q += kXchBytes;
+    s.vec = reinterpret_cast<float*>(q); q += kVecBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(q);
     s.full = bars;
     s.empty = bars + kNSlot;
     s.done = bars + 2 * kNSlot;
     s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNSlot + 1);
     return s;
 }
-__host__ __device__ constexpr uint32_t tc_weight_bytes(bool resident, uint32_t total) { return resident ? (total + 127u) / 128u * 128u : kNSlot * kSlotBytes; }
-constexpr uint32_t kTcTail = 128;      // barriers + TMEM slot
 
 __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, Ring& ring, const TcPlan& plan, uint32_t my_tiles) {
     if (threadIdx.x < 32) tmem_alloc(s.tmem_slot, ncols);
@@ -239,6 +276,9 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
         mbar_init(s.done, 1);
         mbar_fence_init();
     }
+    for (int i = threadIdx.x; i < 2 * TM; i += NT2)
+        reinterpret_cast<float4*>(s.ones)[i] = i < TM ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -252,7 +292,7 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
         else ring_top_up(ring, plan);
     }
 }
-__device__ __forceinline__ void tc_epilogue_done(const TcShared& s, uint32_t tm, uint32_t ncols) {
+__device__ __forceinline__ void tc_finish(uint32_t tm, uint32_t ncols) {
     fence_before_sync();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(tm, ncols);
@@ -284,28 +324,31 @@ __device__ __forceinline__ int unit_pixel(const UnitGeom& g, int u, int tok) {
     return u * 64 + tok;
 }
 
-// this thread's pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to KIN
+// this thread's half of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
 template <int CIN>
-__device__ __forceinline__ void load_input_row(const float* __restrict__ xin, bool nchw, size_t npix, size_t img, int pix,
-                                               bool valid, float* dst, int row) {
-    constexpr int KIN = tc_kin(CIN);
-    if (CIN < 8) {
-        float v[8];
+__device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
+                                               float* dst, int row, int half) {
+    if constexpr (CIN < 8) {                       // NCHW network input: half 0 gathers the planes, half 1 zero-fills
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (half == 0 && valid) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = (valid && c < CIN) ? __ldg(xin + (img * CIN + c) * npix + pix) : 0.f;
-        *reinterpret_cast<float4*>(dst + ((size_t)0 * TM + row) * 4) = to_tf32(make_float4(v[0], v[1], v[2], v[3]));
-        *reinterpret_cast<float4*>(dst + ((size_t)1 * TM + row) * 4) = to_tf32(make_float4(v[4], v[5], v[6], v[7]));
+            for (int c = 0; c < CIN; ++c) v[c] = __ldg(xin + (img * CIN + c) * npix + pix);
+            o = to_tf32(make_float4(v[0], v[1], v[2], v[3]));
+        }
+        *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = o;
     } else {
-        (void)nchw;
-        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN);
+        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
 #pragma unroll 4
-        for (int j = 0; j < KIN / 4; ++j)
-            *reinterpret_cast<float4*>(dst + ((size_t)j * TM + row) * 4) = valid ? to_tf32(__ldg(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < CIN / 8; ++j)
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) =
+                valid ? to_tf32(__ldg(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
 // ------------------------------------------------------------------------------------------ branch kernel
 template <int C> struct BranchCfg {
+    static constexpr int CH = C / 2;
     static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
@@ -313,250 +356,239 @@ template <int C> struct BranchCfg {
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
+    static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
 };
 
 template <int CIN, int C, int BR>
-__global__ void __launch_bounds__(TM, 1) tc_branch_kernel(const float* __restrict__ xin, int in_nchw, DownW w, TcPlan plan,
-                                                          UnitGeom geo, float* __restrict__ out) {
+__global__ void __launch_bounds__(NT2, BranchCfg<C>::min_ctas)
+tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = BranchCfg<C>;
-    const TcShared s = carve(smem, Cfg::region, tc_weight_bytes(plan.resident, plan.bytes));
-    const int tid = threadIdx.x;
+    constexpr int CH = Cfg::CH;
+    const TcShared s = carve(smem, Cfg::region, plan);
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const DownW::Branch& br = w.br[BR];
+    for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
     Ring ring;
     tc_prologue(s, Cfg::ncols, ring, plan, my_tiles);
     const uint32_t tm = *s.tmem_slot;
-    const uint32_t lane_base = tm + ((uint32_t)(tid & ~31) << 16);       // this warp's 32-lane window
-    const uint32_t region_addr = smem_u32(s.region);
-    const int ug = (tid & 31) >> 4, tok = (tid >> 5) * 16 + (tid & 15);  // unit / token of this lane
-    const DownW::Branch& br = w.br[BR];
-    const float mix_bias = __ldg(br.gd_b + tok);
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);        // this warp's 32-lane window
+    const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
+    const int ug = (row & 31) >> 4, tok = (row >> 5) * 16 + (row & 15);   // unit / token of this lane
+    const int col0 = half * CH;                                           // this thread's channel range
+    const float mix_b1 = __ldg(br.gd_b + tok) + 1.0f;
     const size_t npix = (size_t)geo.h * geo.w;
-    uint32_t phase = 0;
+    uint32_t phase = 0, xb = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int unit = 2 * t + ug;
         const bool valid = unit < geo.total_units;
         const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
         const int pix = unit_pixel<BR>(geo, u, tok);
-        // ---- x -> conv.0 -> ReLU -> LayerNorm
-        load_input_row<CIN>(xin, in_nchw != 0, npix, (size_t)img, pix, valid, s.region, tid);
+        float* orow = out + ((size_t)img * npix + pix) * C + col0;
+        float v[CH], rstd, shift;
+        // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
+        load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, BG_CONV0, region_addr, TM, tm + Cfg::col_y, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, BG_CONV0, region_addr, TM, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         wait_done(s.done, phase);
-        float sum, sq, mean, rstd;
-        epi_act<C, 1, true>(lane_base + Cfg::col_y, w.conv0_b, sum, sq);
-        ln_stats(sum, sq, C, mean, rstd);
-        epi_ln_to_a<C>(lane_base + Cfg::col_y, mean, rstd, w.pn_w, w.pn_b, s.region, tid);
-        sync_for_mma();
-        // ---- this branch's half of dense1 -> GELU = u (residual) -> LayerNorm
-        if (tid == 0) { issue_linear(ring, plan, BG_PD1, region_addr, TM, tm + Cfg::col_u, true); commit(s.done); }
-        wait_done(s.done, phase);
-        epi_act<C, 2, true>(lane_base + Cfg::col_u, w.pd1_b + BR * C, sum, sq);
-        ln_stats(sum, sq, C, mean, rstd);
-        float* orow = out + ((size_t)img * npix + pix) * C;
-        if (!Cfg::park_u) {                                        // u round-trips through the output row
-#pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 32) {                   // (tcgen05.ld is warp-collective: never under `valid`)
-                float v[32];
-                tmem_ld32(lane_base + Cfg::col_u + c0, v);
-                tmem_ld_wait();
-                if (valid) {
+        {
+            ld_row<CH>(lane_base + Cfg::col_y + col0, v);
+            float sum = 0.f, sq = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-            }
+            for (int i = 0; i < CH; ++i) { v[i] = fmaxf(v[i], 0.f); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            row_to_a<CH>(v, s.region, row, col0);
         }
-        epi_ln_to_a<C>(lane_base + Cfg::col_u, mean, rstd, br.n_w, br.n_b, s.region, tid);
+        sync_for_mma();
+        // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
+        if (tid == 0) { issue_linear(ring, plan, BG_PD1, region_addr, TM, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
+        wait_done(s.done, phase);
+        {
+            ld_row<CH>(lane_base + Cfg::col_u + col0, v);
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) { v[i] = gelu_erf(v[i]); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+            if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
+            else if (valid) {
+#pragma unroll
+                for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            row_to_a<CH>(v, s.region, row, col0);
+        }
         sync_for_mma();
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
         if (tid == 0) {
-            issue_linear(ring, plan, BG_D1A, region_addr, TM, tm + Cfg::col_y, true);
-            issue_linear(ring, plan, BG_D1B, region_addr, TM, tm + Cfg::col_y + C, true);
+            issue_linear(ring, plan, BG_D1A, region_addr, TM, ones_addr, tm + Cfg::col_y, true);
+            issue_linear(ring, plan, BG_D1B, region_addr, TM, ones_addr, tm + Cfg::col_y + C, true);
             commit(s.done);
         }
         wait_done(s.done, phase);
-        float s1, q1;
-        epi_act<C, 2, true>(lane_base + Cfg::col_y, br.d1_b, s1, q1);
-        epi_act<C, 2, true>(lane_base + Cfg::col_y + C, br.d1_b + C, sum, sq);
-        ln_stats(sum, sq, C, mean, rstd);
         {
-            float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3);
-#pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                float v[32];
-                tmem_ld32(lane_base + Cfg::col_y + C + c0, v);
-                tmem_ld_wait();
+            ld_row<CH>(lane_base + Cfg::col_y + col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    yt[(size_t)(c0 + i) * 4] = to_tf32((v[i] - mean) * rstd * __ldg(br.gn_w + c0 + i) + __ldg(br.gn_b + c0 + i));
-            }
+            for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+            st_row<CH>(lane_base + Cfg::col_y + col0, v);
+            ld_row<CH>(lane_base + Cfg::col_y + C + col0, v);
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) { v[i] = gelu_erf(v[i]); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3) + (size_t)col0 * 4;
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                yt[(size_t)i * 4] = to_tf32(fmaf(fmaf(v[i], rstd, shift), s.vec[col0 + i], s.vec[256 + col0 + i]));
         }
         sync_for_mma();
         // ---- token mixing, gating y1 * (y2' + 1)
         if (tid == 0) { issue_mix(ring, plan, BG_WM, region_addr, Cfg::y_stride, Cfg::CP, C, tm + Cfg::col_y + C); commit(s.done); }
         wait_done(s.done, phase);
+        {
+            constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
 #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float y1[32], y2[32];
-            tmem_ld32(lane_base + Cfg::col_y + c0, y1);
-            tmem_ld32(lane_base + Cfg::col_y + C + c0, y2);
-            tmem_ld_wait();
+            for (int c = 0; c < CH; c += SC) {
+                float y1[SC], y2[SC];
+                ld_row<SC>(lane_base + Cfg::col_y + col0 + c, y1);
+                ld_row<SC>(lane_base + Cfg::col_y + C + col0 + c, y2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = y1[4 * j + 0] * (y2[4 * j + 0] + mix_bias + 1.0f);
-                o.y = y1[4 * j + 1] * (y2[4 * j + 1] + mix_bias + 1.0f);
-                o.z = y1[4 * j + 2] * (y2[4 * j + 2] + mix_bias + 1.0f);
-                o.w = y1[4 * j + 3] * (y2[4 * j + 3] + mix_bias + 1.0f);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
+                for (int i = 0; i < SC; ++i) y2[i] = y1[i] * (y2[i] + mix_b1);
+                row_to_a<SC>(y2, s.region, row, col0 + c);
             }
         }
         sync_for_mma();
         // ---- dense2 + residual u -> out
-        if (tid == 0) { issue_linear(ring, plan, BG_D2, region_addr, TM, tm + Cfg::col_y, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, BG_D2, region_addr, TM, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         wait_done(s.done, phase);
+        {
+            constexpr int SC = CH > 64 ? 64 : CH;
 #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float a[32], r[32];
-            tmem_ld32(lane_base + Cfg::col_y + c0, a);
-            if (Cfg::park_u) tmem_ld32(lane_base + Cfg::col_u + c0, r);
-            tmem_ld_wait();
-            if (valid) {
+            for (int c = 0; c < CH; c += SC) {
+                float a[SC], r[SC];
+                ld_row<SC>(lane_base + Cfg::col_y + col0 + c, a);
+                if (Cfg::park_u) ld_row<SC>(lane_base + Cfg::col_u + col0 + c, r);
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 res;
-                    if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                    else res = *reinterpret_cast<const float4*>(orow + c0 + 4 * j);
-                    float4 o;
-                    o.x = a[4 * j + 0] + __ldg(br.d2_b + c0 + 4 * j + 0) + res.x;
-                    o.y = a[4 * j + 1] + __ldg(br.d2_b + c0 + 4 * j + 1) + res.y;
-                    o.z = a[4 * j + 2] + __ldg(br.d2_b + c0 + 4 * j + 2) + res.z;
-                    o.w = a[4 * j + 3] + __ldg(br.d2_b + c0 + 4 * j + 3) + res.w;
-                    *reinterpret_cast<float4*>(orow + c0 + 4 * j) = o;
+                    for (int j = 0; j < SC / 4; ++j) {
+                        float4 res;
+                        if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        else res = *reinterpret_cast<const float4*>(orow + c + 4 * j);
+                        *reinterpret_cast<float4*>(orow + c + 4 * j) =
+                            make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
+                    }
                 }
             }
         }
         // the next tile's input load overwrites the region: every MMA reading it has completed (wait_done)
     }
-    tc_epilogue_done(s, tm, Cfg::ncols);
+    tc_finish(tm, Cfg::ncols);
 }
 
 // ------------------------------------------------------------------------------------------ merge kernel
 template <int C> struct MergeCfg {
+    static constexpr int CH = C / 2;
     static constexpr uint32_t region = (uint32_t)TM * C * 4;
     static constexpr int col_x0 = 0, col_acc = C;
     static constexpr int ncols = tc_cols(2 * C);
+    static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
 };
 
 template <int CIN, int C>
-__global__ void __launch_bounds__(TM, 1) tc_merge_kernel(const float* __restrict__ xin, int in_nchw, DownW w, TcPlan plan,
-                                                         UnitGeom geo, const float* __restrict__ uin, const float* __restrict__ vin,
-                                                         float* __restrict__ rout, float* __restrict__ qout,
-                                                         float* __restrict__ partial) {
+__global__ void __launch_bounds__(NT2, MergeCfg<C>::min_ctas)
+tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
+                const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = MergeCfg<C>;
-    const TcShared s = carve(smem, Cfg::region, tc_weight_bytes(plan.resident, plan.bytes));
-    const int tid = threadIdx.x;
+    constexpr int CH = Cfg::CH;
+    (void)w;
+    const TcShared s = carve(smem, Cfg::region, plan);
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
     tc_prologue(s, Cfg::ncols, ring, plan, my_tiles);
     const uint32_t tm = *s.tmem_slot;
-    const uint32_t lane_base = tm + ((uint32_t)(tid & ~31) << 16);
-    const uint32_t region_addr = smem_u32(s.region);
-    const int ug = tid >> 6, tok = tid & 63;
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
+    const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
+    const int ug = row >> 6, tok = row & 63;
+    const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
-    uint32_t phase = 0;
+    uint32_t phase = 0, xb = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int unit = 2 * t + ug;
         const bool valid = unit < geo.total_units;
         const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
         const int pix = u * 64 + tok;
-        const size_t row_off = ((size_t)img * npix + pix) * C;
+        const size_t row_off = ((size_t)img * npix + pix) * C + col0;
+        float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
-        load_input_row<CIN>(xin, in_nchw != 0, npix, (size_t)img, pix, valid, s.region, tid);
+        load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_CONV0, region_addr, TM, tm + Cfg::col_x0, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, MG_CONV0, region_addr, TM, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
         wait_done(s.done, phase);
-        float sum, sq, mean, rstd;
-        epi_act<C, 1, true>(lane_base + Cfg::col_x0, w.conv0_b, sum, sq);
+        ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+        st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
-        load_input_row<C>(uin, false, npix, (size_t)img, pix, valid, s.region, tid);
+        load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_PD2A, region_addr, TM, tm + Cfg::col_acc, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, MG_PD2A, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
-        load_input_row<C>(vin, false, npix, (size_t)img, pix, valid, s.region, tid);
+        load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_PD2B, region_addr, TM, tm + Cfg::col_acc, false); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, MG_PD2B, region_addr, TM, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
         wait_done(s.done, phase);
-        // x1 = acc + b + x0 (parked over the accumulator); q = x1 + x0 -> global; LayerNorm(x1) -> region
-        sum = 0.f; sq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float a[32], x0[32];
-            tmem_ld32(lane_base + Cfg::col_acc + c0, a);
-            tmem_ld32(lane_base + Cfg::col_x0 + c0, x0);
-            tmem_ld_wait();
+        // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
+        {
+            float rstd, shift;
+            ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+            float sum = 0.f, sq = 0.f;
+            constexpr int SC = CH > 64 ? 64 : CH;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                a[i] = a[i] + __ldg(w.pd2_b + c0 + i) + x0[i];
-                sum += a[i];
-                sq = fmaf(a[i], a[i], sq);
-                x0[i] = a[i] + x0[i];
-            }
-            tmem_st32(lane_base + Cfg::col_acc + c0, a);
-            if (valid) {
+            for (int c = 0; c < CH; c += SC) {
+                float x0[SC];
+                ld_row<SC>(lane_base + Cfg::col_x0 + col0 + c, x0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(qout + row_off + c0 + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
+                for (int i = 0; i < SC; ++i) { v[c + i] += x0[i]; sum += v[c + i]; sq = fmaf(v[c + i], v[c + i], sq); x0[i] += v[c + i]; }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < SC / 4; ++j)
+                        *reinterpret_cast<float4*>(qout + row_off + c + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
+                }
             }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            row_to_a<CH>(v, s.region, row, col0);
         }
-        tmem_st_wait();
-        ln_stats(sum, sq, C, mean, rstd);
-        epi_ln_to_a<C>(lane_base + Cfg::col_acc, mean, rstd, w.rn_w, w.rn_b, s.region, tid);
         sync_for_mma();
         // ---- conv1 -> LeakyReLU(0.2)
-        if (tid == 0) { issue_linear(ring, plan, MG_RC1, region_addr, TM, tm + Cfg::col_acc, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, MG_RC1, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float a[32];
-            tmem_ld32(lane_base + Cfg::col_acc + c0, a);
-            tmem_ld_wait();
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = tc_act<3>(a[4 * j + 0] + __ldg(w.rc1_b + c0 + 4 * j + 0));
-                o.y = tc_act<3>(a[4 * j + 1] + __ldg(w.rc1_b + c0 + 4 * j + 1));
-                o.z = tc_act<3>(a[4 * j + 2] + __ldg(w.rc1_b + c0 + 4 * j + 2));
-                o.w = tc_act<3>(a[4 * j + 3] + __ldg(w.rc1_b + c0 + 4 * j + 3));
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
-            }
-        }
+        for (int i = 0; i < CH; ++i) v[i] = lrelu02(v[i]);
+        row_to_a<CH>(v, s.region, row, col0);
         sync_for_mma();
-        // ---- conv2 = r -> global, and staged in the region for the per-unit channel sums (squeeze)
-        if (tid == 0) { issue_linear(ring, plan, MG_RC2, region_addr, TM, tm + Cfg::col_acc, true); commit(s.done); }
+        // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
+        if (tid == 0) { issue_linear(ring, plan, MG_RC2, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float a[32];
-            tmem_ld32(lane_base + Cfg::col_acc + c0, a);
-            tmem_ld_wait();
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = a[4 * j + 0] + __ldg(w.rc2_b + c0 + 4 * j + 0);
-                o.y = a[4 * j + 1] + __ldg(w.rc2_b + c0 + 4 * j + 1);
-                o.z = a[4 * j + 2] + __ldg(w.rc2_b + c0 + 4 * j + 2);
-                o.w = a[4 * j + 3] + __ldg(w.rc2_b + c0 + 4 * j + 3);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = o;
-                if (valid) *reinterpret_cast<float4*>(rout + row_off + c0 + 4 * j) = o;
-            }
+        for (int j = 0; j < CH / 4; ++j) {
+            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
+            if (valid) *reinterpret_cast<float4*>(rout + row_off + 4 * j) = o;
         }
         __syncthreads();
         // channel sums of each unit, fixed order (rotated start so that a warp's lanes hit distinct banks)
-        for (int i = tid; i < 2 * C; i += TM) {
+        for (int i = tid; i < 2 * C; i += NT2) {
             const int uu = i / C, c = i - uu * C;
             const int un = 2 * t + uu;
             if (un < geo.total_units) {
@@ -568,29 +600,31 @@ __global__ void __launch_bounds__(TM, 1) tc_merge_kernel(const float* __restrict
         }
         __syncthreads();
     }
-    tc_epilogue_done(s, tm, Cfg::ncols);
+    tc_finish(tm, Cfg::ncols);
 }
 
 // ------------------------------------------------------------------------------------------ head kernel (last stage)
-// t = r * s + q -> conv2 (C -> C) -> ReLU -> dense (C -> 65) -> folded BatchNorm = logits -> softmax ->
-// drop the dustbin -> depth-to-space.  One thread = one 8x8 cell.
+// t = r * s + q -> conv2 (C -> C) -> ReLU -> dense (C -> 65, BatchNorm folded into weights and bias) = logits ->
+// softmax -> drop the dustbin -> depth-to-space.  The half-0 thread of a row finishes its 8x8 cell.
 template <int C>
-__global__ void __launch_bounds__(TM, 1) tc_head_kernel(const float* __restrict__ r, const float* __restrict__ q,
-                                                        const float* __restrict__ scale, DownW w, HeadW hw, TcPlan plan,
-                                                        UnitGeom geo, int cell, float* __restrict__ logits, float* __restrict__ prob) {
+__global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict__ r, const float* __restrict__ q,
+                                                         const float* __restrict__ scale, TcPlan plan, UnitGeom geo, int cell,
+                                                         float* __restrict__ logits, float* __restrict__ prob) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr uint32_t region_bytes = (uint32_t)TM * C * 4;
-    constexpr int ncols = tc_cols(C + kHeadN);
-    const TcShared s = carve(smem, region_bytes, tc_weight_bytes(plan.resident, plan.bytes));
-    const int tid = threadIdx.x;
+    constexpr int ncols = tc_cols(C + 96);
+    constexpr int CH = C / 2;
+    const TcShared s = carve(smem, region_bytes, plan);
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
     tc_prologue(s, ncols, ring, plan, my_tiles);
     const uint32_t tm = *s.tmem_slot;
-    const uint32_t lane_base = tm + ((uint32_t)(tid & ~31) << 16);
-    const uint32_t region_addr = smem_u32(s.region);
-    const int ug = tid >> 6, tok = tid & 63;
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
+    const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
+    const int ug = row >> 6, tok = row & 63;
+    const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
     const int nlog = cell * cell + 1;
     uint32_t phase = 0;
@@ -599,100 +633,100 @@ __global__ void __launch_bounds__(TM, 1) tc_head_kernel(const float* __restrict_
         const bool valid = unit < geo.total_units;
         const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
         const int pix = u * 64 + tok;
-        const size_t row_off = ((size_t)img * npix + pix) * C;
+        const size_t row_off = ((size_t)img * npix + pix) * C + col0;
 #pragma unroll 4
-        for (int j = 0; j < C / 4; ++j) {
+        for (int j = 0; j < CH / 4; ++j) {
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 const float4 rv = __ldg(reinterpret_cast<const float4*>(r + row_off) + j);
                 const float4 qv = __ldg(reinterpret_cast<const float4*>(q + row_off) + j);
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C) + j);
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + col0) + j);
                 o = make_float4(rv.x * sv.x + qv.x, rv.y * sv.y + qv.y, rv.z * sv.z + qv.z, rv.w * sv.w + qv.w);
             }
-            *reinterpret_cast<float4*>(s.region + ((size_t)j * TM + tid) * 4) = to_tf32(o);
+            *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = to_tf32(o);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, HG_C2, region_addr, TM, tm, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, HG_C2, region_addr, TM, ones_addr, tm, true); commit(s.done); }
         wait_done(s.done, phase);
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float a[32];
-            tmem_ld32(lane_base + c0, a);
-            tmem_ld_wait();
+        {
+            float v[CH];
+            ld_row<CH>(lane_base + col0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = fmaxf(a[4 * j + 0] + __ldg(w.c2_b + c0 + 4 * j + 0), 0.f);
-                o.y = fmaxf(a[4 * j + 1] + __ldg(w.c2_b + c0 + 4 * j + 1), 0.f);
-                o.z = fmaxf(a[4 * j + 2] + __ldg(w.c2_b + c0 + 4 * j + 2), 0.f);
-                o.w = fmaxf(a[4 * j + 3] + __ldg(w.c2_b + c0 + 4 * j + 3), 0.f);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(c0 / 4 + j) * TM + tid) * 4) = to_tf32(o);
-            }
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            row_to_a<CH>(v, s.region, row, col0);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, HG_DENSE, region_addr, TM, tm + C, true); commit(s.done); }
+        if (tid == 0) { issue_linear(ring, plan, HG_DENSE, region_addr, TM, ones_addr, tm + C, true); commit(s.done); }
         wait_done(s.done, phase);
-        // logits: folded BatchNorm; softmax over nlog channels (3 passes over 65 parked values)
-        float mx = kNegInf;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 96; c0 += 32) {
-            if (c0 >= kHeadN) break;
-            float a[32];
-            tmem_ld32(lane_base + C + c0, a);      // columns beyond kHeadN hold stale data and are masked below
-            tmem_ld_wait();
+        // logits = columns C .. C+64 of the row.  tcgen05.ld is warp-collective and `half` is warp-uniform, so the
+        // branch below is convergent per warp.
+        if (half == 0) {
+            float z[96];
+            ld_row<96>(lane_base + C, z);                           // columns >= 80 hold stale data (never read below)
+            float mx = kNegInf;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int n = c0 + i;
-                if (n < nlog) {
-                    const float z = (a[i] + __ldg(hw.b + n)) * __ldg(hw.alpha + n) + __ldg(hw.beta + n);
-                    a[i] = z;
-                    mx = fmaxf(mx, z);
-                    if (valid && logits) logits[((size_t)img * nlog + n) * npix + pix] = z;
-                } else a[i] = kNegInf;
-            }
-            tmem_st32(lane_base + C + c0, a);      // 32 wide: columns up to C + 96 are inside the allocation
-        }
-        tmem_st_wait();
-        float den = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 96; c0 += 32) {
-            float a[32];
-            tmem_ld32(lane_base + C + c0, a);
-            tmem_ld_wait();
+            for (int n = 0; n < 65; ++n) mx = fmaxf(mx, z[n]);
+            float den = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c0 + i < nlog) den += expf(a[i] - mx);
-        }
-        const int cy = pix / geo.w, cx = pix - cy * geo.w;
-        const int Wp = geo.w * cell, Hp = geo.h * cell;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-            float a[32];
-            tmem_ld32(lane_base + C + c0, a);
-            tmem_ld_wait();
+            for (int n = 0; n < 65; ++n) den += expf(z[n] - mx);
             if (valid) {
+                const int cy = pix / geo.w, cx = pix - cy * geo.w;
+                const int Wp = geo.w * cell, Hp = geo.h * cell;
+                if (logits) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = c0 + i;
-                    if (n < nlog - 1) {
-                        const int yy = cy * cell + n / cell, xx = cx * cell + n % cell;
-                        prob[((size_t)img * Hp + yy) * Wp + xx] = expf(a[i] - mx) / den;
-                    }
+                    for (int n = 0; n < 65; ++n) logits[((size_t)img * nlog + n) * npix + pix] = z[n];
+                }
+                const float inv = 1.0f / den;
+#pragma unroll
+                for (int n = 0; n < 64; ++n) {
+                    const int yy = cy * cell + (n >> 3), xx = cx * cell + (n & 7);
+                    prob[((size_t)img * Hp + yy) * Wp + xx] = expf(z[n] - mx) * inv;
                 }
             }
         }
     }
-    tc_epilogue_done(s, tm, ncols);
+    tc_finish(tm, ncols);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing (tc blob)
-// wT [K][ld] (the fp32 path's transposed weight) -> blocks of [rows x kb] chunk-major, rows n0..n0+rows
+// wT [K][ld] (the fp32 path's transposed weight) -> blocks of [rows x kb] chunk-major, rows n0..n0+rows.
+// Optional folds: gamma[k] (LayerNorm weight of the layer's input), alpha[n] (per-output scale).
 __global__ void tc_pack_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real, int k_pad, int kb,
-                               float* __restrict__ dst) {
+                               const float* __restrict__ gamma, const float* __restrict__ alpha, float* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * k_pad) return;
     const int k = i / rows, n = i - k * rows;
     const int b = k / kb, kk = k - b * kb;
-    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = k < k_real ? to_tf32(wT[(size_t)k * ld + n0 + n]) : 0.f;
+    float v = 0.f;
+    if (k < k_real) {
+        v = wT[(size_t)k * ld + n0 + n];
+        if (gamma) v *= gamma[k];
+        if (alpha) v *= alpha[n0 + n];
+    }
+    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = to_tf32(v);
+}
+// bias columns of the last block: b' = (bias[n] + sum_k W[n][k] beta[k]) * alpha[n] + add[n], split into tf32 hi + lo
+__global__ void tc_pack_bias_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real,
+                                    const float* __restrict__ bias, const float* __restrict__ beta,
+                                    const float* __restrict__ alpha, const float* __restrict__ add, float* __restrict__ dst) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= rows) return;
+    float acc = bias ? bias[n0 + n] : 0.f;
+    if (beta) {
+        float comp = 0.f;                                           // compensated: the fold must not cost precision
+        for (int k = 0; k < k_real; ++k) {
+            const float y = wT[(size_t)k * ld + n0 + n] * beta[k] - comp, t = acc + y;
+            comp = (t - acc) - y;
+            acc = t;
+        }
+    }
+    if (alpha) acc *= alpha[n0 + n];
+    if (add) acc += add[n0 + n];
+    const float hi = to_tf32(acc), lo = to_tf32(acc - hi);
+    dst[n * 4 + 0] = hi;
+    dst[n * 4 + 1] = lo;
+    dst[n * 4 + 2] = 0.f;
+    dst[n * 4 + 3] = 0.f;
 }
 
 struct TcPlans {
@@ -700,15 +734,18 @@ struct TcPlans {
     size_t floats;
 };
 
-static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K) {
+static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias) {
     const int kb = tc_kb(rows, K);
-    p.g[gi].goff = (uint32_t)off;
-    p.g[gi].nblk = (uint16_t)(K / kb);
-    p.g[gi].rows = (uint16_t)rows;
-    p.g[gi].kb = (uint16_t)kb;
-    p.g[gi].pad = 0;
-    off += (size_t)rows * K;
-    p.bytes += (uint32_t)rows * K * 4u;
+    TcGemm& g = p.g[gi];
+    g.goff = (uint32_t)off;
+    g.nblk = (uint16_t)(K / kb);
+    g.rows = (uint16_t)rows;
+    g.kb = (uint16_t)kb;
+    g.bias = bias ? 1 : 0;
+    off += gemm_bytes(g) / 4;
+    p.bytes += gemm_bytes(g);
+    const uint32_t big = (gemm_block_bytes(g, g.nblk - 1) + 127u) / 128u * 128u;
+    if (big > p.slot_bytes) p.slot_bytes = big;
 }
 
 static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPlans* out) {
@@ -721,27 +758,27 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
             p.base = base; p.ngemm = BG_COUNT; p.resident = resident;
-            tc_add(p, BG_CONV0, off, c, cin);
-            tc_add(p, BG_PD1, off, c, c);
-            tc_add(p, BG_D1A, off, c, c);
-            tc_add(p, BG_D1B, off, c, c);
-            tc_add(p, BG_WM, off, 64, 64);
-            tc_add(p, BG_D2, off, c, c);
+            tc_add(p, BG_CONV0, off, c, cin, true);
+            tc_add(p, BG_PD1, off, c, c, true);
+            tc_add(p, BG_D1A, off, c, c, true);
+            tc_add(p, BG_D1B, off, c, c, true);
+            tc_add(p, BG_WM, off, 64, 64, false);
+            tc_add(p, BG_D2, off, c, c, true);
         }
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        tc_add(m, MG_CONV0, off, c, cin);
-        tc_add(m, MG_PD2A, off, c, c);
-        tc_add(m, MG_PD2B, off, c, c);
-        tc_add(m, MG_RC1, off, c, c);
-        tc_add(m, MG_RC2, off, c, c);
+        tc_add(m, MG_CONV0, off, c, cin, true);
+        tc_add(m, MG_PD2A, off, c, c, false);
+        tc_add(m, MG_PD2B, off, c, c, true);
+        tc_add(m, MG_RC1, off, c, c, true);
+        tc_add(m, MG_RC2, off, c, c, true);
     }
     TcPlan& h = P.head;
     h = TcPlan{};
     h.base = base; h.ngemm = HG_COUNT; h.resident = 0;
-    tc_add(h, HG_C2, off, a.dims[4], a.dims[4]);
-    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4]);
+    tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true);
+    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true);
     P.floats = off;
     if (out) *out = P;
 }
@@ -752,10 +789,16 @@ size_t tc_blob_floats(const balf_detector_arch& a) {
     return P.floats;
 }
 
-static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0, int k_real, float* blob, cudaStream_t st) {
+struct Fold { const float* gamma; const float* beta; const float* alpha; const float* add; };
+
+static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0, int k_real, const float* bias, Fold f,
+                        float* blob, cudaStream_t st) {
     const TcGemm& g = p.g[gi];
     const int k_pad = g.nblk * g.kb;
-    tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, blob + g.goff);
+    tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha, blob + g.goff);
+    if (g.bias)   // two chunk planes after the last block's kb columns; the second stays zero (blob is memset)
+        tc_pack_bias_kernel<<<cdiv(g.rows, 128), 128, 0, st>>>(wT, ld, n0, g.rows, k_real, bias, f.beta, f.alpha, f.add,
+                                                               blob + g.goff + (size_t)g.rows * k_pad);
 }
 
 // fp32-path packed weights (DetW) -> tc blob
@@ -763,28 +806,30 @@ int tc_pack_weights(const balf_detector_arch& a, const DetW& w, float* blob, cud
     TcPlans P;
     tc_build_plans(a, blob, &P);
     BALF_CUDA_OK(cudaMemsetAsync(blob, 0, P.floats * sizeof(float), st));
+    const Fold none{nullptr, nullptr, nullptr, nullptr};
     for (int l = 0; l < 4; ++l) {
         const int ci = a.dims[l], c = a.dims[l + 1];
         const DownW& d = w.down[l];
         for (int b = 0; b < 2; ++b) {
             const TcPlan& p = P.branch[l][b];
             const DownW::Branch& r = d.br[b];
-            tc_pack_one(p, BG_CONV0, d.conv0_w, c, 0, ci, blob, st);
-            tc_pack_one(p, BG_PD1, d.pd1_w, 2 * c, b * c, c, blob, st);
-            tc_pack_one(p, BG_D1A, r.d1_w, 2 * c, 0, c, blob, st);
-            tc_pack_one(p, BG_D1B, r.d1_w, 2 * c, c, c, blob, st);
-            tc_pack_one(p, BG_WM, r.gd_w, 64, 0, 64, blob, st);
-            tc_pack_one(p, BG_D2, r.d2_w, c, 0, c, blob, st);
+            tc_pack_one(p, BG_CONV0, d.conv0_w, c, 0, ci, d.conv0_b, none, blob, st);
+            tc_pack_one(p, BG_PD1, d.pd1_w, 2 * c, b * c, c, d.pd1_b, Fold{d.pn_w, d.pn_b, nullptr, nullptr}, blob, st);
+            tc_pack_one(p, BG_D1A, r.d1_w, 2 * c, 0, c, r.d1_b, Fold{r.n_w, r.n_b, nullptr, nullptr}, blob, st);
+            tc_pack_one(p, BG_D1B, r.d1_w, 2 * c, c, c, r.d1_b, Fold{r.n_w, r.n_b, nullptr, nullptr}, blob, st);
+            tc_pack_one(p, BG_WM, r.gd_w, 64, 0, 64, nullptr, none, blob, st);
+            tc_pack_one(p, BG_D2, r.d2_w, c, 0, c, r.d2_b, none, blob, st);
         }
         const TcPlan& m = P.merge[l];
-        tc_pack_one(m, MG_CONV0, d.conv0_w, c, 0, ci, blob, st);
-        tc_pack_one(m, MG_PD2A, d.pd2_w, c, 0, c, blob, st);
-        tc_pack_one(m, MG_PD2B, d.pd2_w + (size_t)c * c, c, 0, c, blob, st);
-        tc_pack_one(m, MG_RC1, d.rc1_w, c, 0, c, blob, st);
-        tc_pack_one(m, MG_RC2, d.rc2_w, c, 0, c, blob, st);
+        tc_pack_one(m, MG_CONV0, d.conv0_w, c, 0, ci, d.conv0_b, none, blob, st);
+        tc_pack_one(m, MG_PD2A, d.pd2_w, c, 0, c, nullptr, none, blob, st);
+        tc_pack_one(m, MG_PD2B, d.pd2_w + (size_t)c * c, c, 0, c, d.pd2_b, none, blob, st);
+        tc_pack_one(m, MG_RC1, d.rc1_w, c, 0, c, d.rc1_b, Fold{d.rn_w, d.rn_b, nullptr, nullptr}, blob, st);
+        tc_pack_one(m, MG_RC2, d.rc2_w, c, 0, c, d.rc2_b, none, blob, st);
     }
-    tc_pack_one(P.head, HG_C2, w.down[3].c2_w, a.dims[4], 0, a.dims[4], blob, st);
-    tc_pack_one(P.head, HG_DENSE, w.head.w, kHeadPad, 0, a.dims[4], blob, st);
+    tc_pack_one(P.head, HG_C2, w.down[3].c2_w, a.dims[4], 0, a.dims[4], w.down[3].c2_b, none, blob, st);
+    // logits = (x W^T + b) * alpha + beta_bn  (eval BatchNorm folded, decoder.py:18-22)
+    tc_pack_one(P.head, HG_DENSE, w.head.w, kHeadPad, 0, a.dims[4], w.head.b, Fold{nullptr, nullptr, w.head.alpha, w.head.beta}, blob, st);
     BALF_LAUNCH_OK();
     return 0;
 }
@@ -810,7 +855,7 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     BALF_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
-    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * TM;
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT2;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (regs_per_cta > 0 && 65536 / regs_per_cta < per_sm) per_sm = 65536 / regs_per_cta;
     if (512 / tmem_cols < per_sm) per_sm = 512 / tmem_cols;
@@ -821,30 +866,30 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
 }
 
 template <int CIN, int C>
-static int tc_run_level(const float* xin, bool nchw, const DownW& w, const TcPlans& P, int level, int Bc, int h, int wd,
+static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int level, int Bc, int h, int wd,
                         float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
     UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64)};
     const int ntiles = (g.total_units + 1) / 2;
     int grid = 0;
     for (int b = 0; b < 2; ++b) {
         const TcPlan& p = P.branch[level][b];
-        const size_t smem = BranchCfg<C>::region + tc_weight_bytes(p.resident, p.bytes) + kTcTail;
+        const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p);
         if (b == 0) {
             if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
-            tc_branch_kernel<CIN, C, 0><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, u);
+            tc_branch_kernel<CIN, C, 0><<<grid, NT2, smem, st>>>(xin, w, p, g, u);
         } else {
             if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
-            tc_branch_kernel<CIN, C, 1><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, v);
+            tc_branch_kernel<CIN, C, 1><<<grid, NT2, smem, st>>>(xin, w, p, g, v);
         }
     }
     {
         const TcPlan& p = P.merge[level];
-        const size_t smem = MergeCfg<C>::region + tc_weight_bytes(p.resident, p.bytes) + kTcTail;
+        const size_t smem = tc_smem_bytes(MergeCfg<C>::region, p);
         if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, MergeCfg<C>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 32 ? "det_merge_c32" : C == 64 ? "det_merge_c64" : C == 128 ? "det_merge_c128" : "det_merge_c256", st);
-        tc_merge_kernel<CIN, C><<<grid, TM, smem, st>>>(xin, nchw, w, p, g, u, v, r, q, partial);
+        tc_merge_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     }
     BALF_COUNT_LAUNCH(3);
     BALF_LAUNCH_OK();
@@ -853,28 +898,30 @@ static int tc_run_level(const float* xin, bool nchw, const DownW& w, const TcPla
 
 int tc_run_level_dispatch(int level, const float* xin, bool nchw, const DownW& w, const balf_detector_arch& a, const float* blob,
                           int Bc, int h, int wd, float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
+    (void)nchw;
     TcPlans P;
     tc_build_plans(a, blob, &P);
     switch (level) {
-        case 0: return tc_run_level<3, 32>(xin, nchw, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
-        case 1: return tc_run_level<32, 64>(xin, nchw, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
-        case 2: return tc_run_level<64, 128>(xin, nchw, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
-        default: return tc_run_level<128, 256>(xin, nchw, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
+        case 0: return tc_run_level<3, 32>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
+        case 1: return tc_run_level<32, 64>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
+        case 2: return tc_run_level<64, 128>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
+        default: return tc_run_level<128, 256>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
     }
 }
 
 int tc_run_head(const float* r, const float* q, const float* scale, const DownW& w, const HeadW& hw, const balf_detector_arch& a,
                 const float* blob, int Bc, int hc, int wc, float* logits, float* prob, cudaStream_t st) {
+    (void)w; (void)hw;
     TcPlans P;
     tc_build_plans(a, blob, &P);
     UnitGeom g{hc, wc, hc / 8, wc / 8, hc * wc / 64, Bc * (hc * wc / 64)};
     const int ntiles = (g.total_units + 1) / 2;
-    const size_t smem = (size_t)TM * 256 * 4 + tc_weight_bytes(false, 0) + kTcTail;
+    const size_t smem = tc_smem_bytes((uint32_t)TM * 256 * 4, P.head);
     int grid = 0;
     if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
     {
         ProfScope ps("det_head", st);
-        tc_head_kernel<256><<<grid, TM, smem, st>>>(r, q, scale, w, hw, P.head, g, a.cell, logits, prob);
+        tc_head_kernel<256><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
