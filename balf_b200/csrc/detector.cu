@@ -329,25 +329,45 @@ __global__ void __launch_bounds__(NT, 1) merge_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ squeeze-excite
+// One CTA per image.  The per-unit channel sums are reduced in a fixed order (thread (seg, c) walks units seg,
+// seg + NSEG, ...; then a fixed shared-memory tree over seg), so the mean -- and with it the score map -- is
+// bit-reproducible run to run and independent of the batch the image sits in.
+constexpr int kSeThreads = 1024;
 template <int C>
-__global__ void __launch_bounds__(C) se_kernel(const float* __restrict__ partial, int tiles, float inv_npix, DownW w,
-                                               float* __restrict__ scale) {
+__global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict__ partial, int tiles, float inv_npix, DownW w,
+                                                        float* __restrict__ scale) {
+    constexpr int NSEG = kSeThreads / C;
+    __shared__ float red[kSeThreads];
     __shared__ float mean[C];
     __shared__ float hid[C / 4];
-    const int b = blockIdx.x, c = threadIdx.x;
-    float s = 0.0f;
-    for (int t = 0; t < tiles; ++t) s += partial[((size_t)b * tiles + t) * C + c];
-    mean[c] = s * inv_npix;
+    const int b = blockIdx.x, c = threadIdx.x % C, seg = threadIdx.x / C;
+    const float* src = partial + (size_t)b * tiles * C + c;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int t = seg;
+    for (; t + 3 * NSEG < tiles; t += 4 * NSEG) {
+        s0 += src[(size_t)t * C]; s1 += src[(size_t)(t + NSEG) * C];
+        s2 += src[(size_t)(t + 2 * NSEG) * C]; s3 += src[(size_t)(t + 3 * NSEG) * C];
+    }
+    for (; t < tiles; t += NSEG) s0 += src[(size_t)t * C];
+    red[threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (c < C / 4) {
+    for (int n = NSEG / 2; n >= 1; n >>= 1) {
+        if (seg < n) red[threadIdx.x] += red[threadIdx.x + n * C];
+        __syncthreads();
+    }
+    if (threadIdx.x < C) mean[c] = red[c] * inv_npix;
+    __syncthreads();
+    if (threadIdx.x < C / 4) {
         float h = __ldg(w.ex0_b + c);
         for (int k = 0; k < C; ++k) h = fmaf(mean[k], __ldg(w.ex0_w + (size_t)k * (C / 4) + c), h);
         hid[c] = fmaxf(h, 0.0f);
     }
     __syncthreads();
-    float o = __ldg(w.ex2_b + c);
-    for (int k = 0; k < C / 4; ++k) o = fmaf(hid[k], __ldg(w.ex2_w + (size_t)k * C + c), o);
-    scale[(size_t)b * C + c] = 1.0f / (1.0f + expf(-o));
+    if (threadIdx.x < C) {
+        float o = __ldg(w.ex2_b + c);
+        for (int k = 0; k < C / 4; ++k) o = fmaf(hid[k], __ldg(w.ex2_w + (size_t)k * C + c), o);
+        scale[(size_t)b * C + c] = 1.0f / (1.0f + expf(-o));
+    }
 }
 
 // ------------------------------------------------------------------------------------------ pool (stages 1-3)
@@ -546,7 +566,7 @@ static int run_level(const float* xin, bool nchw, const DownW& w, int Bc, int h,
     }
     {
         ProfScope p("det_se", st);
-        se_kernel<C><<<Bc, C, 0, st>>>(ws.partial, npix / MM, 1.0f / (float)npix, w, ws.scale);
+        se_kernel<C><<<Bc, kSeThreads, 0, st>>>(ws.partial, npix / MM, 1.0f / (float)npix, w, ws.scale);
     }
     BALF_COUNT_LAUNCH(4);
     BALF_LAUNCH_OK();
@@ -558,7 +578,7 @@ template <int C>
 static int run_se(const Workspace& ws, const DownW& w, int Bc, int npix, int parts, cudaStream_t st) {
     {
         ProfScope p("det_se", st);
-        se_kernel<C><<<Bc, C, 0, st>>>(ws.partial, parts, 1.0f / (float)npix, w, ws.scale);
+        se_kernel<C><<<Bc, kSeThreads, 0, st>>>(ws.partial, parts, 1.0f / (float)npix, w, ws.scale);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();

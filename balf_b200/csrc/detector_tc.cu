@@ -112,49 +112,79 @@ __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
         off += bytes;
     }
 }
-__device__ __forceinline__ uint32_t resident_off(const TcPlan& p, int gi) {
-    uint32_t off = 0;
-    for (int i = 0; i < gi; ++i) off += gemm_bytes(p.g[i]);
-    return off;
+// ---- compile-time plans.  Every GEMM of a kernel is fixed by its template parameters, so thread 0's issue path is
+// straight-line code: descriptors are a per-kernel base plus immediates instead of per-MMA address arithmetic
+// (the serial issue path sits on the critical path of every phase of every tile).  Must mirror tc_build_plans.
+template <int CIN, int C> struct BranchG {
+    static constexpr int count = BG_COUNT;
+    static constexpr bool resident = C <= 32;
+    __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
+    __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
+    __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
+};
+template <int CIN, int C> struct MergeG {
+    static constexpr int count = MG_COUNT;
+    static constexpr bool resident = C <= 32;
+    __host__ __device__ static constexpr int rows(int) { return C; }
+    __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
+    __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
+};
+template <int C> struct HeadG {
+    static constexpr int count = HG_COUNT;
+    static constexpr bool resident = false;
+    __host__ __device__ static constexpr int rows(int gi) { return gi == HG_DENSE ? kHeadN : C; }
+    __host__ __device__ static constexpr int K(int) { return C; }
+    __host__ __device__ static constexpr bool bias(int) { return true; }
+};
+template <typename G> __host__ __device__ constexpr uint32_t g_bytes(int gi) { return (uint32_t)G::rows(gi) * (G::K(gi) + (G::bias(gi) ? 8 : 0)) * 4u; }
+template <typename G> __host__ __device__ constexpr uint32_t g_off(int gi) { uint32_t o = 0; for (int i = 0; i < gi; ++i) o += g_bytes<G>(i); return o; }
+
+// high word of a SWIZZLE_NONE descriptor (SBO = 128, version 1) -- the low word is (LBO >> 4) << 16 | addr >> 4
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t desc_of(uint32_t addr, uint32_t lbo) {
+    return ((uint64_t)kDescHi << 32) | (uint64_t)(((lbo >> 4) << 16) | ((addr >> 4) & 0x3FFFu));
 }
 
-// Thread 0: D[128 x N] (+)= A[128 x K] * W^T (+ bias).  A: chunk-major at shared address a_addr with
-// a_rows physical rows; W: gemm gi of the plan (rows == N); ones_addr: the constant [1 1 0 ..] operand.
-__device__ __forceinline__ void issue_linear(Ring& r, const TcPlan& p, int gi, uint32_t a_addr, uint32_t a_rows,
-                                             uint32_t ones_addr, uint32_t d_tmem, bool first) {
-    const TcGemm& g = p.g[gi];
-    const uint32_t idesc = make_idesc_tf32(128, g.rows);
-    const uint32_t a_lbo = a_rows * 16u, b_lbo = (uint32_t)g.rows * 16u;
-    const uint32_t res_base = p.resident ? r.wsm + resident_off(p, gi) : 0u;
-    for (uint32_t b = 0; b < g.nblk; ++b) {
+// Thread 0: D[128 x N] (+)= A[128 x K] * W^T (+ bias) for GEMM GI of plan G (see issue_linear).
+template <typename G, int GI>
+__device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_t a_addr, uint32_t ones_addr, uint32_t d_tmem, bool first) {
+    constexpr int ROWS = G::rows(GI), K = G::K(GI);
+    constexpr bool BIAS = G::bias(GI);
+    constexpr int KB = tc_kb(ROWS, K), NBLK = K / KB;
+    constexpr uint32_t idesc = make_idesc_tf32(128, ROWS);
+    constexpr uint32_t a_lbo = TM * 16u, b_lbo = (uint32_t)ROWS * 16u;
+    const uint64_t a_desc = desc_of(a_addr, a_lbo);
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
         uint32_t w_addr, slot = 0;
-        if (p.resident) {
-            w_addr = res_base + b * (uint32_t)g.rows * g.kb * 4u;
+        if (G::resident) {
+            w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * 4u;
         } else {
             ring_top_up(r, p);
             slot = r.ccnt % kNSlot;
             mbar_wait(&r.full[slot], (r.ccnt / kNSlot) & 1);
             w_addr = r.wsm + slot * p.slot_bytes;
         }
+        const uint64_t b_desc = desc_of(w_addr, b_lbo);
         fence_after_sync();
-        for (uint32_t k8 = 0; k8 < (uint32_t)g.kb / 8u; ++k8) {
-            const uint32_t kchunk = (b * g.kb) / 4u + k8 * 2u;
-            mma_tf32(d_tmem, make_desc(a_addr + kchunk * a_lbo, a_lbo, 128), make_desc(w_addr + k8 * 2u * b_lbo, b_lbo, 128),
-                     idesc, !(first && b == 0 && k8 == 0));
+#pragma unroll
+        for (int k8 = 0; k8 < KB / 8; ++k8) {
+            const uint32_t kchunk = (uint32_t)(b * KB) / 4u + (uint32_t)k8 * 2u;
+            mma_tf32(d_tmem, a_desc + ((kchunk * a_lbo) >> 4), b_desc + (((uint32_t)k8 * 2u * b_lbo) >> 4), idesc,
+                     !(first && b == 0 && k8 == 0));
         }
-        if (g.bias && b + 1 == g.nblk)
-            mma_tf32(d_tmem, make_desc(ones_addr, TM * 16u, 128), make_desc(w_addr + ((uint32_t)g.kb / 4u) * b_lbo, b_lbo, 128), idesc, true);
-        if (!p.resident) { commit(&r.empty[slot]); ++r.ccnt; }
+        if (BIAS && b + 1 == NBLK)
+            mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / 4u) * b_lbo) >> 4), idesc, true);
+        if (!G::resident) { commit(&r.empty[slot]); ++r.ccnt; }
     }
 }
 
-// Thread 0: token mixing of both units.  A = mixing matrix (gemm gi, 64 x 64, one block); B = unit u's
-// activations [C rows][64 tokens] chunk-major with cp physical rows at y_addr + u * y_stride.
-__device__ __forceinline__ void issue_mix(Ring& r, const TcPlan& p, int gi, uint32_t y_addr, uint32_t y_stride, uint32_t cp,
-                                          int C, uint32_t d_tmem) {
+// Thread 0: token mixing of both units (see issue_mix), GEMM GI = the 64 x 64 mixing matrix.
+template <typename G, int GI, int C, int CP>
+__device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y_addr, uint32_t y_stride, uint32_t d_tmem) {
     uint32_t w_addr, slot = 0;
-    if (p.resident) {
-        w_addr = r.wsm + resident_off(p, gi);
+    if (G::resident) {
+        w_addr = r.wsm + g_off<G>(GI);
     } else {
         ring_top_up(r, p);
         slot = r.ccnt % kNSlot;
@@ -162,27 +192,38 @@ __device__ __forceinline__ void issue_mix(Ring& r, const TcPlan& p, int gi, uint
         w_addr = r.wsm + slot * p.slot_bytes;
     }
     fence_after_sync();
-    const uint32_t idesc = make_idesc_tf32(64, C);
-    const uint32_t b_lbo = cp * 16u;
-    for (uint32_t u = 0; u < 2; ++u)
+    constexpr uint32_t idesc = make_idesc_tf32(64, C);
+    constexpr uint32_t b_lbo = (uint32_t)CP * 16u;
+    const uint64_t w_desc = desc_of(w_addr, 1024u);
+#pragma unroll
+    for (uint32_t u = 0; u < 2; ++u) {
+        const uint64_t y_desc = desc_of(y_addr + u * y_stride, b_lbo);
+#pragma unroll
         for (uint32_t k8 = 0; k8 < 8; ++k8)
-            mma_tf32(d_tmem + ((u * 16u) << 16), make_desc(w_addr + k8 * 2u * 1024u, 1024, 128),
-                     make_desc(y_addr + u * y_stride + k8 * 2u * b_lbo, b_lbo, 128), idesc, k8 > 0);
-    if (!p.resident) { commit(&r.empty[slot]); ++r.ccnt; }
+            mma_tf32(d_tmem + ((u * 16u) << 16), w_desc + ((k8 * 2u * 1024u) >> 4), y_desc + ((k8 * 2u * b_lbo) >> 4), idesc, k8 > 0);
+    }
+    if (!G::resident) { commit(&r.empty[slot]); ++r.ccnt; }
 }
 
 // ------------------------------------------------------------------------------------------ epilogue pieces
-// exact-erf GELU: v * Phi(v), erfc(t) = exp2(t * P(t)) on t = |v| / sqrt(2) in [0, 4]
+// exact-erf GELU: gelu(v) = max(v, 0) - a * e,  a = |v|,  e = 0.5 erfc(a / sqrt(2)) = exp2(R(a)) with R a degree-6
+// polynomial (R(0) = -1; scripts/fit_gelu.py, |err| < 3.1e-7 absolute).  a is clamped to 4 sqrt(2), where e < 1e-8.
+// 10 instructions: 2 FMNMX, 7 FFMA (immediate coefficients), 1 MUFU.EX2.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_erf(float v) {
-    const float t = fminf(fabsf(v) * 0.70710678118654752440f, 4.0f);
-    float p = 2.576425322e-04f;
-    p = fmaf(p, t, -4.260182846e-03f);
-    p = fmaf(p, t, 3.200358897e-02f);
-    p = fmaf(p, t, -1.506087184e-01f);
-    p = fmaf(p, t, -9.178448915e-01f);
-    p = fmaf(p, t, -1.627962232e+00f);
-    const float h = (0.5f * v) * exp2f(p * t);        // 0.5 v erfc(t), carries the sign of v
-    return fmaxf(v, 0.0f) - fabsf(h);                 // v < 0: h;  v >= 0: v - h
+    const float a = fminf(fabsf(v), 5.6568542494923806f);
+    float p = 3.220531653e-05f;
+    p = fmaf(p, a, -7.531010197e-04f);
+    p = fmaf(p, a, 8.000897244e-03f);
+    p = fmaf(p, a, -5.324822292e-02f);
+    p = fmaf(p, a, -4.589224458e-01f);
+    p = fmaf(p, a, -1.151143193e+00f);
+    p = fmaf(p, a, -1.0f);
+    return fmaf(-a, ex2_approx(p), fmaxf(v, 0.0f));
 }
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
 
@@ -304,8 +345,11 @@ __device__ __forceinline__ void sync_for_mma() {
     __syncthreads();
     fence_after_sync();
 }
+// One thread polls the mbarrier; everybody else parks on the (hardware-blocking) CTA barrier instead of
+// spinning -- 255 spinning threads per CTA took ~40 % of the SM's issue slots away from co-resident CTAs.
 __device__ __forceinline__ void wait_done(uint64_t* done, uint32_t& phase) {
-    mbar_wait(done, phase & 1);
+    if (threadIdx.x == 0) mbar_wait(done, phase & 1);
+    __syncthreads();
     ++phase;
     fence_after_sync();
 }
@@ -364,6 +408,7 @@ __global__ void __launch_bounds__(NT2, BranchCfg<C>::min_ctas)
 tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = BranchCfg<C>;
+    using G = BranchG<CIN, C>;
     constexpr int CH = Cfg::CH;
     const TcShared s = carve(smem, Cfg::region, plan);
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
@@ -391,7 +436,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
         load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, BG_CONV0, region_addr, TM, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         wait_done(s.done, phase);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
@@ -405,7 +450,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         }
         sync_for_mma();
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
-        if (tid == 0) { issue_linear(ring, plan, BG_PD1, region_addr, TM, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
         wait_done(s.done, phase);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
@@ -425,8 +470,8 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         sync_for_mma();
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
         if (tid == 0) {
-            issue_linear(ring, plan, BG_D1A, region_addr, TM, ones_addr, tm + Cfg::col_y, true);
-            issue_linear(ring, plan, BG_D1B, region_addr, TM, ones_addr, tm + Cfg::col_y + C, true);
+            issue_linear_t<G, BG_D1A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true);
+            issue_linear_t<G, BG_D1B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y + C, true);
             commit(s.done);
         }
         wait_done(s.done, phase);
@@ -447,7 +492,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         }
         sync_for_mma();
         // ---- token mixing, gating y1 * (y2' + 1)
-        if (tid == 0) { issue_mix(ring, plan, BG_WM, region_addr, Cfg::y_stride, Cfg::CP, C, tm + Cfg::col_y + C); commit(s.done); }
+        if (tid == 0) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
         wait_done(s.done, phase);
         {
             constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
@@ -463,7 +508,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         }
         sync_for_mma();
         // ---- dense2 + residual u -> out
-        if (tid == 0) { issue_linear(ring, plan, BG_D2, region_addr, TM, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         wait_done(s.done, phase);
         {
             constexpr int SC = CH > 64 ? 64 : CH;
@@ -504,6 +549,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                 const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = MergeCfg<C>;
+    using G = MergeG<CIN, C>;
     constexpr int CH = Cfg::CH;
     (void)w;
     const TcShared s = carve(smem, Cfg::region, plan);
@@ -529,7 +575,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- x0 = ReLU(conv.0(x)), parked
         load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_CONV0, region_addr, TM, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
 #pragma unroll
@@ -538,11 +584,11 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
         load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_PD2A, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, MG_PD2B, region_addr, TM, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
         wait_done(s.done, phase);
         // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
         {
@@ -569,7 +615,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         }
         sync_for_mma();
         // ---- conv1 -> LeakyReLU(0.2)
-        if (tid == 0) { issue_linear(ring, plan, MG_RC1, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, MG_RC1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -577,7 +623,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         row_to_a<CH>(v, s.region, row, col0);
         sync_for_mma();
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
-        if (tid == 0) { issue_linear(ring, plan, MG_RC2, region_addr, TM, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<G, MG_RC2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -646,7 +692,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
             *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = to_tf32(o);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, HG_C2, region_addr, TM, ones_addr, tm, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
         wait_done(s.done, phase);
         {
             float v[CH];
@@ -656,7 +702,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
             row_to_a<CH>(v, s.region, row, col0);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear(ring, plan, HG_DENSE, region_addr, TM, ones_addr, tm + C, true); commit(s.done); }
+        if (tid == 0) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
         wait_done(s.done, phase);
         // logits = columns C .. C+64 of the row.  tcgen05.ld is warp-collective and `half` is warp-uniform, so the
         // branch below is convergent per warp.
@@ -746,6 +792,20 @@ static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias) {
     p.bytes += gemm_bytes(g);
     const uint32_t big = (gemm_block_bytes(g, g.nblk - 1) + 127u) / 128u * 128u;
     if (big > p.slot_bytes) p.slot_bytes = big;
+}
+
+template <typename G>
+static bool plan_matches(const TcPlan& p) {
+    if (p.ngemm != G::count || (p.resident != 0) != G::resident) return false;
+    uint32_t off = 0;
+    bool ok = true;
+    for (int gi = 0; gi < G::count; ++gi) {
+        const TcGemm& g = p.g[gi];
+        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi)) && g.nblk * g.kb == G::K(gi) &&
+             (g.bias != 0) == G::bias(gi) && gemm_bytes(g) == g_bytes<G>(gi) && (g.goff - p.g[0].goff) * 4u == off;
+        off += gemm_bytes(g);
+    }
+    return ok;
 }
 
 static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPlans* out) {
@@ -871,6 +931,8 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64)};
     const int ntiles = (g.total_units + 1) / 2;
     int grid = 0;
+    BALF_REQUIRE((plan_matches<BranchG<CIN, C>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C>>(P.branch[level][1]) &&
+                  plan_matches<MergeG<CIN, C>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
     for (int b = 0; b < 2; ++b) {
         const TcPlan& p = P.branch[level][b];
         const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p);
@@ -918,6 +980,7 @@ int tc_run_head(const float* r, const float* q, const float* scale, const DownW&
     const int ntiles = (g.total_units + 1) / 2;
     const size_t smem = tc_smem_bytes((uint32_t)TM * 256 * 4, P.head);
     int grid = 0;
+    BALF_REQUIRE(plan_matches<HeadG<256>>(P.head), "internal: compile-time and packed GEMM plans differ (head)");
     if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
     {
         ProfScope ps("det_head", st);

@@ -31,3 +31,20 @@ for deg in (6, 7, 8, 9):
     rel = abs_err / np.maximum(np.abs(exact), 1e-6)
     print("deg %d: max abs %.3e (at v=%.3f)  max rel(|exact|>1e-6) %.3e" % (deg, abs_err.max(), v[abs_err.argmax()], rel[np.abs(exact) > 1e-6].max()))
     print("   coeffs:", ", ".join("%.9ef" % x for x in c32))
+
+# ---- the form the kernels evaluate (csrc/detector_tc.cu: gelu_erf): constants absorbed so that the epilogue needs
+# no FMUL:  a = min(|v|, 4 sqrt 2),  R(a) = -1 + sum_i c_i s^(i+1) a^(i+1)  (s = 1/sqrt 2, c = the degree-6 fit above),
+# gelu(v) = max(v, 0) - a * exp2(R(a)).
+c6 = np.array([-1.627962232e+00, -9.178448915e-01, -1.506087184e-01, 3.200358897e-02, -4.260182846e-03, 2.576425322e-04])
+s = 1 / np.sqrt(2)
+d = np.array([c6[i] * s ** (i + 1) for i in range(6)]).astype(np.float32)
+print("absorbed coefficients (a^1 .. a^6):", ", ".join("%.9ef" % x for x in d))
+v = np.linspace(-9, 9, 2000001).astype(np.float32)
+a = np.minimum(np.abs(v), np.float32(4 * np.sqrt(2))).astype(np.float32)
+p = np.full_like(a, d[5])
+for ci in list(d[4::-1]) + [np.float32(-1.0)]:
+    p = (p * a + ci).astype(np.float32)
+e = np.exp2(p.astype(np.float64)).astype(np.float32)
+g = (np.maximum(v, 0) - (a * e).astype(np.float32)).astype(np.float32)
+exact = 0.5 * v.astype(np.float64) * (1 + erf(v.astype(np.float64) / np.sqrt(2)))
+print("absorbed form: max abs err %.3e" % np.abs(g - exact).max())
