@@ -76,6 +76,7 @@ def profile_report(reset=True):
 
 
 debug_set = _sig("balf_debug_set", c_int, c_int, c_int)
+debug_set_trace = _sig("balf_debug_set_trace", c_int, c_void_p)
 
 
 def declared_symbols():

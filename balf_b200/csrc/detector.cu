@@ -535,7 +535,8 @@ static size_t ws_layout(const balf_detector_arch& a, int Bc, int Hp, int Wp, voi
 
 int g_tc_mask = 0x1F;              // debug hook (balf_debug_set key 0): bit l = stage l on the tensor-core path, bit 4 = head
 
-constexpr int kChunkImages = 8;   // images per internal pass: bounds the workspace, keeps stage outputs near L2
+int g_chunk_images = 16;           // images per internal pass (bounds the workspace; debug hook key 1).  16 keeps the
+                                   // persistent grids of the two coarsest stages at >= 4 tiles per SM (tail effect)
 
 template <typename K> static int set_smem(K kernel, size_t bytes) {
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -602,8 +603,9 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
 using namespace balf;
 
 extern "C" int balf_debug_set(int key, int value) {
-    BALF_REQUIRE(key == 0, "unknown debug key %d", key);
-    g_tc_mask = value & 0x1F;
+    BALF_REQUIRE(key == 0 || key == 1, "unknown debug key %d", key);
+    if (key == 0) g_tc_mask = value & 0x1F;
+    else { BALF_REQUIRE(value >= 1 && value <= 64, "chunk must be in [1, 64]"); g_chunk_images = value; }
     return 0;
 }
 
@@ -671,7 +673,7 @@ extern "C" int balf_detector_pack_weights(const balf_detector_arch* arch, const 
 
 extern "C" size_t balf_detector_workspace_bytes(const balf_detector_arch* arch, int B, int Hp, int Wp) {
     if (check_arch(arch) || B <= 0 || Hp <= 0 || Wp <= 0) return 0;
-    return ws_layout(*arch, B < kChunkImages ? B : kChunkImages, Hp, Wp, nullptr, nullptr);
+    return ws_layout(*arch, B < g_chunk_images ? B : g_chunk_images, Hp, Wp, nullptr, nullptr);
 }
 
 extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float* packed, const float* x, int B, int Hp,
@@ -684,7 +686,7 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
                  "(3 max-pools x 8x8 grid/block tokens; pad with mod_padding_symmetric)", Hp, Wp);
     BALF_REQUIRE(precision == 0 || precision == 1, "precision %d is not built in this library (0 = fp32, 1 = tf32)", precision);
     const balf_detector_arch& a = *arch;
-    const int chunk = B < kChunkImages ? B : kChunkImages;
+    const int chunk = B < g_chunk_images ? B : g_chunk_images;
     BALF_REQUIRE(workspace_bytes >= ws_layout(a, chunk, Hp, Wp, nullptr, nullptr), "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DetW w;

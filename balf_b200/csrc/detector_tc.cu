@@ -54,7 +54,16 @@ struct TcPlan {
     int resident;         // all blocks stay in shared memory for the life of the CTA
     uint32_t bytes;       // total bytes of all blocks (resident footprint)
     uint32_t slot_bytes;  // ring slot size (largest block, 128-byte multiple)
+    long long* trace;     // development hook (balf_debug_set_trace): clock stamps of CTA 0, or null
 };
+long long* g_tc_trace = nullptr;
+constexpr int kTracePoints = 16, kTraceTiles = 16;
+// stamp `pt` of tile iteration `it` for thread 0 (slot 0: the MMA issuer) and the last thread (slot 1: pure epilogue)
+#define TC_TRACE(plan, it, pt)                                                                                     \
+    do {                                                                                                           \
+        if ((plan).trace && blockIdx.x == 0 && (it) < kTraceTiles && (threadIdx.x == 0 || threadIdx.x == NT2 - 1)) \
+            (plan).trace[(((it) * kTracePoints + (pt)) << 1) + (threadIdx.x ? 1 : 0)] = clock64();                 \
+    } while (0)
 
 enum { BG_CONV0 = 0, BG_PD1, BG_D1A, BG_D1B, BG_WM, BG_D2, BG_COUNT };
 enum { MG_CONV0 = 0, MG_PD2A, MG_PD2B, MG_RC1, MG_RC2, MG_COUNT };
@@ -310,7 +319,7 @@ __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_b
     return s;
 }
 
-__device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, Ring& ring, const TcPlan& plan, uint32_t my_tiles) {
+__device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, Ring& ring, const TcPlan& plan, uint32_t my_tiles, bool w0) {
     if (threadIdx.x < 32) tmem_alloc(s.tmem_slot, ncols);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNSlot; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -328,7 +337,7 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
     uint32_t nb = 0;
     for (int i = 0; i < plan.ngemm; ++i) nb += plan.g[i].nblk;
     ring.to_load = nb * my_tiles;
-    if (threadIdx.x == 0) {
+    if (w0 && elect_one()) {      // the elected lane of warp 0 owns the ring state and issues every MMA
         if (plan.resident) { ring_load_all(ring, plan); mbar_wait(&s.full[0], 0); }
         else ring_top_up(ring, plan);
     }
@@ -417,7 +426,8 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     const DownW::Branch& br = w.br[BR];
     for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
     Ring ring;
-    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles);
+    const bool w0 = warp0_uniform();
+    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);        // this warp's 32-lane window
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -426,7 +436,9 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     const float mix_b1 = __ldg(br.gd_b + tok) + 1.0f;
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        TC_TRACE(plan, it, 0);
         const int unit = 2 * t + ug;
         const bool valid = unit < geo.total_units;
         const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
@@ -435,9 +447,12 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         float v[CH], rstd, shift;
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
         load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        TC_TRACE(plan, it, 1);
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        TC_TRACE(plan, it, 2);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 3);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
             float sum = 0.f, sq = 0.f;
@@ -448,10 +463,13 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
+        TC_TRACE(plan, it, 4);
         sync_for_mma();
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
-        if (tid == 0) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
+        TC_TRACE(plan, it, 5);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 6);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
             float sum = 0.f, sq = 0.f;
@@ -467,14 +485,17 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
+        TC_TRACE(plan, it, 7);
         sync_for_mma();
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
-        if (tid == 0) {
+        if (w0 && elect_one()) {
             issue_linear_t<G, BG_D1A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true);
             issue_linear_t<G, BG_D1B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y + C, true);
             commit(s.done);
         }
+        TC_TRACE(plan, it, 8);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
 #pragma unroll
@@ -490,10 +511,13 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             for (int i = 0; i < CH; ++i)
                 yt[(size_t)i * 4] = to_tf32(fmaf(fmaf(v[i], rstd, shift), s.vec[col0 + i], s.vec[256 + col0 + i]));
         }
+        TC_TRACE(plan, it, 10);
         sync_for_mma();
         // ---- token mixing, gating y1 * (y2' + 1)
-        if (tid == 0) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
+        if (w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
+        TC_TRACE(plan, it, 11);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 12);
         {
             constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
 #pragma unroll 1
@@ -506,10 +530,13 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                 row_to_a<SC>(y2, s.region, row, col0 + c);
             }
         }
+        TC_TRACE(plan, it, 13);
         sync_for_mma();
         // ---- dense2 + residual u -> out
-        if (tid == 0) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        TC_TRACE(plan, it, 14);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 15);
         {
             constexpr int SC = CH > 64 ? 64 : CH;
 #pragma unroll 1
@@ -557,7 +584,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
-    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles);
+    const bool w0 = warp0_uniform();
+    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -575,7 +603,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- x0 = ReLU(conv.0(x)), parked
         load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
 #pragma unroll
@@ -584,11 +612,11 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
         load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
         wait_done(s.done, phase);
         // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
         {
@@ -615,7 +643,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         }
         sync_for_mma();
         // ---- conv1 -> LeakyReLU(0.2)
-        if (tid == 0) { issue_linear_t<G, MG_RC1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -623,7 +651,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         row_to_a<CH>(v, s.region, row, col0);
         sync_for_mma();
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
-        if (tid == 0) { issue_linear_t<G, MG_RC2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done(s.done, phase);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -665,7 +693,8 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
-    tc_prologue(s, ncols, ring, plan, my_tiles);
+    const bool w0 = warp0_uniform();
+    tc_prologue(s, ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -692,7 +721,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
             *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = to_tf32(o);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
         wait_done(s.done, phase);
         {
             float v[CH];
@@ -702,7 +731,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
             row_to_a<CH>(v, s.region, row, col0);
         }
         sync_for_mma();
-        if (tid == 0) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
         wait_done(s.done, phase);
         // logits = columns C .. C+64 of the row.  tcgen05.ld is warp-collective and `half` is warp-uniform, so the
         // branch below is convergent per warp.
@@ -840,6 +869,8 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
     tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true);
     tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true);
     P.floats = off;
+    for (int l = 0; l < 4; ++l) P.branch[l][0].trace = P.branch[l][1].trace = P.merge[l].trace = g_tc_trace;
+    P.head.trace = g_tc_trace;
     if (out) *out = P;
 }
 
@@ -992,3 +1023,8 @@ int tc_run_head(const float* r, const float* q, const float* scale, const DownW&
 }
 
 }  // namespace balf
+
+extern "C" int balf_debug_set_trace(void* buf) {
+    balf::g_tc_trace = static_cast<long long*>(buf);
+    return 0;
+}

@@ -61,6 +61,18 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- single-lane election.  tcgen05.mma / commit / bulk copies take uniform-register operands; when the issuing
+// code is guarded by a warp-uniform test plus elect.sync, ptxas knows exactly one lane is active and moves operands
+// with plain R2UR.  Guarded by `threadIdx.x == 0` instead it emits a waterfall loop (ELECT / R2UR.BROADCAST /
+// BRA.U.ANY) around every instruction -- measured at 60-80 cycles per MMA on the critical path.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// true in warp 0, and known to the compiler as warp-uniform (the shuffle broadcasts lane 0's value)
+__device__ __forceinline__ bool warp0_uniform() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0; }
+
 // ---- TMEM allocation (one full warp executes these)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");

@@ -88,8 +88,12 @@ BALF_API int balf_detector_forward(const balf_detector_arch* arch, const float* 
                           int Wp, float* logits, float* prob, void* workspace, size_t workspace_bytes,
                           int precision, void* stream);
 /* development hook, no reference counterpart: key 0 = bit mask of detector stages that run on the tensor-core
- * kernels when precision = 1 (bits 0-3: the four Down stages, bit 4: the head; default all). */
+ * kernels when precision = 1 (bits 0-3: the four Down stages, bit 4: the head; default all); key 1 = images per
+ * internal pass of balf_detector_forward (default 16; query the workspace size again after changing it). */
 BALF_API int balf_debug_set(int key, int value);
+/* development hook: `buf` = device buffer of 8192 int64 (or NULL to switch off).  While set, CTA 0 of every tensor-core
+ * detector kernel records SM-clock stamps of its first tiles' phases there (scripts/tc_trace.py reads them). */
+BALF_API int balf_debug_set_trace(void* buf);
 /* stand-alone depth-to-space (balf/utils/tensor_op.py:1-27): in [N,C,H,W] -> out [N,C/r^2,H*r,W*r] */
 BALF_API int balf_pixel_shuffle(const float* in, float* out, int N, int C, int H, int W, int r, void* stream);
 
