@@ -14,6 +14,7 @@
 // shared-memory halo tile), the window maximum is separable (row pass with lanes on rows, column
 // pass with lanes on columns, log-step doubling networks in registers), survivors are compacted
 // as 64-bit (score, ~raster) keys, and one CTA per image does radix-select + bitonic sort.
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/balf_b200.h"
 
@@ -162,6 +163,192 @@ __global__ void __launch_bounds__(256) windowed_nms_kernel(MapView mv, NmsWs ws)
         }
     };
     run_tile<LO, HI, float>(smem, ty0, tx0, mv.H, mv.W, load, emit);
+}
+
+// ------------------------------------------------------------------------------------------ windowed NMS, 15 x 15
+// The default window (nms_size 15, +-7) runs as a two-level prune instead of a dense window maximum: the dense
+// separable form costs ~20 instructions per pixel, which on B200 is already the whole HBM budget (23 B/cycle/SM =
+// 22 thread-instructions per fp32 pixel), while NMS survivors are ~1 % of the pixels.  One kernel, one CTA per
+// 64 x 64 output tile:
+//   1  the tile plus an 8-pixel halo is read once with coalesced 128-bit loads, border-masked, and kept in shared
+//      memory as integers: only positive scores can survive (apply_nms keeps zeros at zero, the selection takes
+//      positive keys) and for positive floats the IEEE bit pattern is monotonic, so every value is max(bits, 0);
+//   2  maxima of the aligned 4 x 4 blocks (20 x 20 per tile, DPX three-input maximum);
+//   3  coarse test, one thread per inner block.  With y = 4 by + r the window rows y-7 .. y+7 always contain block
+//      rows by-1 .. by+1 and are contained in by-2 .. by+2, so
+//        own <  max(3 x 3 blocks)  -> no pixel of the block survives            (8/9 of the blocks stop here)
+//        own >= max(5 x 5 blocks)  -> every pixel equal to own survives
+//        otherwise                 -> exact test against the ring blocks whose maximum exceeds own (usually 1-2);
+//   4  candidates are compacted and finished with four lanes each, entirely from shared memory;
+//   5  survivors are staged per CTA and appended to the image's key list with ONE global atomic (same-address
+//      atomics from every warp measured ~3x slower end to end).
+// The score map is read from HBM exactly once; halos (1.56x) are served by L2.
+constexpr int kNmsB = 4, kNmsR = 7;
+static_assert(kNmsR == 7 && kNmsB == 4, "the 3x3 / 5x5 block bounds below are derived for a +-7 window and 4x4 blocks");
+constexpr int kNmsTile = 64, kNmsHalo = 8, kNmsIn = kNmsTile + 2 * kNmsHalo;       // 80 x 80 pixels in shared memory
+constexpr int kNmsNB = kNmsIn / kNmsB, kNmsInner = kNmsTile / kNmsB;              // 20 x 20 blocks, 16 x 16 inner
+constexpr int kNmsListCap = 512;                                                    // survivors staged per CTA
+
+// interior test of remove_borders as two unsigned compares
+struct Interior {
+    int b0;
+    unsigned hh, ww;      // H - 2 border, W - 2 border (0 when the border swallows the map)
+    __device__ __forceinline__ bool yok(int y) const { return (unsigned)(y - b0) < hh; }
+    __device__ __forceinline__ bool xok(int x) const { return (unsigned)(x - b0) < ww; }
+};
+__device__ __forceinline__ Interior interior_of(const MapView& mv) {
+    return Interior{mv.border, (unsigned)max(mv.H - 2 * mv.border, 0), (unsigned)max(mv.W - 2 * mv.border, 0)};
+}
+
+__global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int vec_ok) {
+    __shared__ __align__(16) int px[kNmsIn][kNmsIn];
+    __shared__ int cmax[kNmsNB][kNmsNB + 1];
+    __shared__ uint32_t cand[kNmsInner * kNmsInner];       // lby | lbx << 8 | sure << 16
+    __shared__ u64 surv[kNmsListCap];
+    __shared__ int n_cand, n_surv, g_base;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kNmsTile, ty0 = blockIdx.y * kNmsTile;
+    const int tid = threadIdx.x, sub = tid & 3;
+    const Interior in = interior_of(mv);
+    if (tid == 0) { n_cand = 0; n_surv = 0; }
+    // ---- 1: tile + halo -> shared memory
+    const int* img = reinterpret_cast<const int*>(mv.score) + ((size_t)b * mv.Hs + mv.top) * mv.Ws + mv.left;   // crop origin, raw bits
+    // (all of a thread's loads are issued before the first one is consumed: one HBM round trip per CTA, not seven)
+    constexpr int kQuads = kNmsIn * (kNmsIn / 4), kIter = (kQuads + 255) / 256;
+    int4 v[kIter];
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+        const int i = tid + 256 * k;
+        const int row = i / (kNmsIn / 4), c4 = i - row * (kNmsIn / 4);
+        const int gy = ty0 - kNmsHalo + row, gx = tx0 - kNmsHalo + 4 * c4;
+        v[k] = make_int4(0, 0, 0, 0);
+        if (i < kQuads && in.yok(gy) && gx + 3 >= in.b0 && gx < mv.W - in.b0) {
+            const int* src = img + (size_t)gy * mv.Ws + gx;
+            if (vec_ok && gx >= 0 && gx + 3 < mv.W) v[k] = __ldg(reinterpret_cast<const int4*>(src));
+            else {
+                if (gx >= 0 && gx < mv.W) v[k].x = __ldg(src);
+                if (gx + 1 >= 0 && gx + 1 < mv.W) v[k].y = __ldg(src + 1);
+                if (gx + 2 >= 0 && gx + 2 < mv.W) v[k].z = __ldg(src + 2);
+                if (gx + 3 >= 0 && gx + 3 < mv.W) v[k].w = __ldg(src + 3);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+        const int i = tid + 256 * k;
+        const int row = i / (kNmsIn / 4), c4 = i - row * (kNmsIn / 4);
+        const int gx = tx0 - kNmsHalo + 4 * c4;
+        int4 o;
+        o.x = in.xok(gx) ? max(v[k].x, 0) : 0;
+        o.y = in.xok(gx + 1) ? max(v[k].y, 0) : 0;
+        o.z = in.xok(gx + 2) ? max(v[k].z, 0) : 0;
+        o.w = in.xok(gx + 3) ? max(v[k].w, 0) : 0;
+        if (i < kQuads) *reinterpret_cast<int4*>(&px[row][4 * c4]) = o;
+    }
+    __syncthreads();
+    // ---- 2: block maxima
+    for (int i = tid; i < kNmsNB * kNmsNB; i += 256) {
+        const int by = i / kNmsNB, bx = i - by * kNmsNB;
+        const int4 r0 = *reinterpret_cast<const int4*>(&px[4 * by][4 * bx]);
+        const int4 r1 = *reinterpret_cast<const int4*>(&px[4 * by + 1][4 * bx]);
+        const int4 r2 = *reinterpret_cast<const int4*>(&px[4 * by + 2][4 * bx]);
+        const int4 r3 = *reinterpret_cast<const int4*>(&px[4 * by + 3][4 * bx]);
+        int m = __vimax3_s32(r0.x, r0.y, r0.z);
+        m = __vimax3_s32(m, r0.w, r1.x);
+        m = __vimax3_s32(m, r1.y, r1.z);
+        m = __vimax3_s32(m, r1.w, r2.x);
+        m = __vimax3_s32(m, r2.y, r2.z);
+        m = __vimax3_s32(m, r2.w, r3.x);
+        m = __vimax3_s32(m, r3.y, r3.z);
+        cmax[by][bx] = max(m, r3.w);
+    }
+    __syncthreads();
+    // ---- 3: coarse test, one thread per inner block
+    {
+        const int ly = (tid >> 4) + 2, lx = (tid & 15) + 2;
+        const int own = cmax[ly][lx];
+        if (own > 0) {
+            int m3 = __vimax3_s32(cmax[ly - 1][lx - 1], cmax[ly - 1][lx], cmax[ly - 1][lx + 1]);
+            m3 = __vimax3_s32(m3, cmax[ly][lx - 1], cmax[ly][lx + 1]);
+            m3 = __vimax3_s32(m3, cmax[ly + 1][lx - 1], cmax[ly + 1][lx]);
+            m3 = max(m3, cmax[ly + 1][lx + 1]);
+            if (own >= m3) {
+                int m5 = 0;
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx) m5 = __vimax3_s32(m5, cmax[ly - 2][lx + dx], cmax[ly + 2][lx + dx]);
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) m5 = __vimax3_s32(m5, cmax[ly + dy][lx - 2], cmax[ly + dy][lx + 2]);
+                cand[atomicAdd(&n_cand, 1)] = (uint32_t)ly | ((uint32_t)lx << 8) | (own >= m5 ? 0x10000u : 0u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 4: finish the candidates, four lanes each (sub-lane s owns row s of a block)
+    const int nc = n_cand;
+    u64* gkeys = ws.keys + (size_t)b * ws.cap;
+    for (int base = 0; base < nc; base += 64) {
+        const int ci = base + (tid >> 2);
+        if ((ci & ~7) >= nc) continue;                      // this warp's eight candidate slots are empty (warp-uniform)
+        const bool live = ci < nc;
+        const uint32_t c = live ? cand[ci] : 0u;
+        const bool sure = (c & 0x10000u) != 0;
+        const int ly = live ? (int)(c & 0xFFu) : 2, lx = live ? (int)((c >> 8) & 0xFFu) : 2;
+        const int own = live ? cmax[ly][lx] : -1;
+        unsigned peaks = 0;
+        {
+            const int4 v = *reinterpret_cast<const int4*>(&px[4 * ly + sub][4 * lx]);
+            peaks = ((v.x == own ? 1u : 0u) | (v.y == own ? 2u : 0u) | (v.z == own ? 4u : 0u) | (v.w == own ? 8u : 0u)) << (4 * sub);
+        }
+        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 1);
+        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 2);
+        while (__any_sync(0xffffffffu, peaks != 0)) {
+            const bool act = peaks != 0;
+            const int j = act ? __ffs(peaks) - 1 : 0;
+            peaks &= peaks - 1;
+            const int r = j >> 2, cc = j & 3;
+            int wmax = 0;
+            if (act && !sure) {
+                // ring blocks whose maximum exceeds own; inside the window lie rows >= r+1 of block row -2, rows <= r-1
+                // of block row +2, columns >= cc+1 of block column -2, columns <= cc-1 of block column +2
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int dy = k < 5 ? -2 : k < 10 ? 2 : (k - 10) / 2 - 1;
+                    const int dx = k < 10 ? (k % 5) - 2 : ((k & 1) ? 2 : -2);
+                    if (cmax[ly + dy][lx + dx] > own) {
+                        const bool row_in = dy == -2 ? sub >= r + 1 : dy == 2 ? sub <= r - 1 : true;
+                        if (row_in) {
+                            const int4 v = *reinterpret_cast<const int4*>(&px[4 * (ly + dy) + sub][4 * (lx + dx)]);
+                            const int lo = dx == -2 ? cc + 1 : 0, hi = dx == 2 ? cc - 1 : 3;
+                            if (lo <= 0 && 0 <= hi) wmax = max(wmax, v.x);
+                            if (lo <= 1 && 1 <= hi) wmax = max(wmax, v.y);
+                            if (lo <= 2 && 2 <= hi) wmax = max(wmax, v.z);
+                            if (lo <= 3 && 3 <= hi) wmax = max(wmax, v.w);
+                        }
+                    }
+                }
+            }
+            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
+            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
+            if (act && sub == 0 && own >= wmax) {
+                const int y = ty0 - kNmsHalo + 4 * ly + r, x = tx0 - kNmsHalo + 4 * lx + cc;
+                const u64 key = make_key(__int_as_float(own), (uint32_t)(y * mv.W + x));   // own > 0: its bits are the score
+                const int slot = atomicAdd(&n_surv, 1);
+                if (slot < kNmsListCap) surv[slot] = key;
+                else {                                       // plateau: more survivors than the staging list holds
+                    const unsigned gs = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+                    if (gs < ws.cap) gkeys[gs] = key; else atomicOr(ws.flags + b, 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 5: one append per CTA
+    const int ns = min(n_surv, kNmsListCap);
+    if (tid == 0 && ns > 0) g_base = (int)atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), (unsigned)ns);
+    __syncthreads();
+    for (int i = tid; i < ns; i += 256) {
+        const size_t gs = (size_t)g_base + i;
+        if (gs < ws.cap) gkeys[gs] = surv[i]; else atomicOr(ws.flags + b, 1);
+    }
 }
 
 // any window size: one thread per pixel, window read through L1/L2 (small maps, unusual sizes)
@@ -498,6 +685,18 @@ static int launch_windowed(const MapView& mv, const NmsWs& ws, int B, cudaStream
     return 0;
 }
 
+// nms_size 15: the fused two-level kernel
+static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStream_t st) {
+    const int vec_ok = (mv.left % 4 == 0) && (mv.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(mv.score) % 16 == 0);
+    dim3 grid(cdiv(mv.W, kNmsTile), cdiv(mv.H, kNmsTile), B);
+    {
+        ProfScope p("nms_windowed", st);
+        nms15_kernel<<<grid, 256, 0, st>>>(mv, ws, vec_ok);
+    }
+    BALF_COUNT_LAUNCH(1);
+    return 0;
+}
+
 template <int R>
 static int launch_greedy(const NmsWs& ws, int B, int H, int W, int r, cudaStream_t st) {
     size_t smem = R > 0 ? Tile<(R > 0 ? R : 1), (R > 0 ? R : 1), u64>::smem_bytes : 0;
@@ -563,7 +762,7 @@ extern "C" int balf_windowed_nms_topk(const float* score, int B, int Hs, int Ws,
     BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
     const int lo = nms_size / 2, hi = (nms_size - 1) / 2;
     int e = 0;
-    if (nms_size == 15) e = launch_windowed<7, 7>(mv, ws, B, st);
+    if (nms_size == 15) e = launch_windowed15(mv, ws, B, st);
     else if (nms_size == 31) e = launch_windowed<15, 15>(mv, ws, B, st);
     else {
         dim3 grid(cdiv(W, 128), H, B);

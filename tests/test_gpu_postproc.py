@@ -194,3 +194,32 @@ def test_large_map_1200x900_topk_binds():
     assert len(want) == 2048
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(gpu_windowed(s, 8192, 15, 15)[0], postproc.windowed_detect(s, 15, 15, 8192))
+
+
+def test_windowed15_two_level_edge_cases():
+    """nms_size 15 runs as block-maximum + coarse-select passes (csrc/nms.cu): unaligned crops (scalar load path), sizes
+    that are not multiples of the 4x4 blocks, every border width, negative and zero scores, plateaus larger than the
+    per-CTA survivor staging list, and isolated peaks next to the map edge."""
+    rng = np.random.default_rng(23)
+    base = (rng.random((3, 200, 333), dtype=np.float32) - 0.2).astype(np.float32)          # ~20 % negative
+    base[1] = np.round(base[1] * 8) / 8                                                     # plateaus / ties
+    base[2] *= (rng.random((200, 333)) > 0.97)                                              # sparse, many zeros
+    for (top, left, H, W) in ((0, 0, 200, 333), (3, 5, 190, 321), (8, 4, 64, 128), (1, 2, 17, 29), (0, 1, 15, 15)):
+        for border in (0, 1, 7, 15):
+            if 2 * border >= min(H, W):
+                continue
+            k = min(2048, H * W)
+            got = gpu_windowed(base, k, border, 15, (top, left, H, W))
+            for b in range(3):
+                want = postproc.windowed_detect(base[b, top:top + H, left:left + W], border, 15, k)
+                np.testing.assert_array_equal(got[b], want, err_msg="crop %s border %d image %d" % ((top, left, H, W), border, b))
+    # one big plateau: every pixel of the interior survives (far more than the 512-entry staging list per tile)
+    flat = np.full((1, 96, 256), 0.25, np.float32)
+    for k in (100, 16384):
+        np.testing.assert_array_equal(gpu_windowed(flat, k, 2, 15)[0], postproc.windowed_detect(flat[0], 2, 15, k))
+    # peaks at the corners and edges, equal-valued neighbours exactly 7 and 8 pixels apart
+    m = np.zeros((1, 64, 64), np.float32)
+    for (y, x, v) in ((0, 0, 1.0), (0, 63, 1.0), (63, 0, 2.0), (63, 63, 0.5), (20, 20, 3.0), (20, 27, 3.0), (20, 35, 2.9),
+                      (27, 27, 3.0), (28, 28, 3.1), (40, 8, 1.0), (40, 16, 1.0), (47, 12, 1.0)):
+        m[0, y, x] = v
+    np.testing.assert_array_equal(gpu_windowed(m, 64, 0, 15)[0], postproc.windowed_detect(m[0], 0, 15, 64))
