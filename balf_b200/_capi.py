@@ -274,8 +274,8 @@ _patches = _sig("balf_extract_patches_u8", c_int, _P, c_int, c_int, c_int, _P, _
 _hn_raw = _sig("balf_hardnet_raw_weight_count", ctypes.c_int64)
 _hn_packed = _sig("balf_hardnet_packed_weight_count", ctypes.c_int64)
 _hn_pack = _sig("balf_hardnet_pack_weights", c_int, _P, _P, _P)
-_hn_ws = _sig("balf_hardnet_workspace_bytes", c_size_t, c_int)
-_hn_fwd = _sig("balf_hardnet_forward", c_int, _P, _P, c_int, _P, _P, c_size_t, _P)
+_hn_ws = _sig("balf_hardnet_workspace_bytes", c_size_t, c_int, c_int)
+_hn_fwd = _sig("balf_hardnet_forward", c_int, _P, _P, c_int, _P, _P, c_size_t, c_int, _P)
 _match_ws = _sig("balf_match_workspace_bytes", c_size_t, c_int, c_int)
 _match = _sig("balf_match_smnn", c_int, _P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_size_t, _P)
 
@@ -321,18 +321,24 @@ def hardnet_pack_weights(raw):
     return packed
 
 
-def hardnet_forward(patches, packed):
+HARDNET_PRECISIONS = {"fp32": 0, "tf32": 1}
+
+
+def hardnet_forward(patches, packed, precision="tf32"):
     """patches fp32 [N,1,32,32] CUDA -> descriptors fp32 [N,128]."""
+    if precision not in HARDNET_PRECISIONS:
+        raise ValueError("precision %r is not built (choose from %s)" % (precision, sorted(HARDNET_PRECISIONS)))
+    prec = HARDNET_PRECISIONS[precision]
     _need_cuda(patches, "the patches")
     patches = patches.contiguous().float()
     n = patches.shape[0]
     desc = torch.empty(n, 128, dtype=torch.float32, device=patches.device)
     if n == 0:
         return desc
-    nbytes = _hn_ws(n)
+    nbytes = _hn_ws(n, prec)
     ws = _workspace(patches.device, nbytes)
     with torch.cuda.device(patches.device):
-        _ok(_hn_fwd(_ptr(packed), _ptr(patches), n, _ptr(desc), _ptr(ws), nbytes, _stream(patches.device)))
+        _ok(_hn_fwd(_ptr(packed), _ptr(patches), n, _ptr(desc), _ptr(ws), nbytes, prec, _stream(patches.device)))
     return desc
 
 

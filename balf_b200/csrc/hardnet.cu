@@ -12,33 +12,10 @@
 // zero-haloed input in shared memory and computes register tiles of PX pixels x CH channels with the
 // folded BatchNorm + ReLU in the epilogue.  The 8x8 "valid" layer is a [patches x 8192] x [8192 x 128]
 // product followed by BatchNorm and the L2 normalisation.
-#include "common.cuh"
-#include "../../include/balf_b200.h"
+#include "hardnet.cuh"
 
 namespace balf {
 
-struct HnLayer { int cin, cout, hin, stride, ks; };
-static const HnLayer kHn[7] = {{1, 32, 32, 1, 3},  {32, 32, 32, 1, 3},  {32, 64, 32, 2, 3},  {64, 64, 16, 1, 3},
-                               {64, 128, 16, 2, 3}, {128, 128, 8, 1, 3}, {128, 128, 8, 1, 8}};
-
-struct HnW {
-    const float* w[7];       // [cin][ks*ks][cout]
-    const float* scale[7];   // 1 / sqrt(var + 1e-5)
-    const float* shift[7];   // -mean * scale
-};
-
-static size_t hn_walk(const float* base, HnW* out) {
-    size_t off = 0;
-    HnW w;
-    for (int l = 0; l < 7; ++l) {
-        const HnLayer& L = kHn[l];
-        w.w[l] = base + off; off += (size_t)L.cin * L.ks * L.ks * L.cout;
-        w.scale[l] = base + off; off += L.cout;
-        w.shift[l] = base + off; off += L.cout;
-    }
-    if (out) *out = w;
-    return off;
-}
 static size_t hn_raw_count() {
     size_t n = 0;
     for (int l = 0; l < 7; ++l) n += (size_t)kHn[l].cin * kHn[l].ks * kHn[l].ks * kHn[l].cout + 2 * kHn[l].cout;
@@ -201,12 +178,22 @@ static int hn_launch_conv(const char* name, const float* in, const HnW& w, int l
     return 0;
 }
 
+int hn_run_final(const float* in, int n, const HnW& w, float* desc, cudaStream_t st) {
+    {
+        ProfScope p("hn_final", st);
+        hn_final_kernel<8><<<cdiv(n, 8), 128, 0, st>>>(in, n, w.w[6], w.scale[6], w.shift[6], desc);
+    }
+    BALF_COUNT_LAUNCH(1);
+    BALF_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace balf
 
 using namespace balf;
 
 extern "C" int64_t balf_hardnet_raw_weight_count(void) { return (int64_t)hn_raw_count(); }
-extern "C" int64_t balf_hardnet_packed_weight_count(void) { return (int64_t)hn_walk(nullptr, nullptr); }
+extern "C" int64_t balf_hardnet_packed_weight_count(void) { return (int64_t)(hn_walk(nullptr, nullptr) + hn_tc_blob_floats()); }
 
 extern "C" int balf_hardnet_pack_weights(const float* raw, float* packed, void* stream) {
     BALF_REQUIRE(raw && packed, "null pointer argument");
@@ -223,23 +210,26 @@ extern "C" int balf_hardnet_pack_weights(const float* raw, float* packed, void* 
         src += 2 * L.cout;
     }
     BALF_LAUNCH_OK();
-    return 0;
+    return hn_tc_pack_weights(w, packed + hn_walk(nullptr, nullptr), st);     // second half: tensor-core operand images
 }
 
-// two ping-pong activation buffers of N x 32 x 32 x 32 floats
-extern "C" size_t balf_hardnet_workspace_bytes(int n_patches) {
+// fp32 path: two ping-pong activation buffers of N x 32 x 32 x 32 floats; tensor-core path: see hardnet_tc.cu
+static size_t hn_fp32_workspace_bytes(int n_patches) { return 2 * align_up((size_t)n_patches * 32 * 1024 * sizeof(float), 256); }
+extern "C" size_t balf_hardnet_workspace_bytes(int n_patches, int precision) {
     if (n_patches <= 0) return 0;
-    return 2 * align_up((size_t)n_patches * 32 * 1024 * sizeof(float), 256);
+    return precision == 1 ? hn_tc_workspace_bytes(n_patches) : hn_fp32_workspace_bytes(n_patches);
 }
 
 extern "C" int balf_hardnet_forward(const float* packed, const float* patches, int n_patches, float* desc, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    size_t workspace_bytes, int precision, void* stream) {
     BALF_REQUIRE(packed && patches && desc && workspace, "null pointer argument");
     BALF_REQUIRE(n_patches > 0, "n_patches must be positive");
-    BALF_REQUIRE(workspace_bytes >= balf_hardnet_workspace_bytes(n_patches), "workspace too small");
+    BALF_REQUIRE(precision == 0 || precision == 1, "precision %d is not built in this library (0 = fp32, 1 = tf32)", precision);
+    BALF_REQUIRE(workspace_bytes >= balf_hardnet_workspace_bytes(n_patches, precision), "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     HnW w;
-    hn_walk(packed, &w);
+    const size_t fp32_floats = hn_walk(packed, &w);
+    if (precision == 1) return hn_tc_forward(w, packed + fp32_floats, patches, n_patches, desc, workspace, st);
     float* a = static_cast<float*>(workspace);
     float* b = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)n_patches * 32 * 1024 * sizeof(float), 256));
     const int n = n_patches;
@@ -255,11 +245,5 @@ extern "C" int balf_hardnet_forward(const float* packed, const float* patches, i
     if (int e = hn_launch_conv<64, 64, 16, 1, 4, 16>("hn_conv4", b, w, 3, a, n, st)) return e;
     if (int e = hn_launch_conv<64, 128, 16, 2, 4, 8>("hn_conv5", a, w, 4, b, n, st)) return e;
     if (int e = hn_launch_conv<128, 128, 8, 1, 4, 8>("hn_conv6", b, w, 5, a, n, st)) return e;
-    {
-        ProfScope p("hn_final", st);
-        hn_final_kernel<8><<<cdiv(n, 8), 128, 0, st>>>(a, n, w.w[6], w.scale[6], w.shift[6], desc);
-    }
-    BALF_COUNT_LAUNCH(1);
-    BALF_LAUNCH_OK();
-    return 0;
+    return hn_run_final(a, n, w, desc, st);
 }

@@ -155,13 +155,16 @@ BALF_API int balf_extract_patches_u8(const uint8_t* gray, int B, int H, int W, c
  *               demo/demo_match.py:71-93.
  * `raw` = every floating tensor of the HardNet state_dict concatenated in state_dict order
  * (features.{0,3,6,9,12,15,19}.weight each followed by its BatchNorm running_mean, running_var).
- * patches fp32 [N,1,32,32] -> desc fp32 [N,128]. */
+ * patches fp32 [N,1,32,32] -> desc fp32 [N,128].
+ * precision: 0 = fp32 FFMA kernels (hardnet.cu),
+ *            1 = the six 3x3 layers after the first as implicit-GEMM tcgen05 tiles, TF32 operands, fp32 accumulate
+ *                in TMEM (hardnet_tc.cu); the workspace size depends on it. */
 BALF_API int64_t balf_hardnet_raw_weight_count(void);
 BALF_API int64_t balf_hardnet_packed_weight_count(void);
 BALF_API int balf_hardnet_pack_weights(const float* raw, float* packed, void* stream);
-BALF_API size_t balf_hardnet_workspace_bytes(int n_patches);
+BALF_API size_t balf_hardnet_workspace_bytes(int n_patches, int precision);
 BALF_API int balf_hardnet_forward(const float* packed, const float* patches, int n_patches, float* desc, void* workspace,
-                                  size_t workspace_bytes, void* stream);
+                                  size_t workspace_bytes, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * M1  SMNN matching

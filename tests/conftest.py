@@ -61,11 +61,14 @@ def detector_sd(detector):
     return {k: v.detach().clone() for k, v in detector.state_dict().items()}
 
 
-@pytest.fixture(scope="session")
-def hardnet():
+@pytest.fixture(scope="session", params=["tf32", "fp32"])
+def hardnet(request):
+    """HardNet with the reference's random init (seed 0), once per precision of balf_hardnet_forward."""
     from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
     torch.manual_seed(0)
-    return HardNet().eval()
+    hn = HardNet().eval()
+    hn.precision = request.param
+    return hn
 
 
 def weight_digest(sd):
