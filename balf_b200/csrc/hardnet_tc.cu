@@ -4,8 +4,8 @@
 // (+ ReLU)), :62-67 input_norm, :7-15 L2Norm -- restated in oracle/hardnet.py.
 //
 // The five 3x3 convolutions after the first (99 % of the 78.2 MFLOP per patch) run as implicit GEMMs on tcgen05
-// (kind::tf32, fp32 accumulation in TMEM); the first layer (K = 9) and the final 8x8 "valid" layer + L2 norm stay on
-// the CUDA cores (hardnet.cu).
+// (kind::tf32, fp32 accumulation in TMEM), the final 8x8 "valid" layer as a split-K [patches x 8192] x [8192 x 128]
+// product on the same pipe; only the first layer (K = 9) stays on the CUDA cores.
 //
 // Implicit GEMM without im2col.  A layer's input lives in shared memory as the canonical K-major SWIZZLE_NONE
 // operand ("chunk-major": [C/4 chunks][R rows][4 floats], one row per position of a zero-haloed pixel grid), so the
@@ -27,6 +27,8 @@ using namespace umma;
 
 constexpr int kHnSlots = 3;
 constexpr int kHnThreads = 128;
+// final layer (8x8 "valid" conv = [patches x 8192] x [8192 x 128]): K blocks of 32 = (position, 32 channels)
+constexpr int kFinalKB = 32, kFinalBlocks = 8192 / kFinalKB, kFinalBlockFloats = 128 * kFinalKB, kFinalSplit = 4;
 
 __host__ __device__ constexpr int hn_cmax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int hn_cmin(int a, int b) { return a < b ? a : b; }
@@ -208,8 +210,13 @@ hn_tc_conv_kernel(const float* __restrict__ in, const float* __restrict__ wblk, 
                 bool valid = q <= Ge::QLAST && ox >= 0 && ox < HOUT && oy >= 0 && oy < HOUT;
                 if (t > 0 && q < Ge::qs(t - 1) + 128) valid = false;     // the pulled-back last tile repeats rows
                 float* dst;
-                if (NEXT == 2) dst = out + (size_t)(p0 + g) * (COUT * 64) + oy * 8 + ox;
-                else dst = out + (size_t)(p0 + g) * ((size_t)COUT * RN) + (size_t)hn_next_row<NEXT == 1 ? 1 : 0, HOUT>(oy, ox) * 4;
+                if (NEXT == 2) {
+                    // final layer's A operand: [tile of 128 patches][K block = (position, 32 channels)][8 chunks][128 rows][4]
+                    const int p = p0 + g;
+                    dst = out + ((size_t)(p >> 7) * kFinalBlocks + (size_t)(oy * 8 + ox) * (COUT / 32)) * kFinalBlockFloats + (size_t)(p & 127) * 4;
+                } else {
+                    dst = out + (size_t)(p0 + g) * ((size_t)COUT * RN) + (size_t)hn_next_row<NEXT == 1 ? 1 : 0, HOUT>(oy, ox) * 4;
+                }
 #pragma unroll
                 for (int c0 = 0; c0 < COUT; c0 += 32) {
                     float v[32];
@@ -218,7 +225,11 @@ hn_tc_conv_kernel(const float* __restrict__ in, const float* __restrict__ wblk, 
                     if (valid) {
                         if (NEXT == 2) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dst[(size_t)(c0 + i) * 64] = fmaxf(v[i] + s_shift[c0 + i], 0.f);
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 o = make_float4(fmaxf(v[4 * j] + s_shift[c0 + 4 * j], 0.f), fmaxf(v[4 * j + 1] + s_shift[c0 + 4 * j + 1], 0.f),
+                                                             fmaxf(v[4 * j + 2] + s_shift[c0 + 4 * j + 2], 0.f), fmaxf(v[4 * j + 3] + s_shift[c0 + 4 * j + 3], 0.f));
+                                *reinterpret_cast<float4*>(dst + ((size_t)(c0 / 32) * 8 + j) * 512) = to_tf32(o);
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -290,6 +301,91 @@ __global__ void __launch_bounds__(256) hn_tc_first_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------ final layer
+// [128 patches x 8192] x [8192 x 128] on tcgen05, split-K over kFinalSplit CTAs per patch tile.  Both operands arrive as
+// pre-laid-out 16 KB blocks (A written by conv6's epilogue, B packed once), one bulk copy each per K block.
+__global__ void __launch_bounds__(kHnThreads, 1)
+hn_tc_final_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ partial, int n) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t kBlk = kFinalBlockFloats * 4u;               // 16 KB
+    constexpr int kPer = kFinalBlocks / kFinalSplit;                // K blocks per CTA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kHnSlots * kBlk);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kHnSlots;
+    uint64_t* done = bars + 2 * kHnSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHnSlots + 1);
+    const int tid = threadIdx.x, tile = blockIdx.x, split = blockIdx.y;
+    const bool w0 = warp0_uniform();
+    if (tid < 32) tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int i = 0; i < kHnSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *tmem_slot;
+    if (w0 && elect_one()) {
+        const float* ga = a + ((size_t)tile * kFinalBlocks + (size_t)split * kPer) * kFinalBlockFloats;
+        const float* gb = b + (size_t)split * kPer * kFinalBlockFloats;
+        const uint32_t s_addr = smem_u32(smem);
+        constexpr uint32_t idesc = make_idesc_tf32(128, 128);
+        int produced = 0;
+        for (int blk = 0; blk < kPer; ++blk) {
+            while (produced < kPer && produced < blk + kHnSlots) {
+                const int slot = produced % kHnSlots, use = produced / kHnSlots;
+                if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+                mbar_expect_tx(&full[slot], 2 * kBlk);
+                bulk_g2s(smem + (size_t)slot * 2 * kBlk, ga + (size_t)produced * kFinalBlockFloats, kBlk, &full[slot]);
+                bulk_g2s(smem + (size_t)slot * 2 * kBlk + kBlk, gb + (size_t)produced * kFinalBlockFloats, kBlk, &full[slot]);
+                ++produced;
+            }
+            const int slot = blk % kHnSlots;
+            mbar_wait(&full[slot], (blk / kHnSlots) & 1);
+            fence_after_sync();
+            const uint64_t a_desc = hn_desc(s_addr + slot * 2 * kBlk, 128u * 16u), b_desc = hn_desc(s_addr + slot * 2 * kBlk + kBlk, 128u * 16u);
+#pragma unroll
+            for (int k8 = 0; k8 < kFinalKB / 8; ++k8)
+                mma_tf32(tm, a_desc + ((k8 * 2u * 128u * 16u) >> 4), b_desc + ((k8 * 2u * 128u * 16u) >> 4), idesc, !(blk == 0 && k8 == 0));
+            commit(&empty[slot]);
+        }
+        commit(done);
+    }
+    if (tid == 0) mbar_wait(done, 0);
+    __syncthreads();
+    fence_after_sync();
+    const int p = tile * 128 + tid;
+    float* dst = partial + ((size_t)split * n + p) * 128;
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)(tid & ~31) << 16) + c0, v);
+        tmem_ld_wait();
+        if (p < n) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tm, 128);
+}
+
+// split-K partial sums -> + BatchNorm shift -> L2 normalisation (hardnet_pytorch.py:7-15).  One warp per patch.
+__global__ void hn_tc_finish_kernel(const float* __restrict__ partial, const float* __restrict__ shift, int n, float* __restrict__ desc) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= n) return;
+    float4 v = __ldg(reinterpret_cast<const float4*>(shift) + lane);
+#pragma unroll
+    for (int s = 0; s < kFinalSplit; ++s) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)s * n + p) * 128) + lane);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    const float nrm = sqrtf(warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w)) + 1e-10f);
+    reinterpret_cast<float4*>(desc + (size_t)p * 128)[lane] = make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
+}
+
 // ------------------------------------------------------------------------------------------ weights
 struct HnTcLayer { int cin, cout, kb; };
 static const HnTcLayer kHnTc[5] = {{32, 32, 32}, {32, 64, 32}, {64, 64, 64}, {64, 128, 16}, {128, 128, 32}};   // conv2 .. conv6
@@ -297,6 +393,7 @@ static const HnTcLayer kHnTc[5] = {{32, 32, 32}, {32, 64, 32}, {64, 64, 64}, {64
 struct HnTcBlob {
     size_t first_w, first_shift;     // conv1: [9][32] scaled, [32]
     size_t w[5], shift[5];           // conv2..6: NBLK blocks of [cout x kb] chunk-major, [cout]
+    size_t final_w, final_shift;     // final layer: kFinalBlocks blocks of [128 x 32] chunk-major, [128]
     size_t floats;
 };
 static HnTcBlob hn_tc_layout() {
@@ -308,6 +405,7 @@ static HnTcBlob hn_tc_layout() {
         b.w[l] = take((size_t)9 * kHnTc[l].cin * kHnTc[l].cout);
         b.shift[l] = take(kHnTc[l].cout);
     }
+    b.final_w = take((size_t)8192 * 128); b.final_shift = take(128);
     b.floats = off;
     return b;
 }
@@ -322,6 +420,14 @@ __global__ void hn_tc_pack_kernel(const float* __restrict__ wT, const float* __r
     const int kp = ci / kb, kk = ci - kp * kb;
     const float v = wT[((size_t)ci * 9 + tap) * cout + n] * scale[n];
     dst[(size_t)(tap * (cin / kb) + kp) * cout * kb + (size_t)(kk >> 2) * cout * 4 + n * 4 + (kk & 3)] = to_tf32(v);
+}
+// final layer: wT [cin = 128][64 positions][cout = 128] * scale -> K blocks (position, 32 channels) of [128 rows][32], tf32
+__global__ void hn_tc_pack_final_kernel(const float* __restrict__ wT, const float* __restrict__ scale, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 8192 * 128) return;
+    const int n = i % 128, c = (i / 128) % 128, pos = i / (128 * 128);
+    const int blk = pos * 4 + c / 32, kk = c % 32;
+    dst[(size_t)blk * kFinalBlockFloats + (size_t)(kk >> 2) * 512 + n * 4 + (kk & 3)] = to_tf32(wT[((size_t)c * 64 + pos) * 128 + n] * scale[n]);
 }
 __global__ void hn_tc_pack_first_kernel(const float* __restrict__ wT, const float* __restrict__ scale, float* __restrict__ dst) {
     const int i = threadIdx.x + blockIdx.x * blockDim.x;
@@ -342,6 +448,8 @@ int hn_tc_pack_weights(const HnW& w, float* blob, cudaStream_t st) {
         hn_tc_pack_kernel<<<cdiv(9 * T.cin * T.cout, 256), 256, 0, st>>>(w.w[l + 1], w.scale[l + 1], T.cin, T.cout, T.kb, blob + L.w[l]);
         hn_tc_copy_kernel<<<1, 128, 0, st>>>(w.shift[l + 1], T.cout, blob + L.shift[l]);
     }
+    hn_tc_pack_final_kernel<<<cdiv(8192 * 128, 256), 256, 0, st>>>(w.w[6], w.scale[6], blob + L.final_w);
+    hn_tc_copy_kernel<<<1, 128, 0, st>>>(w.shift[6], 128, blob + L.final_shift);
     BALF_LAUNCH_OK();
     return 0;
 }
@@ -355,13 +463,15 @@ using G6 = HnGeom<128, 128, 1, 8, 2, 32>;
 static_assert(G2::R == 1160 && G3::R == 1160 && G4::R == 328 && G5::R == 384 && G6::R == 152, "layer image sizes");
 
 constexpr int kHnTcChunk = 4096;     // patches per internal pass (bounds the workspace: 0.57 MB per patch)
-struct HnTcWs { float* a[6]; };      // inputs of conv2 .. conv6, then the flat [n][8192] input of the final layer
+struct HnTcWs { float* a[7]; };      // inputs of conv2 .. conv6, the final layer's A operand (whole 128-patch tiles), split-K partials
 static size_t hn_tc_ws_layout(int n, void* base, HnTcWs* ws) {
-    const size_t per[6] = {(size_t)32 * G2::R, (size_t)32 * G3::R, (size_t)64 * G4::R, (size_t)64 * G5::R, (size_t)128 * G6::R, 8192};
+    const size_t ntile = (size_t)cdiv(n, 128) * 128;
+    const size_t floats[7] = {(size_t)32 * G2::R * n, (size_t)32 * G3::R * n, (size_t)64 * G4::R * n, (size_t)64 * G5::R * n,
+                              (size_t)128 * G6::R * n, 8192 * ntile, (size_t)kFinalSplit * 128 * n};
     size_t off = 0;
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
         if (ws) ws->a[i] = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-        off = align_up(off + per[i] * sizeof(float) * n, 256);
+        off = align_up(off + floats[i] * sizeof(float), 256);
     }
     return off;
 }
@@ -395,7 +505,7 @@ static int hn_tc_launch(const char* name, const float* in, const float* wblk, co
     return 0;
 }
 
-int hn_tc_forward(const HnW& w, const float* blob, const float* patches, int n_patches, float* desc, void* workspace, cudaStream_t st) {
+int hn_tc_forward(const HnW& /*w*/, const float* blob, const float* patches, int n_patches, float* desc, void* workspace, cudaStream_t st) {
     const HnTcBlob L = hn_tc_layout();
     for (int p0 = 0; p0 < n_patches; p0 += kHnTcChunk) {
         const int n = n_patches - p0 < kHnTcChunk ? n_patches - p0 : kHnTcChunk;
@@ -412,7 +522,15 @@ int hn_tc_forward(const HnW& w, const float* blob, const float* patches, int n_p
         if (int e = hn_tc_launch<64, 64, 1, 16, 2, 64, 1, G5::R>("hn_tc_conv4", ws.a[2], blob + L.w[2], blob + L.shift[2], ws.a[3], n, st)) return e;
         if (int e = hn_tc_launch<64, 128, 2, 8, 2, 16, 0, G6::R>("hn_tc_conv5", ws.a[3], blob + L.w[3], blob + L.shift[3], ws.a[4], n, st)) return e;
         if (int e = hn_tc_launch<128, 128, 1, 8, 2, 32, 2, 0>("hn_tc_conv6", ws.a[4], blob + L.w[4], blob + L.shift[4], ws.a[5], n, st)) return e;
-        if (int e = hn_run_final(ws.a[5], n, w, desc + (size_t)p0 * 128, st)) return e;
+        {
+            constexpr size_t smem = 2 * kHnSlots * kFinalBlockFloats * 4 + 128;
+            BALF_CUDA_OK(cudaFuncSetAttribute(hn_tc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope p("hn_tc_final", st);
+            hn_tc_final_kernel<<<dim3(cdiv(n, 128), kFinalSplit), kHnThreads, smem, st>>>(ws.a[5], blob + L.final_w, ws.a[6], n);
+            hn_tc_finish_kernel<<<cdiv(n, 8), 256, 0, st>>>(ws.a[6], blob + L.final_shift, n, desc + (size_t)p0 * 128);
+        }
+        BALF_COUNT_LAUNCH(2);
+        BALF_LAUNCH_OK();
     }
     return 0;
 }
