@@ -533,6 +533,7 @@ static size_t ws_layout(const balf_detector_arch& a, int Bc, int Hp, int Wp, voi
     return off;
 }
 
+extern int g_tc_trace_sel;        // detector_tc.cu
 int g_tc_mask = 0x1F;              // debug hook (balf_debug_set key 0): bit l = stage l on the tensor-core path, bit 4 = head
 
 int g_chunk_images = 16;           // images per internal pass (bounds the workspace; debug hook key 1).  16 keeps the
@@ -603,8 +604,9 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
 using namespace balf;
 
 extern "C" int balf_debug_set(int key, int value) {
-    BALF_REQUIRE(key == 0 || key == 1, "unknown debug key %d", key);
+    BALF_REQUIRE(key >= 0 && key <= 2, "unknown debug key %d", key);
     if (key == 0) g_tc_mask = value & 0x1F;
+    else if (key == 2) g_tc_trace_sel = value;
     else { BALF_REQUIRE(value >= 1 && value <= 64, "chunk must be in [1, 64]"); g_chunk_images = value; }
     return 0;
 }

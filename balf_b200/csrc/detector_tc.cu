@@ -57,6 +57,7 @@ struct TcPlan {
     long long* trace;     // development hook (balf_debug_set_trace): clock stamps of CTA 0, or null
 };
 long long* g_tc_trace = nullptr;
+int g_tc_trace_sel = 0;           // which kernel family records (debug key 2): 0 = branch kernels, 1 = merge kernels
 constexpr int kTracePoints = 16, kTraceTiles = 16;
 // stamp `pt` of tile iteration `it` for thread 0 (slot 0: the MMA issuer) and the last thread (slot 1: pure epilogue)
 #define TC_TRACE(plan, it, pt)                                                                                     \
@@ -593,7 +594,9 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        TC_TRACE(plan, it, 0);
         const int unit = 2 * t + ug;
         const bool valid = unit < geo.total_units;
         const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
@@ -602,22 +605,31 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
         load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        TC_TRACE(plan, it, 1);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
+        TC_TRACE(plan, it, 2);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 3);
         ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
         st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
         load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+        TC_TRACE(plan, it, 4);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        TC_TRACE(plan, it, 5);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 6);
         load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
+        TC_TRACE(plan, it, 8);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 9);
         // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
         {
             float rstd, shift;
@@ -641,18 +653,24 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
+        TC_TRACE(plan, it, 10);
         sync_for_mma();
         // ---- conv1 -> LeakyReLU(0.2)
         if (w0 && elect_one()) { issue_linear_t<G, MG_RC1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        TC_TRACE(plan, it, 11);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 12);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = lrelu02(v[i]);
         row_to_a<CH>(v, s.region, row, col0);
+        TC_TRACE(plan, it, 13);
         sync_for_mma();
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
         if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        TC_TRACE(plan, it, 14);
         wait_done(s.done, phase);
+        TC_TRACE(plan, it, 15);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
@@ -869,8 +887,11 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
     tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true);
     tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true);
     P.floats = off;
-    for (int l = 0; l < 4; ++l) P.branch[l][0].trace = P.branch[l][1].trace = P.merge[l].trace = g_tc_trace;
-    P.head.trace = g_tc_trace;
+    for (int l = 0; l < 4; ++l) {
+        P.branch[l][0].trace = P.branch[l][1].trace = g_tc_trace_sel == 0 ? g_tc_trace : nullptr;
+        P.merge[l].trace = g_tc_trace_sel == 1 ? g_tc_trace : nullptr;
+    }
+    P.head.trace = nullptr;
     if (out) *out = P;
 }
 

@@ -229,6 +229,41 @@ def roofline_of(name, launches, total_ms, steps, images, pk, traffic=None):
             "launches_per_step": launches / steps, "peak_source": pk["src"]}
 
 
+def extras(dev, pk):
+    """Secondary rows of the hot path (BASELINE.json configs[2] shapes), not part of `value`:
+    HardNet on 4096 patches and SMNN on 2048 x 2048 descriptors, device-resident, CUDA-event timed."""
+    import balf_b200._capi as capi
+    from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
+    torch.manual_seed(0)
+    hn = HardNet().eval().to(dev)
+    x = torch.rand(4096, 1, 32, 32, device=dev)
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+    with torch.inference_mode():
+        ms = timed(lambda: hn(x))
+        tf = 4096 * 78.184e6 / (ms * 1e-3) / 1e12
+        out["hardnet"] = {"patches": 4096, "ms": ms, "patches_per_s": 4096 / (ms * 1e-3), "tflops": tf, "dtype": hn.precision,
+                          "frac_of_tf32_peak": tf / (pk["tensor"] / 2), "peak": "half of the bf16 figure (%s)" % pk["src"]}
+        d1 = torch.nn.functional.normalize(torch.randn(2048, 128, device=dev), dim=1)
+        d2 = torch.nn.functional.normalize(d1 + 0.05 * torch.randn(2048, 128, device=dev), dim=1)
+        ms = timed(lambda: capi.match_smnn(d1, d2, 0.99))
+        out["smnn"] = {"n1": 2048, "n2": 2048, "ms": ms, "pairs_per_s": 2048 * 2048 / (ms * 1e-3),
+                       "note": "includes the device->host read of the match count"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ main arm
 def main():
     a = parse()
@@ -342,6 +377,8 @@ def main():
                      if det_ms else None},
         "kernels": kernels,
     }
+    if world == 1:
+        line["extras"] = extras(dev, pk)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line))

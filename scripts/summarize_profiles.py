@@ -13,7 +13,7 @@ from collections import OrderedDict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-KEYS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ("gpu__time_duration.sum", "sm__inst_executed_pipe_tensor", "smsp__issue_active.avg.pct", "lts__throughput.avg.pct", "l1tex__throughput.avg.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_registers",
@@ -54,8 +54,8 @@ def launches(tag):
     print("wrote", tag + "_launches.md")
 
 
-def full(tag):
-    rep = os.path.join(OUT, "prof.ncu-rep")
+def full(tag, report="prof.ncu-rep", suffix="_ncu_full.md", what="the dominant detector kernels"):
+    rep = os.path.join(OUT, report)
     if not os.path.exists(rep):
         return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -64,8 +64,8 @@ def full(tag):
         print("no rows in report")
         return
     head, units = rows[0], rows[1]
-    with open(os.path.join(PROF, tag + "_ncu_full.md"), "w") as f:
-        f.write("# %s -- `ncu --set full --clock-control none` of the dominant kernel (one row per captured launch)\n\n" % tag)
+    with open(os.path.join(PROF, tag + suffix), "w") as f:
+        f.write("# %s -- `ncu --set full --clock-control none` of %s (one row per captured launch)\n\n" % (tag, what))
         for r in rows[2:]:
             d = dict(zip(head, r))
             f.write("## %s  grid %s block %s\n\n| metric | value | unit |\n|---|---:|---|\n" % (
@@ -74,7 +74,7 @@ def full(tag):
                 if any(h.startswith(k) for k in KEYS):
                     f.write("| %s | %s | %s |\n" % (h, r[i], units[i]))
             f.write("\n")
-    print("wrote", tag + "_ncu_full.md")
+    print("wrote", tag + suffix)
 
 
 def bench(tag):
@@ -92,4 +92,6 @@ if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
     full(tag)
+    full(tag, "prof_nms.ncu-rep", "_ncu_nms.md", "the windowed NMS + select/sort kernels (scripts/nms_bench.py, 64 maps)")
+    full(tag, "prof_hn.ncu-rep", "_ncu_hardnet.md", "the HardNet tensor-core kernels (scripts/hn_bench.py, 4096 patches)")
     bench(tag)

@@ -13,6 +13,7 @@ from balf_b200.utils import test_utils
 from balf_b200.configs import config
 
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+which = sys.argv[3] if len(sys.argv) > 3 else "branch"   # "branch": last writer = block branch; "merge": needs BALF trace of merge (runs last)
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda:0")
 cfg = test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)
@@ -25,6 +26,7 @@ with torch.inference_mode():
     buf = torch.zeros(8192, dtype=torch.int64, device=dev)
     # only the chosen level on the tensor-core path, so that its branch kernel is the last writer of the buffer
     c.debug_set(0, 1 << level)
+    c.debug_set(2, 1 if which == "merge" else 0)
     c.debug_set_trace(buf.data_ptr())
     det(x[:B])
     torch.cuda.synchronize()
