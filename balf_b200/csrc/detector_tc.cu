@@ -89,7 +89,8 @@ struct Ring {
     uint32_t wsm;          // shared address of the weight area
     uint64_t* full;        // [kNSlot]
     uint64_t* empty;       // [kNSlot]
-    uint32_t pg, pb;       // producer cursor (gemm, block)
+    uint32_t pidx, nsched; // producer cursor into the block schedule / its length
+    const uint2* sched;    // [nsched] (float offset inside the tc blob, bytes) of every block of the plan, in issue order
     uint32_t pcnt, ccnt;   // blocks loaded / consumed so far
     uint32_t to_load;      // blocks still to be requested over the life of the CTA
 };
@@ -98,16 +99,26 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const float* src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// The block schedule is tabulated once per CTA (ring_build_schedule): walking the plan structure for every block put
+// ~1500 cycles of serial single-thread code (local-memory struct reads, 64-bit address arithmetic) on the critical
+// path of every GEMM phase of the streamed stages.
+__device__ __forceinline__ void ring_build_schedule(uint2* sched, const TcPlan& p, uint32_t* count) {
+    uint32_t n = 0;
+    for (int gi = 0; gi < p.ngemm; ++gi) {
+        const TcGemm g = p.g[gi];
+        for (uint32_t b = 0; b < g.nblk; ++b) sched[n++] = make_uint2(g.goff + b * (uint32_t)g.rows * g.kb, gemm_block_bytes(g, b));
+    }
+    *count = n;
+}
 __device__ __forceinline__ void ring_load_one(Ring& r, const TcPlan& p) {
-    const TcGemm& g = p.g[r.pg];
-    const uint32_t bytes = gemm_block_bytes(g, r.pb);
+    const uint2 e = r.sched[r.pidx];
     const uint32_t slot = r.pcnt % kNSlot, use = r.pcnt / kNSlot;
     if (use > 0) mbar_wait(&r.empty[slot], (use - 1) & 1);
-    mbar_expect_tx(&r.full[slot], bytes);
-    bulk_load(r.wsm + slot * p.slot_bytes, p.base + g.goff + (size_t)r.pb * g.rows * g.kb, bytes, &r.full[slot]);
+    mbar_expect_tx(&r.full[slot], e.y);
+    bulk_load(r.wsm + slot * p.slot_bytes, p.base + e.x, e.y, &r.full[slot]);
     ++r.pcnt;
     --r.to_load;
-    if (++r.pb == g.nblk) { r.pb = 0; if (++r.pg == (uint32_t)p.ngemm) r.pg = 0; }
+    if (++r.pidx == r.nsched) r.pidx = 0;
 }
 __device__ __forceinline__ void ring_top_up(Ring& r, const TcPlan& p) {
     while (r.to_load > 0 && r.pcnt < r.ccnt + kNSlot) ring_load_one(r, p);
@@ -292,17 +303,19 @@ struct TcShared {
     float* ones;           // [2 chunks][128 rows][4]: (1 1 0 0), (0 0 0 0)
     float2* xch;           // [2 buffers][2 halves][128 rows]
     float* vec;            // small per-kernel vectors (gating LayerNorm affine)
+    uint2* sched;          // weight-block schedule of the ring (kSchedEntries entries) + its length
     uint64_t* full;
     uint64_t* empty;
     uint64_t* done;
     uint32_t* tmem_slot;
 };
-constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kTcTail = 128;
+constexpr uint32_t kSchedEntries = 62;
+constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 128;
 __host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
     return p.resident ? (p.bytes + 127u) / 128u * 128u : kNSlot * p.slot_bytes;
 }
 __host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p) {
-    return region + tc_weight_bytes(p) + kOnesBytes + kXchBytes + kVecBytes + kTcTail;
+    return region + tc_weight_bytes(p) + kOnesBytes + kXchBytes + kVecBytes + kSchedBytes + kTcTail;
 }
 __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p) {
     TcShared s;
@@ -312,6 +325,7 @@ __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_b
     s.ones = reinterpret_cast<float*>(q); q += kOnesBytes;
     s.xch = reinterpret_cast<float2*>(q); q += kXchBytes;
     s.vec = reinterpret_cast<float*>(q); q += kVecBytes;
+    s.sched = reinterpret_cast<uint2*>(q); q += kSchedBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(q);
     s.full = bars;
     s.empty = bars + kNSlot;
@@ -333,14 +347,19 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    ring.wsm = s.wsm; ring.full = s.full; ring.empty = s.empty;
-    ring.pg = ring.pb = ring.pcnt = ring.ccnt = 0;
+    ring.wsm = s.wsm; ring.full = s.full; ring.empty = s.empty; ring.sched = s.sched;
+    ring.pidx = ring.pcnt = ring.ccnt = 0;
     uint32_t nb = 0;
     for (int i = 0; i < plan.ngemm; ++i) nb += plan.g[i].nblk;
+    ring.nsched = nb;
     ring.to_load = nb * my_tiles;
     if (w0 && elect_one()) {      // the elected lane of warp 0 owns the ring state and issues every MMA
         if (plan.resident) { ring_load_all(ring, plan); mbar_wait(&s.full[0], 0); }
-        else ring_top_up(ring, plan);
+        else {
+            uint32_t cnt;
+            ring_build_schedule(s.sched, plan, &cnt);
+            ring_top_up(ring, plan);
+        }
     }
 }
 __device__ __forceinline__ void tc_finish(uint32_t tm, uint32_t ncols) {
