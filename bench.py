@@ -179,31 +179,34 @@ def level_dims():
 
 
 def kernel_work(name, images):
-    """Algorithmic work of ONE step's launches of kernel `name`: ("tensor", flops) or ("hbm", bytes).
-    Detector kernels count Linear / token-mixing MACs x 2 once (recomputation is not credited);
-    SURVEY.md 8d.  NMS counts 4*H*W + 16*K bytes per image."""
+    """Algorithmic work of ONE step's launches of kernel `name`: (flops, bytes).
+    Detector kernels: Linear / token-mixing MACs x 2 counted once (recomputation is not credited) and the
+    fp32 tensors each kernel must read and write once (x, u, v, r, q: DESIGN.md section 3).  NMS: 4*H*W bytes per
+    image (+ 16*K for the select/sort kernel)."""
     lv = {32: 0, 64: 1, 128: 2, 256: 3}
     if name.startswith("det_"):
         tail = name.rsplit("_c", 1)
         c = int(tail[1]) if len(tail) == 2 and tail[1].isdigit() else None
         if c in lv:
             cin, ch, px = level_dims()[lv[c]]
-            if "branch" in name:                       # half of dense1, branch dense1, token mix, dense2
-                return "tensor", images * px * (2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch)
-            if "merge" in name:                        # conv.0, dense2 (2C->C), conv1, conv2
-                return "tensor", images * px * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch)
-            if "level" in name:                        # a whole Down stage in one kernel
-                return "tensor", images * px * (2 * cin * ch + 24 * ch * ch + 256 * ch)
-        if name == "det_head":
-            return "tensor", images * level_dims()[3][2] * (2 * 256 * 256 + 2 * 256 * 65)
-        return "tensor", 0
+            n = images * px
+            if "branch" in name:                       # half of dense1, branch dense1, token mix, dense2; x in, u' out
+                return n * (2 * cin * ch + 2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch), n * 4 * (cin + ch)
+            if "merge" in name:                        # conv.0, dense2 (2C->C), conv1, conv2; x, u', v' in, r, q out
+                return n * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch), n * 4 * (cin + 4 * ch)
+        if name == "det_head":                         # r, q in; prob out (64 values per 8x8 cell)
+            n = images * level_dims()[3][2]
+            return n * (2 * 256 * 256 + 2 * 256 * 65), n * 4 * (2 * 256 + 64)
+        if name == "det_pool":                         # r, q in, pooled out, stages 1-3
+            return 0, sum(images * px * 4 * (2 * ch + ch // 4) for _, ch, px in level_dims()[:3])
+        return 0, 0
     if name.startswith("nms_windowed"):
-        return "hbm", images * (4 * H * W)
+        return 0, images * (4 * H * W)
     if name == "nms_select_sort":
-        return "hbm", images * 16 * K_FEATURES
+        return 0, images * 16 * K_FEATURES
     if name == "preprocess_u8":
-        return "hbm", images * (H * W + 12 * 512 * 640)
-    return "hbm", 0
+        return 0, images * (H * W + 12 * 512 * 640)
+    return 0, 0
 
 
 def peaks():
@@ -214,19 +217,39 @@ def peaks():
     return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def roofline_of(name, launches, total_ms, steps, images, pk, traffic=None):
-    kind, work = kernel_work(name, images)
-    per_launch_ms = total_ms / max(launches, 1)
-    work_per_launch = work * steps / max(launches, 1)
+def ncu_traffic(name):
+    """dram__bytes_read + dram__bytes_write per launch of kernel `name` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/summarize_profiles.py), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(name)
+    return None
+
+
+def roofline_of(name, launches, total_ms, steps, images, pk):
+    """The bound is the kernel's own: arithmetic intensity (algorithmic flops / algorithmic bytes) against the machine
+    balance for tf32 operands (half the bf16 tensor peak / HBM peak) decides between "tensor" and "hbm"."""
+    flops, nbytes = kernel_work(name, images)
+    per_launch_s = total_ms / max(launches, 1) * 1e-3
+    per = steps / max(launches, 1)
+    balance = (pk["tensor"] / 2 * 1e12) / (pk["hbm"] * 1e9)
+    if flops == 0 and nbytes == 0:
+        return {"kernel": name, "bound": "latency", "launch_ms": per_launch_s * 1e3, "launches_per_step": launches / steps}
+    kind = "tensor" if nbytes == 0 or (flops and flops / nbytes > balance) else "hbm"
+    out = {"kernel": name, "bound": kind, "launch_ms": per_launch_s * 1e3, "launches_per_step": launches / steps,
+           "peak_source": pk["src"], "traffic": ncu_traffic(name),
+           "algorithmic": {"flops_per_launch": flops * per, "bytes_per_launch": nbytes * per,
+                           "intensity_flop_per_byte": (flops / nbytes) if nbytes else None, "tf32_balance": balance}}
     if kind == "tensor":
-        achieved = work_per_launch / (per_launch_ms * 1e-3) / 1e12
-        unit = "TFLOP/s"
+        ach = flops * per / per_launch_s / 1e12
+        out.update({"achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+                    "frac_of_tf32_peak": ach / (pk["tensor"] / 2)})
     else:
-        achieved = work_per_launch / (per_launch_ms * 1e-3) / 1e9
-        unit = "GB/s"
-    return {"kernel": name, "bound": kind, "achieved": achieved, "peak": pk[kind], "unit": unit,
-            "frac": achieved / pk[kind], "traffic": traffic, "launch_ms": per_launch_ms,
-            "launches_per_step": launches / steps, "peak_source": pk["src"]}
+        ach = nbytes * per / per_launch_s / 1e9
+        out.update({"achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]})
+        if flops:
+            out["tensor_tflops"] = flops * per / per_launch_s / 1e12
+    return out
 
 
 def extras(dev, pk):
@@ -353,8 +376,11 @@ def main():
     images = a.batch * world
     pk = peaks()
     total_kernel_ms = sum(v[1] for v in prof.values())
-    kernels = {k: {"launches_per_step": v[0] / a.steps, "ms_per_step": v[1] / a.steps,
-                   "share": v[1] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        r = roofline_of(k, v[0], v[1], a.steps, a.batch, pk)
+        kernels[k] = {"launches_per_step": v[0] / a.steps, "ms_per_step": v[1] / a.steps, "share": v[1] / total_kernel_ms,
+                      "bound": r["bound"], "achieved": r.get("achieved"), "unit": r.get("unit"), "frac": r.get("frac")}
     top = max(prof.items(), key=lambda kv: kv[1][1])
     roof = roofline_of(top[0], top[1][0], top[1][1], a.steps, a.batch, pk)
     nms_name = "nms_windowed" if a.nms == "windowed" else "nms_greedy_rounds"

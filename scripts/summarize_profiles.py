@@ -77,6 +77,49 @@ def full(tag, report="prof.ncu-rep", suffix="_ncu_full.md", what="the dominant d
     print("wrote", tag + suffix)
 
 
+def traffic():
+    """profiles/ncu_traffic.json: bench.py kernel name -> dram bytes (read + write) per launch, from the full captures."""
+    import re
+    out = {}
+    for report in ("prof.ncu-rep", "prof_nms.ncu-rep"):
+        rep = os.path.join(OUT, report)
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        if len(rows) < 3:
+            continue
+        head, units = rows[0], rows[1]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            d = dict(zip(head, r))
+            kn = d.get("Kernel Name", "")
+            name = None
+            m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
+            if m:
+                name = "det_branch_%s_c%s" % ("grid" if m.group(3) == "0" else "block", m.group(2))
+            m = re.search(r"tc_merge_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
+            if m:
+                name = "det_merge_c%s" % m.group(2)
+            if "nms15_kernel" in kn:
+                name = "nms_windowed"
+            if "select_sort_kernel" in kn:
+                name = "nms_select_sort"
+            if not name or name in out:
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = head.index(key)
+                tot += float(r[i].replace(",", "")) * mult.get(units[i], 1)
+            out[name] = tot
+    if out:
+        path = os.path.join(PROF, "ncu_traffic.json")
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old.update(out)
+        json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+        print("wrote ncu_traffic.json", out)
+
+
 def bench(tag):
     for name in ("bench.json", "bench_ref.json"):
         p = os.path.join(OUT, name)
@@ -94,4 +137,5 @@ if __name__ == "__main__":
     full(tag)
     full(tag, "prof_nms.ncu-rep", "_ncu_nms.md", "the windowed NMS + select/sort kernels (scripts/nms_bench.py, 64 maps)")
     full(tag, "prof_hn.ncu-rep", "_ncu_hardnet.md", "the HardNet tensor-core kernels (scripts/hn_bench.py, 4096 patches)")
+    traffic()
     bench(tag)
