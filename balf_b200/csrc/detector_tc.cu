@@ -419,6 +419,41 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
     }
 }
 
+// Software prefetch of the level input (CIN <= 32: at most 4 float4 per thread): the next tile's rows are requested
+// right after the current tile's operand is stored, so the ~2000-cycle global-load latency at the top of every tile
+// (scripts/tc_trace.py) hides under the tile's six GEMM phases.
+template <int CIN> struct InputPf {
+    static constexpr bool enabled = CIN <= 32;
+    static constexpr int N = CIN < 8 ? 1 : CIN / 8;
+    float4 v[N];
+};
+template <int CIN>
+__device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid, int half,
+                                                InputPf<CIN>& pf) {
+    if constexpr (CIN < 8) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (half == 0 && valid) {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) v[c] = __ldg(xin + (img * CIN + c) * npix + pix);
+        }
+        pf.v[0] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
+#pragma unroll
+        for (int j = 0; j < CIN / 8; ++j) pf.v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int CIN>
+__device__ __forceinline__ void store_input_row(const InputPf<CIN>& pf, float* dst, int row, int half) {
+    if constexpr (CIN < 8) {
+        *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CIN / 8; ++j)
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) = to_tf32(pf.v[j]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ branch kernel
 template <int C> struct BranchCfg {
     static constexpr int CH = C / 2;
@@ -457,16 +492,35 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
     int it = 0;
+    InputPf<CIN> pf;
+    auto coords = [&](int tt, bool& vld, int& im, int& px) {
+        const int un = 2 * tt + ug;
+        vld = un < geo.total_units;
+        im = vld ? un / geo.upi : 0;
+        px = unit_pixel<BR>(geo, vld ? un - im * geo.upi : 0, tok);
+    };
+    if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
+        bool vld; int im, px;
+        coords(blockIdx.x, vld, im, px);
+        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         TC_TRACE(plan, it, 0);
-        const int unit = 2 * t + ug;
-        const bool valid = unit < geo.total_units;
-        const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
-        const int pix = unit_pixel<BR>(geo, u, tok);
+        bool valid; int img, pix;
+        coords(t, valid, img, pix);
         float* orow = out + ((size_t)img * npix + pix) * C + col0;
         float v[CH], rstd, shift;
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
-        load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        if (InputPf<CIN>::enabled) {
+            store_input_row<CIN>(pf, s.region, row, half);
+            if (t + (int)gridDim.x < ntiles) {
+                bool vld; int im, px;
+                coords(t + gridDim.x, vld, im, px);
+                fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+            }
+        } else {
+            load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        }
         TC_TRACE(plan, it, 1);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
@@ -614,16 +668,37 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
     int it = 0;
+    InputPf<CIN> pf;                       // next tile's level input
+    InputPf<C> pfu;                        // this tile's u' / v' rows, requested one phase ahead (C <= 32)
+    auto coords = [&](int tt, bool& vld, int& im, int& px) {
+        const int un = 2 * tt + ug;
+        vld = un < geo.total_units;
+        im = vld ? un / geo.upi : 0;
+        px = (vld ? un - im * geo.upi : 0) * 64 + tok;
+    };
+    if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
+        bool vld; int im, px;
+        coords(blockIdx.x, vld, im, px);
+        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         TC_TRACE(plan, it, 0);
-        const int unit = 2 * t + ug;
-        const bool valid = unit < geo.total_units;
-        const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
-        const int pix = u * 64 + tok;
+        bool valid; int img, pix;
+        coords(t, valid, img, pix);
         const size_t row_off = ((size_t)img * npix + pix) * C + col0;
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
-        load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        if (InputPf<CIN>::enabled) {
+            store_input_row<CIN>(pf, s.region, row, half);
+            if (t + (int)gridDim.x < ntiles) {
+                bool vld; int im, px;
+                coords(t + gridDim.x, vld, im, px);
+                fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+            }
+        } else {
+            load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+        }
+        if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
@@ -635,14 +710,20 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
         st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
-        load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+        if (InputPf<C>::enabled) {
+            store_input_row<C>(pfu, s.region, row, half);
+            fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
+        } else {
+            load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+        }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
         wait_done(s.done, phase);
         TC_TRACE(plan, it, 6);
-        load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        if (InputPf<C>::enabled) store_input_row<C>(pfu, s.region, row, half);
+        else load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
