@@ -246,6 +246,64 @@ __device__ __forceinline__ float gelu_erf(float v) {
     p = fmaf(p, a, -1.0f);
     return fmaf(-a, ex2_approx(p), fmaxf(v, 0.0f));
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot for two lanes-worth of work.  The
+// epilogues are issue-bound (ncu: ~50 % issue utilisation at 24 warps/SM, a third of it FFMA), so the GELU polynomial,
+// LayerNorm statistics / normalisation and the gating products run on register pairs.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long r, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// two GELUs: the polynomial is evaluated in t = -a (alternating coefficient signs) so that the last step is one FFMA2
+// relu(v) + t * e.  13 instructions per pair (4 FMNMX, 7 FFMA2, 2 MUFU) instead of 20.
+__device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
+    const float t0 = fmaxf(-fabsf(v0), -5.6568542494923806f), t1 = fmaxf(-fabsf(v1), -5.6568542494923806f);
+    const unsigned long long t = pk2(t0, t1);
+    unsigned long long p = fma2(pk2(3.220531653e-05f, 3.220531653e-05f), t, pk2(7.531010197e-04f, 7.531010197e-04f));
+    p = fma2(p, t, pk2(8.000897244e-03f, 8.000897244e-03f));
+    p = fma2(p, t, pk2(5.324822292e-02f, 5.324822292e-02f));
+    p = fma2(p, t, pk2(-4.589224458e-01f, -4.589224458e-01f));
+    p = fma2(p, t, pk2(1.151143193e+00f, 1.151143193e+00f));
+    p = fma2(p, t, pk2(-1.0f, -1.0f));
+    float p0, p1;
+    upk2(p, p0, p1);
+    const unsigned long long r = fma2(t, pk2(ex2_approx(p0), ex2_approx(p1)), pk2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f)));
+    upk2(r, v0, v1);
+}
+// v[i] = gelu(v[i]) over an even-length register array; optionally accumulates sum and sum of squares
+template <int N, bool STATS>
+__device__ __forceinline__ void gelu_row(float (&v)[N], float& sum, float& sq) {
+    unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        gelu_erf2(v[i], v[i + 1]);
+        if (STATS) { const unsigned long long x = pk2(v[i], v[i + 1]); s2 = add2(s2, x); q2 = fma2(x, x, q2); }
+    }
+    if (STATS) { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
+}
+// v[i] = v[i] * rstd + shift
+template <int N>
+__device__ __forceinline__ void norm_row(float (&v)[N], float rstd, float shift) {
+    const unsigned long long r2 = pk2(rstd, rstd), h2 = pk2(shift, shift);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) { const unsigned long long x = fma2(pk2(v[i], v[i + 1]), r2, h2); upk2(x, v[i], v[i + 1]); }
+}
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
 
 // CH consecutive accumulator columns of this thread's row -> registers (tcgen05.ld is warp-collective)
@@ -530,11 +588,20 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
             float sum = 0.f, sq = 0.f;
+            {
+                unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) { v[i] = fmaxf(v[i], 0.f); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+                for (int i = 0; i < CH; i += 2) {
+                    v[i] = fmaxf(v[i], 0.f); v[i + 1] = fmaxf(v[i + 1], 0.f);
+                    const unsigned long long x = pk2(v[i], v[i + 1]);
+                    s2 = add2(s2, x); q2 = fma2(x, x, q2);
+                }
+                float a, b;
+                upk2(s2, a, b); sum = a + b;
+                upk2(q2, a, b); sq = a + b;
+            }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 4);
@@ -547,16 +614,14 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
             float sum = 0.f, sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < CH; ++i) { v[i] = gelu_erf(v[i]); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+            gelu_row<CH, true>(v, sum, sq);
             if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
             else if (valid) {
 #pragma unroll
                 for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 7);
@@ -572,18 +637,22 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+            { float d0, d1; gelu_row<CH, false>(v, d0, d1); }
             st_row<CH>(lane_base + Cfg::col_y + col0, v);
             ld_row<CH>(lane_base + Cfg::col_y + C + col0, v);
             float sum = 0.f, sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < CH; ++i) { v[i] = gelu_erf(v[i]); sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+            gelu_row<CH, true>(v, sum, sq);
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3) + (size_t)col0 * 4;
+            norm_row<CH>(v, rstd, shift);
 #pragma unroll
-            for (int i = 0; i < CH; ++i)
-                yt[(size_t)i * 4] = to_tf32(fmaf(fmaf(v[i], rstd, shift), s.vec[col0 + i], s.vec[256 + col0 + i]));
+            for (int i = 0; i < CH; i += 2) {
+                const float2 gw = *reinterpret_cast<const float2*>(s.vec + col0 + i), gb = *reinterpret_cast<const float2*>(s.vec + 256 + col0 + i);
+                float o0, o1;
+                upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), o0, o1);
+                yt[(size_t)i * 4] = to_tf32(o0);
+                yt[(size_t)(i + 1) * 4] = to_tf32(o1);
+            }
         }
         TC_TRACE(plan, it, 10);
         sync_for_mma();
@@ -599,8 +668,9 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                 float y1[SC], y2[SC];
                 ld_row<SC>(lane_base + Cfg::col_y + col0 + c, y1);
                 ld_row<SC>(lane_base + Cfg::col_y + C + col0 + c, y2);
+                const unsigned long long b2 = pk2(mix_b1, mix_b1);
 #pragma unroll
-                for (int i = 0; i < SC; ++i) y2[i] = y1[i] * (y2[i] + mix_b1);
+                for (int i = 0; i < SC; i += 2) upk2(mul2(pk2(y1[i], y1[i + 1]), add2(pk2(y2[i], y2[i + 1]), b2)), y2[i], y2[i + 1]);
                 row_to_a<SC>(y2, s.region, row, col0 + c);
             }
         }
@@ -736,21 +806,29 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
             float sum = 0.f, sq = 0.f;
             constexpr int SC = CH > 64 ? 64 : CH;
+            unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < CH; c += SC) {
                 float x0[SC];
                 ld_row<SC>(lane_base + Cfg::col_x0 + col0 + c, x0);
 #pragma unroll
-                for (int i = 0; i < SC; ++i) { v[c + i] += x0[i]; sum += v[c + i]; sq = fmaf(v[c + i], v[c + i], sq); x0[i] += v[c + i]; }
+                for (int i = 0; i < SC; i += 2) {
+                    const unsigned long long xz = pk2(x0[i], x0[i + 1]);
+                    const unsigned long long x1 = add2(pk2(v[c + i], v[c + i + 1]), xz);
+                    s2 = add2(s2, x1);
+                    q2 = fma2(x1, x1, q2);
+                    upk2(x1, v[c + i], v[c + i + 1]);
+                    upk2(add2(x1, xz), x0[i], x0[i + 1]);
+                }
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < SC / 4; ++j)
                         *reinterpret_cast<float4*>(qout + row_off + c + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
                 }
             }
+            { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = fmaf(v[i], rstd, shift);
+            norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 10);
@@ -762,7 +840,11 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         TC_TRACE(plan, it, 12);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = lrelu02(v[i]);
+        for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
+            float l0, l1;
+            upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
+            v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
+        }
         row_to_a<CH>(v, s.region, row, col0);
         TC_TRACE(plan, it, 13);
         sync_for_mma();
