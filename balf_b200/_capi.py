@@ -11,7 +11,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbalf_b200.so")
+LIB_PATH = os.environ.get("BALF_B200_LIB") or os.path.join(_HERE, "libbalf_b200.so")   # override: development A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "balf_b200.h")
 
 if not os.path.exists(LIB_PATH):

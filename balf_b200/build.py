@@ -12,7 +12,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "libbalf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict_
 // out[b, py, px, :] = max over the 2x2 window of (r * s + q)
 template <int C>
 __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict__ q, const float* __restrict__ scale,
-                            int h, int w, float* __restrict__ out, size_t total) {
+                            int h, int w, float* __restrict__ out, size_t total, bool swz) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     constexpr int Q = C / 4;
@@ -392,8 +392,11 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
             size_t p = (b * h + 2 * py + dy) * w + 2 * px + dx;
-            float4 rv = __ldg(reinterpret_cast<const float4*>(r + p * C) + c4);
-            float4 qv = __ldg(reinterpret_cast<const float4*>(q + p * C) + c4);
+            // swz: r / q of the tensor-core stage-1 merge kernel are in the swizzled panel layout (detector_tc.cu sw_off;
+            // C = 32 is a single panel: the chunks of a pixel's 128-byte row are permuted by (pixel % 8))
+            const int cs = swz ? (c4 ^ (int)(p & 7)) : c4;
+            float4 rv = __ldg(reinterpret_cast<const float4*>(r + p * C) + cs);
+            float4 qv = __ldg(reinterpret_cast<const float4*>(q + p * C) + cs);
             best.x = fmaxf(best.x, rv.x * s.x + qv.x); best.y = fmaxf(best.y, rv.y * s.y + qv.y);
             best.z = fmaxf(best.z, rv.z * s.z + qv.z); best.w = fmaxf(best.w, rv.w * s.w + qv.w);
         }
@@ -588,11 +591,11 @@ static int run_se(const Workspace& ws, const DownW& w, int Bc, int npix, int par
 }
 
 template <int C>
-static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st) {
+static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st, bool swz = false) {
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
     {
         ProfScope p("det_pool", st);
-        pool_kernel<C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        pool_kernel<C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total, swz);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
@@ -709,7 +712,7 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
             if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
             if (int e = run_se<32>(ws, d[0], Bc, Hp * Wp, Hp * Wp / 64, st)) return e;
         } else if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
-        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st)) return e;
+        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) != 0)) return e;
         if (tcm & 2) {
             if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
             if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;

@@ -37,7 +37,7 @@ using namespace umma;
 
 constexpr int TM = 128;                 // pixel rows per tile
 constexpr int NT2 = 256;                // threads per CTA (two per row)
-constexpr int kNSlot = 2;
+constexpr int kMaxSlot = 4;              // ring slots: per kernel family (G::nslot), sized from the shared-memory budget
 constexpr int kMaxGemm = 6;
 
 struct TcGemm {
@@ -54,17 +54,23 @@ struct TcPlan {
     int resident;         // all blocks stay in shared memory for the life of the CTA
     uint32_t bytes;       // total bytes of all blocks (resident footprint)
     uint32_t slot_bytes;  // ring slot size (largest block, 128-byte multiple)
+    uint32_t nslot;       // ring slots
     long long* trace;     // development hook (balf_debug_set_trace): clock stamps of CTA 0, or null
 };
 long long* g_tc_trace = nullptr;
 int g_tc_trace_sel = 0;           // which kernel family records (debug key 2): 0 = branch kernels, 1 = merge kernels
 constexpr int kTracePoints = 16, kTraceTiles = 16;
 // stamp `pt` of tile iteration `it` for thread 0 (slot 0: the MMA issuer) and the last thread (slot 1: pure epilogue)
+#ifdef BALF_TC_TRACE          // development builds only (NVCC_FLAGS=-DBALF_TC_TRACE python balf_b200/build.py --force): the stamps cost
+                             // ~5 % of the epilogue instructions (predicate + clock read per point)
 #define TC_TRACE(plan, it, pt)                                                                                     \
     do {                                                                                                           \
         if ((plan).trace && blockIdx.x == 0 && (it) < kTraceTiles && (threadIdx.x == 0 || threadIdx.x == NT2 - 1)) \
             (plan).trace[(((it) * kTracePoints + (pt)) << 1) + (threadIdx.x ? 1 : 0)] = clock64();                 \
     } while (0)
+#else
+#define TC_TRACE(plan, it, pt) do { (void)(it); } while (0)
+#endif
 
 enum { BG_CONV0 = 0, BG_PD1, BG_D1A, BG_D1B, BG_WM, BG_D2, BG_COUNT };
 enum { MG_CONV0 = 0, MG_PD2A, MG_PD2B, MG_RC1, MG_RC2, MG_COUNT };
@@ -72,10 +78,10 @@ enum { HG_C2 = 0, HG_DENSE, HG_COUNT };
 constexpr int kHeadN = 80;              // 65 logits padded to a legal UMMA N (multiple of 16)
 
 __host__ __device__ constexpr int tc_kin(int cin) { return cin < 8 ? 8 : cin; }
-// K columns per streamed block: the largest power-of-two divisor of K (>= 8) whose block is <= 32 KB
-__host__ __device__ constexpr int tc_kb(int rows, int K) {
+// K columns per streamed block: the largest power-of-two divisor of K (>= 8) whose block is <= cap bytes
+__host__ __device__ constexpr int tc_kb(int rows, int K, int cap = 32768) {
     int kb = K;
-    while (kb > 8 && (kb * rows * 4 > 32768 || K % kb != 0)) kb /= 2;
+    while (kb > 8 && (kb * rows * 4 > cap || K % kb != 0)) kb /= 2;
     return kb;
 }
 __host__ __device__ constexpr int tc_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
@@ -87,11 +93,13 @@ __host__ __device__ inline uint32_t gemm_bytes(const TcGemm& g) { return (uint32
 // ------------------------------------------------------------------------------------------ weight ring (thread 0)
 struct Ring {
     uint32_t wsm;          // shared address of the weight area
-    uint64_t* full;        // [kNSlot]
-    uint64_t* empty;       // [kNSlot]
+    uint64_t* full;        // [nslot]
+    uint64_t* empty;       // [nslot]
     uint32_t pidx, nsched; // producer cursor into the block schedule / its length
     const uint2* sched;    // [nsched] (float offset inside the tc blob, bytes) of every block of the plan, in issue order
     uint32_t pcnt, ccnt;   // blocks loaded / consumed so far
+    uint32_t pslot, puse;  // producer slot / how many times it has been filled before
+    uint32_t cslot, cpar;  // consumer slot / its full-barrier parity
     uint32_t to_load;      // blocks still to be requested over the life of the CTA
 };
 
@@ -110,18 +118,28 @@ __device__ __forceinline__ void ring_build_schedule(uint2* sched, const TcPlan& 
     }
     *count = n;
 }
+template <int NS>
 __device__ __forceinline__ void ring_load_one(Ring& r, const TcPlan& p) {
     const uint2 e = r.sched[r.pidx];
-    const uint32_t slot = r.pcnt % kNSlot, use = r.pcnt / kNSlot;
-    if (use > 0) mbar_wait(&r.empty[slot], (use - 1) & 1);
+    const uint32_t slot = r.pslot;
+    if (r.puse > 0) mbar_wait(&r.empty[slot], (r.puse - 1) & 1);
     mbar_expect_tx(&r.full[slot], e.y);
     bulk_load(r.wsm + slot * p.slot_bytes, p.base + e.x, e.y, &r.full[slot]);
     ++r.pcnt;
     --r.to_load;
+    if (++r.pslot == NS) { r.pslot = 0; ++r.puse; }
     if (++r.pidx == r.nsched) r.pidx = 0;
 }
+// Called at the top of every block AND right after a phase's MMAs have completed (wait_done_ring): at that point every
+// slot is free, so the next phase's first blocks stream in under the epilogue instead of under the next issue.
+template <int NS>
 __device__ __forceinline__ void ring_top_up(Ring& r, const TcPlan& p) {
-    while (r.to_load > 0 && r.pcnt < r.ccnt + kNSlot) ring_load_one(r, p);
+    while (r.to_load > 0 && r.pcnt < r.ccnt + NS) ring_load_one<NS>(r, p);
+}
+template <int NS>
+__device__ __forceinline__ void ring_consumed(Ring& r) {
+    ++r.ccnt;
+    if (++r.cslot == NS) { r.cslot = 0; r.cpar ^= 1; }
 }
 // resident mode: every gemm, once
 __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
@@ -139,6 +157,8 @@ __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
 template <int CIN, int C> struct BranchG {
     static constexpr int count = BG_COUNT;
     static constexpr bool resident = C <= 32;
+    static constexpr int cap = 32768;
+    static constexpr int nslot = C == 64 ? 3 : C == 128 ? 4 : 2;
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
@@ -146,6 +166,8 @@ template <int CIN, int C> struct BranchG {
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
     static constexpr bool resident = C <= 32;
+    static constexpr int cap = C == 64 ? 8192 : 32768;     // C = 64: three operand regions share the CTA with the ring
+    static constexpr int nslot = C == 128 ? 4 : 2;
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
@@ -153,6 +175,8 @@ template <int CIN, int C> struct MergeG {
 template <int C> struct HeadG {
     static constexpr int count = HG_COUNT;
     static constexpr bool resident = false;
+    static constexpr int cap = 32768;
+    static constexpr int nslot = 2;
     __host__ __device__ static constexpr int rows(int gi) { return gi == HG_DENSE ? kHeadN : C; }
     __host__ __device__ static constexpr int K(int) { return C; }
     __host__ __device__ static constexpr bool bias(int) { return true; }
@@ -167,23 +191,30 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t addr, uint32_t lbo) {
 }
 
 // Thread 0: D[128 x N] (+)= A[128 x K] * W^T (+ bias) for GEMM GI of plan G (see issue_linear).
-template <typename G, int GI>
+// high word of a K-major SWIZZLE_128B descriptor (SBO = 1024: 8 rows x 128 B, version 1, layout type 2); LBO is ignored
+// by the hardware for swizzled K-major operands (encoded 1).  Probed: profiles/r01_umma_probe.txt "Kmaj SW128".
+constexpr uint32_t kDescHiSw = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_sw_of(uint32_t addr) {
+    return ((uint64_t)kDescHiSw << 32) | (uint64_t)((1u << 16) | ((addr >> 4) & 0x3FFFu));
+}
+// ASW: the A operand is a [128 rows x K] tile in the swizzled panel layout (sw_off below) instead of chunk-major
+template <typename G, int GI, bool ASW = false>
 __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_t a_addr, uint32_t ones_addr, uint32_t d_tmem, bool first) {
     constexpr int ROWS = G::rows(GI), K = G::K(GI);
     constexpr bool BIAS = G::bias(GI);
-    constexpr int KB = tc_kb(ROWS, K), NBLK = K / KB;
+    constexpr int KB = tc_kb(ROWS, K, G::cap), NBLK = K / KB;
     constexpr uint32_t idesc = make_idesc_tf32(128, ROWS);
     constexpr uint32_t a_lbo = TM * 16u, b_lbo = (uint32_t)ROWS * 16u;
-    const uint64_t a_desc = desc_of(a_addr, a_lbo);
+    const uint64_t a_desc = ASW ? desc_sw_of(a_addr) : desc_of(a_addr, a_lbo);
 #pragma unroll
     for (int b = 0; b < NBLK; ++b) {
         uint32_t w_addr, slot = 0;
         if (G::resident) {
             w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * 4u;
         } else {
-            ring_top_up(r, p);
-            slot = r.ccnt % kNSlot;
-            mbar_wait(&r.full[slot], (r.ccnt / kNSlot) & 1);
+            ring_top_up<G::nslot>(r, p);
+            slot = r.cslot;
+            mbar_wait(&r.full[slot], r.cpar);
             w_addr = r.wsm + slot * p.slot_bytes;
         }
         const uint64_t b_desc = desc_of(w_addr, b_lbo);
@@ -191,12 +222,14 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
 #pragma unroll
         for (int k8 = 0; k8 < KB / 8; ++k8) {
             const uint32_t kchunk = (uint32_t)(b * KB) / 4u + (uint32_t)k8 * 2u;
-            mma_tf32(d_tmem, a_desc + ((kchunk * a_lbo) >> 4), b_desc + (((uint32_t)k8 * 2u * b_lbo) >> 4), idesc,
+            // swizzled panels: 32 K columns (128 B) per panel of TM rows, 32 B per MMA inside a panel
+            const uint32_t a_off = ASW ? (kchunk / 8u) * (TM * 128u) + (kchunk % 8u) * 16u : kchunk * a_lbo;
+            mma_tf32(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)k8 * 2u * b_lbo) >> 4), idesc,
                      !(first && b == 0 && k8 == 0));
         }
         if (BIAS && b + 1 == NBLK)
             mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / 4u) * b_lbo) >> 4), idesc, true);
-        if (!G::resident) { commit(&r.empty[slot]); ++r.ccnt; }
+        if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
     }
 }
 
@@ -207,9 +240,9 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
     if (G::resident) {
         w_addr = r.wsm + g_off<G>(GI);
     } else {
-        ring_top_up(r, p);
-        slot = r.ccnt % kNSlot;
-        mbar_wait(&r.full[slot], (r.ccnt / kNSlot) & 1);
+        ring_top_up<G::nslot>(r, p);
+        slot = r.cslot;
+        mbar_wait(&r.full[slot], r.cpar);
         w_addr = r.wsm + slot * p.slot_bytes;
     }
     fence_after_sync();
@@ -223,7 +256,7 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
         for (uint32_t k8 = 0; k8 < 8; ++k8)
             mma_tf32(d_tmem + ((u * 16u) << 16), w_desc + ((k8 * 2u * 1024u) >> 4), y_desc + ((k8 * 2u * b_lbo) >> 4), idesc, k8 > 0);
     }
-    if (!G::resident) { commit(&r.empty[slot]); ++r.ccnt; }
+    if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
 }
 
 // ------------------------------------------------------------------------------------------ epilogue pieces
@@ -343,14 +376,39 @@ __device__ __forceinline__ void row_to_a(const float (&v)[CH], float* region, in
             to_tf32(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
 }
 
+// ---- "swizzled panel" layout of a [128 rows x C] tile (the K-major SWIZZLE_128B operand layout of tcgen05): panels of 32
+// channels (128 B per row), rows 128 B apart inside a panel, the eight 16-byte chunks of a row XOR-permuted by (row % 8).
+// A tile stored this way in GLOBAL memory (u', v', r, q of the network-input stage) moves to / from shared memory with one
+// plain bulk copy (cp.async.bulk, 16 KB per panel, perfectly coalesced, no thread instructions), is a valid MMA operand as
+// it lands, and is written by the epilogue threads without bank conflicts (eight consecutive rows hit eight different
+// 16-byte bank groups).  Float offset of chunk `chunk` (4 channels) of row `row`:
+__host__ __device__ __forceinline__ int sw_off(int row, int chunk) { return (chunk >> 3) * (TM * 32) + row * 32 + (((chunk & 7) ^ (row & 7)) << 2); }
+template <int CH, bool ROUND>
+__device__ __forceinline__ void row_to_sw(const float (&v)[CH], float* region, int row, int col0) {
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (ROUND) o = to_tf32(o);
+        *reinterpret_cast<float4*>(region + sw_off(row, col0 / 4 + j)) = o;
+    }
+}
+// bulk copies shared <-> global (async proxy) and their bookkeeping
+__device__ __forceinline__ void bulk_store(const float* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // LayerNorm statistics of a row whose two halves live in two threads: exchange (sum, sum of squares)
 __device__ __forceinline__ void row_stats(float sum, float sq, float2* xch, int row, int half, int C, float& rstd, float& shift) {
     xch[half * TM + row] = make_float2(sum, sq);
     __syncthreads();
     const float2 o = xch[(half ^ 1) * TM + row];
-    const float mean = (sum + o.x) / (float)C;
-    const float var = fmaxf((sq + o.y) / (float)C - mean * mean, 0.f);
-    rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float inv_c = C == 32 ? 1.0f / 32 : C == 64 ? 1.0f / 64 : C == 128 ? 1.0f / 128 : 1.0f / 256;   // C is a literal at every call
+    const float mean = (sum + o.x) * inv_c;
+    const float var = fmaxf((sq + o.y) * inv_c - mean * mean, 0.f);
+    rstd = rsqrtf(var + 1e-5f);                        // MUFU.RSQ, 2 ulp: far inside the tf32 operand rounding that follows
     shift = -mean * rstd;                              // normalised value = v * rstd + shift
 }
 
@@ -370,7 +428,7 @@ struct TcShared {
 constexpr uint32_t kSchedEntries = 62;
 constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 128;
 __host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
-    return p.resident ? (p.bytes + 127u) / 128u * 128u : kNSlot * p.slot_bytes;
+    return p.resident ? (p.bytes + 127u) / 128u * 128u : p.nslot * p.slot_bytes;
 }
 __host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p) {
     return region + tc_weight_bytes(p) + kOnesBytes + kXchBytes + kVecBytes + kSchedBytes + kTcTail;
@@ -386,16 +444,17 @@ __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_b
     s.sched = reinterpret_cast<uint2*>(q); q += kSchedBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(q);
     s.full = bars;
-    s.empty = bars + kNSlot;
-    s.done = bars + 2 * kNSlot;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNSlot + 1);
+    s.empty = bars + kMaxSlot;
+    s.done = bars + 2 * kMaxSlot;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlot + 1);
     return s;
 }
 
+template <int NS>
 __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, Ring& ring, const TcPlan& plan, uint32_t my_tiles, bool w0) {
     if (threadIdx.x < 32) tmem_alloc(s.tmem_slot, ncols);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNSlot; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < kMaxSlot; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.done, 1);
         mbar_fence_init();
     }
@@ -407,6 +466,7 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
     fence_after_sync();
     ring.wsm = s.wsm; ring.full = s.full; ring.empty = s.empty; ring.sched = s.sched;
     ring.pidx = ring.pcnt = ring.ccnt = 0;
+    ring.pslot = ring.puse = ring.cslot = ring.cpar = 0;
     uint32_t nb = 0;
     for (int i = 0; i < plan.ngemm; ++i) nb += plan.g[i].nblk;
     ring.nsched = nb;
@@ -416,7 +476,7 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
         else {
             uint32_t cnt;
             ring_build_schedule(s.sched, plan, &cnt);
-            ring_top_up(ring, plan);
+            ring_top_up<NS>(ring, plan);
         }
     }
 }
@@ -440,18 +500,39 @@ __device__ __forceinline__ void wait_done(uint64_t* done, uint32_t& phase) {
     ++phase;
     fence_after_sync();
 }
+// same, and the issuing lane refills the (now entirely free) weight ring before joining the barrier
+template <typename G>
+__device__ __forceinline__ void wait_done_ring(uint64_t* done, uint32_t& phase, Ring& r, const TcPlan& p, bool w0) {
+    if (w0 && elect_one()) {
+        mbar_wait(done, phase & 1);
+        if (!G::resident) ring_top_up<G::nslot>(r, p);
+    }
+    __syncthreads();
+    ++phase;
+    fence_after_sync();
+}
 
 struct UnitGeom {
     int h, w, fh, fw;       // level size, grid-cell extent
     int upi;                // units (64 tokens) per image
     int total_units;        // over the batch chunk
+    float inv_upi, inv_fw, inv_bw;   // reciprocals for fast_div (bw = w / 8)
 };
+// n / d for 0 <= n < 2^23, d >= 1: float-reciprocal estimate (off by at most one) + exact fix-up; ~8 instructions instead of
+// the ~25 of the integer division sequence (coords() ran it three times per tile on every thread)
+__device__ __forceinline__ int fast_div(int n, int d, float inv_d) {
+    int q = __float2int_rz(__int2float_rn(n) * inv_d);
+    const int r = n - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
 
 // pixel index (inside its image) of token `tok` of unit `u`
 template <int KIND>   // 0 grid, 1 block, 2 linear
 __device__ __forceinline__ int unit_pixel(const UnitGeom& g, int u, int tok) {
-    if (KIND == 0) { const int fy = u / g.fw, fx = u - fy * g.fw; return ((tok >> 3) * g.fh + fy) * g.w + (tok & 7) * g.fw + fx; }
-    if (KIND == 1) { const int bw = g.w >> 3, by = u / bw, bx = u - by * bw; return (by * 8 + (tok >> 3)) * g.w + bx * 8 + (tok & 7); }
+    if (KIND == 0) { const int fy = fast_div(u, g.fw, g.inv_fw), fx = u - fy * g.fw; return ((tok >> 3) * g.fh + fy) * g.w + (tok & 7) * g.fw + fx; }
+    if (KIND == 1) { const int bw = g.w >> 3, by = fast_div(u, bw, g.inv_bw), bx = u - by * bw; return (by * 8 + (tok >> 3)) * g.w + bx * 8 + (tok & 7); }
     return u * 64 + tok;
 }
 
@@ -488,9 +569,9 @@ template <int CIN> struct InputPf {
 template <int CIN>
 __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid, int half,
                                                 InputPf<CIN>& pf) {
-    if constexpr (CIN < 8) {
+    if constexpr (CIN < 8) {                       // conv.0 runs on the CUDA cores: both halves of the row need the pixel
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (half == 0 && valid) {
+        if (valid) {
 #pragma unroll
             for (int c = 0; c < CIN; ++c) v[c] = __ldg(xin + (img * CIN + c) * npix + pix);
         }
@@ -512,6 +593,38 @@ __device__ __forceinline__ void store_input_row(const InputPf<CIN>& pf, float* d
     }
 }
 
+
+// ---- network input stage (CIN < 8): conv.0 has K = 3, so x0 = ReLU(conv.0(x)) is 3 FMAs per channel on the CUDA cores
+// (exact fp32) instead of a whole MMA phase (operand store, two barriers, commit / wait round trip, tcgen05.ld).
+// Weights sit in shared memory as cw[k][C] (k < CIN) followed by the bias [C]  (vec + kConv0Off).
+constexpr int kConv0Off = 64;
+template <int CIN, int C>
+__device__ __forceinline__ void conv0_stage_weights(const DownW& w, float* vec) {
+    for (int i = threadIdx.x; i < CIN * C; i += NT2) vec[kConv0Off + i] = __ldg(w.conv0_w + i);
+    for (int i = threadIdx.x; i < C; i += NT2) vec[kConv0Off + CIN * C + i] = __ldg(w.conv0_b + i);
+}
+template <int CIN, int C, int CH>
+__device__ __forceinline__ void conv0_row(const float4 x, const float* vec, int col0, float (&v)[CH]) {
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float* cw = vec + kConv0Off + col0;
+#pragma unroll
+    for (int i = 0; i < CH; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(cw + CIN * C + i);
+        unsigned long long a01 = pk2(b.x, b.y), a23 = pk2(b.z, b.w);
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(cw + k * C + i);
+            const unsigned long long xk = pk2(xs[k], xs[k]);
+            a01 = fma2(pk2(wv.x, wv.y), xk, a01);
+            a23 = fma2(pk2(wv.z, wv.w), xk, a23);
+        }
+        upk2(a01, v[i], v[i + 1]);
+        upk2(a23, v[i + 2], v[i + 3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i + j] = fmaxf(v[i + j], 0.f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ branch kernel
 template <int C> struct BranchCfg {
     static constexpr int CH = C / 2;
@@ -519,6 +632,7 @@ template <int C> struct BranchCfg {
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
+    static constexpr bool swz_out = C == 32;                       // u' / v' leave in the swizzled panel layout (tc_merge_l1_kernel)
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
@@ -538,9 +652,10 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const DownW::Branch& br = w.br[BR];
     for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
+    if constexpr (CIN < 8) conv0_stage_weights<CIN, C>(w, s.vec);
     Ring ring;
     const bool w0 = warp0_uniform();
-    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles, w0);
+    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);        // this warp's 32-lane window
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -554,7 +669,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     auto coords = [&](int tt, bool& vld, int& im, int& px) {
         const int un = 2 * tt + ug;
         vld = un < geo.total_units;
-        im = vld ? un / geo.upi : 0;
+        im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
         px = unit_pixel<BR>(geo, vld ? un - im * geo.upi : 0, tok);
     };
     if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
@@ -569,30 +684,41 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         float* orow = out + ((size_t)img * npix + pix) * C + col0;
         float v[CH], rstd, shift;
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
-        if (InputPf<CIN>::enabled) {
-            store_input_row<CIN>(pf, s.region, row, half);
+        if constexpr (CIN < 8) {
+            const float4 xv = pf.v[0];
             if (t + (int)gridDim.x < ntiles) {
                 bool vld; int im, px;
                 coords(t + gridDim.x, vld, im, px);
                 fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
             }
+            conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
-            load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
-        }
-        TC_TRACE(plan, it, 1);
-        sync_for_mma();
-        if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
-        TC_TRACE(plan, it, 2);
-        wait_done(s.done, phase);
-        TC_TRACE(plan, it, 3);
-        {
+            if (InputPf<CIN>::enabled) {
+                store_input_row<CIN>(pf, s.region, row, half);
+                if (t + (int)gridDim.x < ntiles) {
+                    bool vld; int im, px;
+                    coords(t + gridDim.x, vld, im, px);
+                    fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+                }
+            } else {
+                load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+            }
+            TC_TRACE(plan, it, 1);
+            sync_for_mma();
+            if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+            TC_TRACE(plan, it, 2);
+            wait_done_ring<G>(s.done, phase, ring, plan, w0);
+            TC_TRACE(plan, it, 3);
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        {
             float sum = 0.f, sq = 0.f;
             {
                 unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < CH; i += 2) {
-                    v[i] = fmaxf(v[i], 0.f); v[i + 1] = fmaxf(v[i + 1], 0.f);
                     const unsigned long long x = pk2(v[i], v[i + 1]);
                     s2 = add2(s2, x); q2 = fma2(x, x, q2);
                 }
@@ -609,7 +735,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
         if (w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
@@ -633,7 +759,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             commit(s.done);
         }
         TC_TRACE(plan, it, 8);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
@@ -659,7 +785,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // ---- token mixing, gating y1 * (y2' + 1)
         if (w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
         TC_TRACE(plan, it, 11);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 12);
         {
             constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
@@ -679,7 +805,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // ---- dense2 + residual u -> out
         if (w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         TC_TRACE(plan, it, 14);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 15);
         {
             constexpr int SC = CH > 64 ? 64 : CH;
@@ -694,8 +820,15 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                         float4 res;
                         if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                         else res = *reinterpret_cast<const float4*>(orow + c + 4 * j);
-                        *reinterpret_cast<float4*>(orow + c + 4 * j) =
-                            make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
+                        float4 o = make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
+                        // u' / v' feed nothing but the merge GEMM: rounding them here (RN, as every operand) lets the merge
+                        // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
+                        // the C >= 128 merge kernels round again when they load, which must be a no-op
+                        if (BR == 1 || Cfg::swz_out) o = to_tf32_clean(o);
+                        if (Cfg::swz_out)    // C == 32: one 128-byte row per pixel, chunks permuted by (pixel % 8) = swizzled panel layout
+                            *reinterpret_cast<float4*>(orow - col0 + ((((col0 + c) / 4 + j) ^ (pix & 7)) << 2)) = o;
+                        else
+                            *reinterpret_cast<float4*>(orow + c + 4 * j) = o;
                     }
                 }
             }
@@ -703,6 +836,35 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // the next tile's input load overwrites the region: every MMA reading it has completed (wait_done)
     }
     tc_finish(tm, Cfg::ncols);
+}
+
+
+// Channel sums of each unit (64 rows) of an exact-fp32 [128 x C] tile staged chunk-major in `reg` (squeeze input of the
+// channel attention).  Every thread takes part: a group of TPP lanes owns one (unit, 4-channel chunk) pair, each lane adds
+// 64 / TPP rows with float4 loads, then an xor butterfly inside the group -- a fixed order, so the result is bit-identical
+// run to run.  (The first version used 2C threads x 64 dependent scalar loads: ~2000 cycles of exposed latency per tile.)
+template <int C>
+__device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int total_units, float* __restrict__ partial) {
+    constexpr int CQ = C / 4, PAIRS = 2 * CQ, TPP = NT2 / PAIRS, RPT = 64 / TPP;
+    static_assert(TPP >= 2 && TPP <= 16, "group must fit in a warp");
+    const int tid = threadIdx.x, pair = tid / TPP, sub = tid % TPP;
+    const int uu = pair / CQ, ch = pair % CQ;
+    const float4* src = reinterpret_cast<const float4*>(reg) + (size_t)ch * TM + uu * 64 + sub;
+    float4 acc = src[0];
+#pragma unroll
+    for (int i = 1; i < RPT; ++i) {
+        const float4 x = src[i * TPP];
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+#pragma unroll
+    for (int o = TPP / 2; o >= 1; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    const int un = 2 * t + uu;
+    if (sub == 0 && un < total_units) *reinterpret_cast<float4*>(partial + (size_t)un * C + ch * 4) = acc;
 }
 
 // ------------------------------------------------------------------------------------------ merge kernel
@@ -729,7 +891,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
     const bool w0 = warp0_uniform();
-    tc_prologue(s, Cfg::ncols, ring, plan, my_tiles, w0);
+    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -743,7 +905,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     auto coords = [&](int tt, bool& vld, int& im, int& px) {
         const int un = 2 * tt + ug;
         vld = un < geo.total_units;
-        im = vld ? un / geo.upi : 0;
+        im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
         px = (vld ? un - im * geo.upi : 0) * 64 + tok;
     };
     if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
@@ -773,7 +935,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
         TC_TRACE(plan, it, 2);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 3);
         ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
 #pragma unroll
@@ -790,7 +952,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         if (InputPf<C>::enabled) store_input_row<C>(pfu, s.region, row, half);
         else load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
@@ -798,7 +960,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
         TC_TRACE(plan, it, 8);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 9);
         // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
         {
@@ -836,7 +998,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- conv1 -> LeakyReLU(0.2)
         if (w0 && elect_one()) { issue_linear_t<G, MG_RC1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         TC_TRACE(plan, it, 11);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 12);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -851,7 +1013,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
         if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         TC_TRACE(plan, it, 14);
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 15);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
@@ -861,19 +1023,328 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             if (valid) *reinterpret_cast<float4*>(rout + row_off + 4 * j) = o;
         }
         __syncthreads();
-        // channel sums of each unit, fixed order (rotated start so that a warp's lanes hit distinct banks)
-        for (int i = tid; i < 2 * C; i += NT2) {
-            const int uu = i / C, c = i - uu * C;
-            const int un = 2 * t + uu;
-            if (un < geo.total_units) {
-                const float* col = s.region + (size_t)(c >> 2) * TM * 4 + (size_t)uu * 64 * 4 + (c & 3);
-                float acc = 0.f;
-                for (int k = 0; k < 64; ++k) acc += col[(size_t)((k + (c >> 2)) & 63) * 4];
-                partial[(size_t)un * C + c] = acc;
-            }
-        }
+        unit_channel_sums<C>(s.region, t, geo.total_units, partial);
         __syncthreads();
     }
+    tc_finish(tm, Cfg::ncols);
+}
+
+
+// ------------------------------------------------------------------------------------------ merge kernel, 3 phases (C <= 64)
+// Same mathematics as tc_merge_kernel, restructured around its latencies (it was neither issue- nor DRAM-bound: 22 % issue
+// utilisation, 28-37 % of HBM).  Three operand regions [u' | v' | x] hold a whole tile's inputs at once, so conv.0, dense2(u')
+// and dense2(v') are issued back to back in ONE phase (5 -> 3 commit / wait / barrier round trips per tile, x0 never parked
+// in TMEM).  Every global read of tile t+1 is requested during tile t: x and u' rows into registers, v' (already
+// tf32-rounded by the block-branch kernel) straight into its region with cp.async as soon as phase 1 has released it.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;           // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int CIN, int C> struct Merge3Cfg {
+    static constexpr int CH = C / 2;
+    static constexpr bool cc0 = CIN < 8;                            // conv.0 on the CUDA cores (network input)
+    static constexpr uint32_t ubytes = (uint32_t)TM * C * 4;
+    static constexpr uint32_t xbytes = cc0 ? 0u : (uint32_t)TM * tc_kin(CIN) * 4;
+    static constexpr uint32_t region = 2 * ubytes + xbytes;
+    static constexpr int col_x0 = 0, col_acc = C;
+    static constexpr int ncols = tc_cols(2 * C);
+    static constexpr int min_ctas = C <= 32 ? 3 : 2;
+};
+
+template <int CIN, int C>
+__global__ void __launch_bounds__(NT2, Merge3Cfg<CIN, C>::min_ctas)
+tc_merge3_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
+                 const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    using Cfg = Merge3Cfg<CIN, C>;
+    using G = MergeG<CIN, C>;
+    constexpr int CH = Cfg::CH;
+    const TcShared s = carve(smem, Cfg::region, plan);
+    float* const regU = s.region;
+    float* const regV = regU + (size_t)TM * C;
+    float* const regX = regV + (size_t)TM * C;
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
+    const int ntiles = (geo.total_units + 1) / 2;
+    const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    if constexpr (Cfg::cc0) conv0_stage_weights<CIN, C>(w, s.vec);
+    Ring ring;
+    const bool w0 = warp0_uniform();
+    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
+    const uint32_t tm = *s.tmem_slot;
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
+    const uint32_t u_addr = smem_u32(regU), v_addr = smem_u32(regV), x_addr = smem_u32(regX), ones_addr = smem_u32(s.ones);
+    const int ug = row >> 6, tok = row & 63;
+    const int col0 = half * CH;
+    const size_t npix = (size_t)geo.h * geo.w;
+    uint32_t phase = 0, xb = 0;
+    InputPf<CIN> pfx;                      // next tile's level input
+    InputPf<C> pfu;                        // next tile's u' rows
+    auto coords = [&](int tt, bool& vld, int& im, int& px) {
+        const int un = 2 * tt + ug;
+        vld = un < geo.total_units;
+        im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
+        px = (vld ? un - im * geo.upi : 0) * 64 + tok;
+    };
+    auto prefetch = [&](int tt) {
+        bool vld; int im, px;
+        coords(tt, vld, im, px);
+#ifdef EXP_NO_LOAD
+        vld = false;
+#endif
+        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pfx);
+        fetch_input_row<C>(uin, npix, (size_t)im, px, vld, half, pfu);
+        const float* vsrc = vin + ((size_t)im * npix + px) * C + col0;
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j)
+            cp_async16(v_addr + (uint32_t)(((col0 / 4 + j) * TM + row) * 16), vsrc + 4 * j, vld);
+        cp_async_commit();
+    };
+    if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        bool valid; int img, pix;
+        coords(t, valid, img, pix);
+        const size_t row_off = ((size_t)img * npix + pix) * C + col0;
+        float v[CH];
+        // ---- phase 1: x0 = ReLU(conv.0(x)) | acc = dense2([u', v'])
+        float4 xcur = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (Cfg::cc0) xcur = pfx.v[0];
+        else store_input_row<CIN>(pfx, regX, row, half);
+        store_input_row<C>(pfu, regU, row, half);
+        cp_async_wait_all();
+        sync_for_mma();
+        if (w0 && elect_one()) {
+            if constexpr (!Cfg::cc0) issue_linear_t<G, MG_CONV0>(ring, plan, x_addr, ones_addr, tm + Cfg::col_x0, true);
+            issue_linear_t<G, MG_PD2A>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true);
+            issue_linear_t<G, MG_PD2B>(ring, plan, v_addr, ones_addr, tm + Cfg::col_acc, false);
+            commit(s.done);
+        }
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
+        {
+            float rstd, shift, x0[CH];
+            ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+            if constexpr (Cfg::cc0) {
+                conv0_row<CIN, C, CH>(xcur, s.vec, col0, x0);
+            } else {
+                ld_row<CH>(lane_base + Cfg::col_x0 + col0, x0);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) x0[i] = fmaxf(x0[i], 0.f);
+            }
+            unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) {
+                const unsigned long long xz = pk2(x0[i], x0[i + 1]);
+                const unsigned long long x1 = add2(pk2(v[i], v[i + 1]), xz);
+                s2 = add2(s2, x1);
+                q2 = fma2(x1, x1, q2);
+                upk2(x1, v[i], v[i + 1]);
+                upk2(add2(x1, xz), x0[i], x0[i + 1]);
+            }
+#ifndef EXP_NO_STORE
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < CH / 4; ++j)
+                    *reinterpret_cast<float4*>(qout + row_off + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
+            }
+#endif
+            float sum, sq;
+            { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            norm_row<CH>(v, rstd, shift);
+            row_to_a<CH>(v, regU, row, col0);
+        }
+        sync_for_mma();
+        // ---- phase 2: conv1 -> LeakyReLU(0.2); the next tile's reads go out under it (v' / x regions were released by phase 1)
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC1>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (t + (int)gridDim.x < ntiles) prefetch(t + gridDim.x);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+#pragma unroll
+        for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
+            float l0, l1;
+            upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
+            v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
+        }
+        row_to_a<CH>(v, regU, row, col0);
+        sync_for_mma();
+        // ---- phase 3: conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(regU + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
+#ifndef EXP_NO_STORE
+            if (valid) *reinterpret_cast<float4*>(rout + row_off + 4 * j) = o;
+#endif
+        }
+        __syncthreads();
+        unit_channel_sums<C>(regU, t, geo.total_units, partial);
+        __syncthreads();
+    }
+    tc_finish(tm, Cfg::ncols);
+}
+
+
+// ------------------------------------------------------------------------------------------ merge kernel of the network-input stage
+// (CIN = 3, C = 32: 64x the pixel rows of the last stage, the largest single kernel of the detector.)  The 3-phase kernel
+// above measured 4.2 ms per 64 images of which 1.5 ms was compute: its per-thread 16-byte global loads and stores neither
+// overlapped the phases nor coalesced (32 sectors per warp instruction).  Here every tile-sized transfer is ONE bulk copy
+// issued by the elected lane: u' and v' arrive from the branch kernels already tf32-rounded in the swizzled panel layout,
+// land in shared memory as valid SWIZZLE_128B operands (no thread touches them) a tile ahead of their use, and q / r leave
+// through swizzled staging tiles with bulk stores that drain under the following phases.  x0 = ReLU(conv.0(x)) is computed
+// on the CUDA cores while the dense2 MMAs run.  Consumers of r / q (pool_kernel) un-permute the chunks.
+struct MergeL1Cfg {
+    static constexpr int C = 32, CH = 16;
+    static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;        // 16 KB
+    static constexpr uint32_t region = 4 * tile_bytes;                  // U | V | W (conv1 / conv2 input, r staging) | Q (q staging)
+    static constexpr int ncols = 32;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(NT2, 2)
+tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
+                   const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    using Cfg = MergeL1Cfg;
+    constexpr int C = Cfg::C, CH = Cfg::CH;
+    using G = MergeG<CIN, C>;
+    static_assert(G::resident, "stage-1 weights are resident");
+    const TcShared s = carve(smem, Cfg::region, plan);
+    float* const regU = s.region;
+    float* const regV = regU + (size_t)TM * C;
+    float* const regW = regV + (size_t)TM * C;
+    float* const regQ = regW + (size_t)TM * C;
+    uint64_t* const ld_bar = s.full + 1;                    // resident plan: full[0] is the weight barrier, the other ring barriers are free
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
+    const int ntiles = geo.total_units / 2;                 // host guarantees an even unit count: whole tiles only
+    const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    conv0_stage_weights<CIN, C>(w, s.vec);
+    Ring ring;
+    const bool w0 = warp0_uniform();
+    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
+    const uint32_t tm = *s.tmem_slot;
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
+    const uint32_t u_addr = smem_u32(regU), v_addr = smem_u32(regV), w_addr = smem_u32(regW), q_addr = smem_u32(regQ);
+    const uint32_t ones_addr = smem_u32(s.ones);
+    const int col0 = half * CH;
+    const size_t npix = (size_t)geo.h * geo.w;
+    const size_t tile_floats = (size_t)TM * C;              // tile t of the batch chunk starts at float t * tile_floats in u', v', r, q
+    uint32_t phase = 0, ld_phase = 0, xb = 0;
+    auto coords = [&](int tt, int& im, int& px) {
+        const int un = 2 * tt + (row >> 6);
+        im = fast_div(un, geo.upi, geo.inv_upi);
+        px = (un - im * geo.upi) * 64 + (row & 63);
+    };
+    auto load_tile = [&](int tt) {                          // elected lane: next tile's u' and v' -> U, V
+        mbar_expect_tx(ld_bar, 2 * Cfg::tile_bytes);
+        bulk_load(u_addr, uin + (size_t)tt * tile_floats, Cfg::tile_bytes, ld_bar);
+        bulk_load(v_addr, vin + (size_t)tt * tile_floats, Cfg::tile_bytes, ld_bar);
+    };
+    InputPf<CIN> pfx;
+    if ((int)blockIdx.x < ntiles) {
+        int im, px;
+        coords(blockIdx.x, im, px);
+        fetch_input_row<CIN>(xin, npix, (size_t)im, px, true, half, pfx);
+        if (w0 && elect_one()) load_tile(blockIdx.x);
+    }
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int nt = t + (int)gridDim.x;
+        float v[CH], x0[CH];
+        // ---- phase 1: acc = dense2([u', v']) on the tensor core | x0 = ReLU(conv.0(x)) on the CUDA cores
+        if (w0 && elect_one()) {
+            mbar_wait(ld_bar, ld_phase & 1);
+            fence_after_sync();
+            issue_linear_t<G, MG_PD2A, true>(ring, plan, u_addr, ones_addr, tm, true);
+            issue_linear_t<G, MG_PD2B, true>(ring, plan, v_addr, ones_addr, tm, false);
+            commit(s.done);
+            bulk_wait_read();                               // the previous tile's q / r stores have left W and Q
+        }
+        ++ld_phase;
+        conv0_row<CIN, C, CH>(pfx.v[0], s.vec, col0, x0);
+        if (nt < ntiles) {
+            int im, px;
+            coords(nt, im, px);
+            fetch_input_row<CIN>(xin, npix, (size_t)im, px, true, half, pfx);
+        }
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        // x1 = acc + x0; q = x1 + x0 -> Q (staging); LayerNorm(x1) (affine folded into conv1) -> W
+        {
+            float rstd, shift;
+            ld_row<CH>(lane_base + col0, v);
+            unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) {
+                const unsigned long long xz = pk2(x0[i], x0[i + 1]);
+                const unsigned long long x1 = add2(pk2(v[i], v[i + 1]), xz);
+                s2 = add2(s2, x1);
+                q2 = fma2(x1, x1, q2);
+                upk2(x1, v[i], v[i + 1]);
+                upk2(add2(x1, xz), x0[i], x0[i + 1]);
+            }
+            row_to_sw<CH, false>(x0, regQ, row, col0);
+            float sum, sq;
+            { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
+            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            norm_row<CH>(v, rstd, shift);
+            row_to_sw<CH, true>(v, regW, row, col0);
+        }
+        sync_for_mma();
+        // ---- phase 2: conv1 -> LeakyReLU(0.2); q leaves, the next tile's u' / v' arrive (phase 1 released U and V)
+        if (w0 && elect_one()) {
+            issue_linear_t<G, MG_RC1, true>(ring, plan, w_addr, ones_addr, tm, true);
+            commit(s.done);
+            bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
+            bulk_commit();
+            if (nt < ntiles) load_tile(nt);
+        }
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        ld_row<CH>(lane_base + col0, v);
+#pragma unroll
+        for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
+            float l0, l1;
+            upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
+            v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
+        }
+        row_to_sw<CH, true>(v, regW, row, col0);
+        sync_for_mma();
+        // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, true>(ring, plan, w_addr, ones_addr, tm, true); commit(s.done); }
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        ld_row<CH>(lane_base + col0, v);
+        row_to_sw<CH, false>(v, regW, row, col0);
+        sync_for_mma();
+        if (w0 && elect_one()) {
+            bulk_store(rout + (size_t)t * tile_floats, w_addr, Cfg::tile_bytes);
+            bulk_commit();
+        }
+        {   // channel sums of each unit from the swizzled staging tile (see unit_channel_sums; same fixed order)
+            constexpr int CQ = C / 4, TPP = NT2 / (2 * CQ), RPT = 64 / TPP;
+            const int pair = tid / TPP, sub = tid % TPP;
+            const int uu = pair / CQ, ch = pair % CQ;
+            float4 acc = *reinterpret_cast<const float4*>(regW + sw_off(uu * 64 + sub, ch));
+#pragma unroll
+            for (int i = 1; i < RPT; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(regW + sw_off(uu * 64 + sub + i * TPP, ch));
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            }
+#pragma unroll
+            for (int o = TPP / 2; o >= 1; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (sub == 0) *reinterpret_cast<float4*>(partial + (size_t)(2 * t + uu) * C + ch * 4) = acc;
+        }
+        // W is next written by the following tile's phase-1 epilogue, i.e. after its wait_done barrier: every thread has
+        // finished the sums by then, and the elected lane has waited for the r store to have read W (bulk_wait_read)
+    }
+    if (w0 && elect_one()) bulk_wait_all();
     tc_finish(tm, Cfg::ncols);
 }
 
@@ -885,6 +1356,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
                                                          const float* __restrict__ scale, TcPlan plan, UnitGeom geo, int cell,
                                                          float* __restrict__ logits, float* __restrict__ prob) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    using G = HeadG<C>;
     constexpr uint32_t region_bytes = (uint32_t)TM * C * 4;
     constexpr int ncols = tc_cols(C + 96);
     constexpr int CH = C / 2;
@@ -894,7 +1366,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
     const bool w0 = warp0_uniform();
-    tc_prologue(s, ncols, ring, plan, my_tiles, w0);
+    tc_prologue<HeadG<C>::nslot>(s, ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -906,7 +1378,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int unit = 2 * t + ug;
         const bool valid = unit < geo.total_units;
-        const int img = valid ? unit / geo.upi : 0, u = valid ? unit - img * geo.upi : 0;
+        const int img = valid ? fast_div(unit, geo.upi, geo.inv_upi) : 0, u = valid ? unit - img * geo.upi : 0;
         const int pix = u * 64 + tok;
         const size_t row_off = ((size_t)img * npix + pix) * C + col0;
 #pragma unroll 4
@@ -922,7 +1394,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
         }
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         {
             float v[CH];
             ld_row<CH>(lane_base + col0, v);
@@ -932,7 +1404,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
         }
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
-        wait_done(s.done, phase);
+        wait_done_ring<G>(s.done, phase, ring, plan, w0);
         // logits = columns C .. C+64 of the row.  tcgen05.ld is warp-collective and `half` is warp-uniform, so the
         // branch below is convergent per warp.
         if (half == 0) {
@@ -978,7 +1450,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ wT, int ld, int n0, int
         if (gamma) v *= gamma[k];
         if (alpha) v *= alpha[n0 + n];
     }
-    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = to_tf32(v);
+    dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = to_tf32_exact(v);
 }
 // bias columns of the last block: b' = (bias[n] + sum_k W[n][k] beta[k]) * alpha[n] + add[n], split into tf32 hi + lo
 __global__ void tc_pack_bias_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real,
@@ -997,7 +1469,7 @@ __global__ void tc_pack_bias_kernel(const float* __restrict__ wT, int ld, int n0
     }
     if (alpha) acc *= alpha[n0 + n];
     if (add) acc += add[n0 + n];
-    const float hi = to_tf32(acc), lo = to_tf32(acc - hi);
+    const float hi = to_tf32_exact(acc), lo = to_tf32_exact(acc - hi);
     dst[n * 4 + 0] = hi;
     dst[n * 4 + 1] = lo;
     dst[n * 4 + 2] = 0.f;
@@ -1009,8 +1481,8 @@ struct TcPlans {
     size_t floats;
 };
 
-static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias) {
-    const int kb = tc_kb(rows, K);
+static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768) {
+    const int kb = tc_kb(rows, K, cap);
     TcGemm& g = p.g[gi];
     g.goff = (uint32_t)off;
     g.nblk = (uint16_t)(K / kb);
@@ -1025,12 +1497,12 @@ static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias) {
 
 template <typename G>
 static bool plan_matches(const TcPlan& p) {
-    if (p.ngemm != G::count || (p.resident != 0) != G::resident) return false;
+    if (p.ngemm != G::count || (p.resident != 0) != G::resident || (int)p.nslot != G::nslot) return false;
     uint32_t off = 0;
     bool ok = true;
     for (int gi = 0; gi < G::count; ++gi) {
         const TcGemm& g = p.g[gi];
-        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi)) && g.nblk * g.kb == G::K(gi) &&
+        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap) && g.nblk * g.kb == G::K(gi) &&
              (g.bias != 0) == G::bias(gi) && gemm_bytes(g) == g_bytes<G>(gi) && (g.goff - p.g[0].goff) * 4u == off;
         off += gemm_bytes(g);
     }
@@ -1047,6 +1519,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
             p.base = base; p.ngemm = BG_COUNT; p.resident = resident;
+            p.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                  // mirrors BranchG::nslot (checked by plan_matches)
             tc_add(p, BG_CONV0, off, c, cin, true);
             tc_add(p, BG_PD1, off, c, c, true);
             tc_add(p, BG_D1A, off, c, c, true);
@@ -1057,15 +1530,17 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        tc_add(m, MG_CONV0, off, c, cin, true);
-        tc_add(m, MG_PD2A, off, c, c, false);
-        tc_add(m, MG_PD2B, off, c, c, true);
-        tc_add(m, MG_RC1, off, c, c, true);
-        tc_add(m, MG_RC2, off, c, c, true);
+        m.nslot = c == 128 ? 4 : 2;                                    // mirrors MergeG::nslot / MergeG::cap
+        const int mcap = c == 64 ? 8192 : 32768;
+        tc_add(m, MG_CONV0, off, c, cin, true, mcap);
+        tc_add(m, MG_PD2A, off, c, c, false, mcap);
+        tc_add(m, MG_PD2B, off, c, c, true, mcap);
+        tc_add(m, MG_RC1, off, c, c, true, mcap);
+        tc_add(m, MG_RC2, off, c, c, true, mcap);
     }
     TcPlan& h = P.head;
     h = TcPlan{};
-    h.base = base; h.ngemm = HG_COUNT; h.resident = 0;
+    h.base = base; h.ngemm = HG_COUNT; h.resident = 0; h.nslot = 2;
     tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true);
     tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true);
     P.floats = off;
@@ -1162,7 +1637,8 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
 template <int CIN, int C>
 static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int level, int Bc, int h, int wd,
                         float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
-    UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64)};
+    UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64), 1.0f / (float)(h * wd / 64), 1.0f / (float)(wd / 8), 1.0f / (float)(wd / 8)};
+    BALF_REQUIRE(g.total_units < (1 << 23), "internal: %d units in one pass exceed the fast_div range", g.total_units);
     const int ntiles = (g.total_units + 1) / 2;
     int grid = 0;
     BALF_REQUIRE((plan_matches<BranchG<CIN, C>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C>>(P.branch[level][1]) &&
@@ -1180,11 +1656,24 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
             tc_branch_kernel<CIN, C, 1><<<grid, NT2, smem, st>>>(xin, w, p, g, v);
         }
     }
-    {
+    if constexpr (C == 32) {
+        const TcPlan& p = P.merge[level];
+        BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at the network-input stage");
+        const size_t smem = tc_smem_bytes(MergeL1Cfg::region, p);
+        if (int e = tc_launch_cfg(tc_merge_l1_kernel<CIN>, smem, MergeL1Cfg::ncols, ntiles, &grid)) return e;
+        ProfScope ps("det_merge_c32", st);
+        tc_merge_l1_kernel<CIN><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+    } else if constexpr (C <= 64) {
+        const TcPlan& p = P.merge[level];
+        const size_t smem = tc_smem_bytes(Merge3Cfg<CIN, C>::region, p);
+        if (int e = tc_launch_cfg(tc_merge3_kernel<CIN, C>, smem, Merge3Cfg<CIN, C>::ncols, ntiles, &grid)) return e;
+        ProfScope ps(C == 32 ? "det_merge_c32" : "det_merge_c64", st);
+        tc_merge3_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+    } else {
         const TcPlan& p = P.merge[level];
         const size_t smem = tc_smem_bytes(MergeCfg<C>::region, p);
         if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, MergeCfg<C>::ncols, ntiles, &grid)) return e;
-        ProfScope ps(C == 32 ? "det_merge_c32" : C == 64 ? "det_merge_c64" : C == 128 ? "det_merge_c128" : "det_merge_c256", st);
+        ProfScope ps(C == 128 ? "det_merge_c128" : "det_merge_c256", st);
         tc_merge_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     }
     BALF_COUNT_LAUNCH(3);
@@ -1210,7 +1699,8 @@ int tc_run_head(const float* r, const float* q, const float* scale, const DownW&
     (void)w; (void)hw;
     TcPlans P;
     tc_build_plans(a, blob, &P);
-    UnitGeom g{hc, wc, hc / 8, wc / 8, hc * wc / 64, Bc * (hc * wc / 64)};
+    UnitGeom g{hc, wc, hc / 8, wc / 8, hc * wc / 64, Bc * (hc * wc / 64), 1.0f / (float)(hc * wc / 64), 1.0f / (float)(wc / 8), 1.0f / (float)(wc / 8)};
+    BALF_REQUIRE(g.total_units < (1 << 23), "internal: %d units in one pass exceed the fast_div range", g.total_units);
     const int ntiles = (g.total_units + 1) / 2;
     const size_t smem = tc_smem_bytes((uint32_t)TM * 256 * 4, P.head);
     int grid = 0;

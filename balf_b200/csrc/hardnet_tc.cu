@@ -419,7 +419,7 @@ __global__ void hn_tc_pack_kernel(const float* __restrict__ wT, const float* __r
     const int n = i % cout, ci = (i / cout) % cin, tap = i / (cout * cin);
     const int kp = ci / kb, kk = ci - kp * kb;
     const float v = wT[((size_t)ci * 9 + tap) * cout + n] * scale[n];
-    dst[(size_t)(tap * (cin / kb) + kp) * cout * kb + (size_t)(kk >> 2) * cout * 4 + n * 4 + (kk & 3)] = to_tf32(v);
+    dst[(size_t)(tap * (cin / kb) + kp) * cout * kb + (size_t)(kk >> 2) * cout * 4 + n * 4 + (kk & 3)] = to_tf32_exact(v);
 }
 // final layer: wT [cin = 128][64 positions][cout = 128] * scale -> K blocks (position, 32 channels) of [128 rows][32], tf32
 __global__ void hn_tc_pack_final_kernel(const float* __restrict__ wT, const float* __restrict__ scale, float* __restrict__ dst) {
@@ -427,7 +427,7 @@ __global__ void hn_tc_pack_final_kernel(const float* __restrict__ wT, const floa
     if (i >= 8192 * 128) return;
     const int n = i % 128, c = (i / 128) % 128, pos = i / (128 * 128);
     const int blk = pos * 4 + c / 32, kk = c % 32;
-    dst[(size_t)blk * kFinalBlockFloats + (size_t)(kk >> 2) * 512 + n * 4 + (kk & 3)] = to_tf32(wT[((size_t)c * 64 + pos) * 128 + n] * scale[n]);
+    dst[(size_t)blk * kFinalBlockFloats + (size_t)(kk >> 2) * 512 + n * 4 + (kk & 3)] = to_tf32_exact(wT[((size_t)c * 64 + pos) * 128 + n] * scale[n]);
 }
 __global__ void hn_tc_pack_first_kernel(const float* __restrict__ wT, const float* __restrict__ scale, float* __restrict__ dst) {
     const int i = threadIdx.x + blockIdx.x * blockDim.x;

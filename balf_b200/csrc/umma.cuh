@@ -157,9 +157,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// fp32 -> tf32 with round-to-nearest (the tensor core itself truncates the low 13 mantissa bits; rounding the
-// operands first halves the worst-case error and removes the towards-zero bias)
-__device__ __forceinline__ float to_tf32(float x) {
+// fp32 -> tf32 with round-to-nearest (the tensor core itself ignores -- truncates -- the low 13 mantissa bits; rounding the
+// operands first halves the worst-case error and removes the towards-zero bias).  Because the hardware drops the low
+// bits anyway, rounding the magnitude to nearest (ties away, = cvt.rna.tf32.f32) is ONE integer add of half a tf32 ulp to
+// the bit pattern; cvt.rna itself expands to FSETP + IMAD + LOP3 (+ SEL) on sm_100 and was ~20 % of the detector's epilogue
+// instructions.  The low bits of the result are not cleared -- the MMA does not read them.  Finite inputs only (an
+// all-ones exponent would carry into the sign); activations and weights here are finite by construction.
+#ifndef BALF_TF32_CLEAN
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+#else      // experiment switch: clear the low bits as well (two instructions)
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+#endif
+// same rounding with the low bits cleared (idempotent): for values that may be rounded again downstream
+__device__ __forceinline__ float to_tf32_clean(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 to_tf32_clean(float4 v) { return make_float4(to_tf32_clean(v.x), to_tf32_clean(v.y), to_tf32_clean(v.z), to_tf32_clean(v.w)); }
+// the PTX conversion (NaN / infinity safe): weight packing
+__device__ __forceinline__ float to_tf32_exact(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);

@@ -1,14 +1,14 @@
 #!/bin/bash
-# Fast GPU iteration: tensor-core detector parity + a short bench (no CPU baseline leg).
+# Quick GPU iteration: tf32 detector parity tests + device-only bench (no CPU legs).  Outputs in gpurun_out/.
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_detector_tf32.py tests/test_gpu_detector.py -q --tb=line 2>&1 | tail -8
-timeout 600 python bench.py --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench exit $?"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_quick.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_quick.log
+tail -4 gpurun_out/pytest_quick.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench exit $?"
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/bench_quick.json"))
-print("value %.1f img/s  e2e %.1f  ms/step %.2f  det %.2f ms  clocks %s" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["detector"]["ms_per_step"], d["clocks"]))
-for k, v in d["kernels"].items():
-    print("  %-24s %8.3f ms %5.1f%%" % (k, v["ms_per_step"], 100 * v["share"]))
+d = json.loads(open('gpurun_out/bench_quick.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'e2e', d['e2e']['value'], 'ms', d['ms_per_step'])
+for n, k in sorted(d['kernels'].items(), key=lambda x: -x[1]['ms_per_step']):
+    print('  %-24s %8.3f ms  %s %s' % (n, k['ms_per_step'], k['bound'], k['frac']))
 PY
-tail -3 gpurun_out/bench_quick.err
