@@ -392,11 +392,13 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
             size_t p = (b * h + 2 * py + dy) * w + 2 * px + dx;
-            // swz: r / q of the tensor-core stage-1 merge kernel are in the swizzled panel layout (detector_tc.cu sw_off;
-            // C = 32 is a single panel: the chunks of a pixel's 128-byte row are permuted by (pixel % 8))
-            const int cs = swz ? (c4 ^ (int)(p & 7)) : c4;
-            float4 rv = __ldg(reinterpret_cast<const float4*>(r + p * C) + cs);
-            float4 qv = __ldg(reinterpret_cast<const float4*>(q + p * C) + cs);
+            // swz: r / q of the tensor-core merge kernels of the first two stages are tiles of 128 pixels in the swizzled
+            // panel layout (detector_tc.cu sw_off): panels of 32 channels, 128-byte rows, chunks permuted by (pixel % 8)
+            const size_t rowi = p & 127;
+            const size_t cs = swz ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
+                                  : ((p * C) >> 2) + c4;
+            float4 rv = __ldg(reinterpret_cast<const float4*>(r) + cs);
+            float4 qv = __ldg(reinterpret_cast<const float4*>(q) + cs);
             best.x = fmaxf(best.x, rv.x * s.x + qv.x); best.y = fmaxf(best.y, rv.y * s.y + qv.y);
             best.z = fmaxf(best.z, rv.z * s.z + qv.z); best.w = fmaxf(best.w, rv.w * s.w + qv.w);
         }
@@ -717,7 +719,7 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
             if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
             if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;
         } else if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
-        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st)) return e;
+        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) != 0)) return e;
         if (tcm & 4) {
             if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
             if (int e = run_se<128>(ws, d[2], Bc, Hp * Wp / 16, Hp * Wp / 1024, st)) return e;

@@ -166,8 +166,8 @@ template <int CIN, int C> struct BranchG {
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
     static constexpr bool resident = C <= 32;
-    static constexpr int cap = C == 64 ? 8192 : 32768;     // C = 64: three operand regions share the CTA with the ring
-    static constexpr int nslot = C == 128 ? 4 : 2;
+    static constexpr int cap = 32768;
+    static constexpr int nslot = C == 64 ? 3 : C == 128 ? 4 : 2;
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
@@ -423,6 +423,7 @@ struct TcShared {
     uint64_t* full;
     uint64_t* empty;
     uint64_t* done;
+    uint64_t* aux;         // kernel-specific barrier (bulk-loaded tiles of tc_merge_bulk_kernel)
     uint32_t* tmem_slot;
 };
 constexpr uint32_t kSchedEntries = 62;
@@ -446,7 +447,8 @@ __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_b
     s.full = bars;
     s.empty = bars + kMaxSlot;
     s.done = bars + 2 * kMaxSlot;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlot + 1);
+    s.aux = bars + 2 * kMaxSlot + 1;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlot + 2);
     return s;
 }
 
@@ -456,6 +458,7 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMaxSlot; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.done, 1);
+        mbar_init(s.aux, 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 2 * TM; i += NT2)
@@ -632,7 +635,7 @@ template <int C> struct BranchCfg {
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
-    static constexpr bool swz_out = C == 32;                       // u' / v' leave in the swizzled panel layout (tc_merge_l1_kernel)
+    static constexpr bool swz_out = C <= 64;                       // u' / v' leave in the swizzled panel layout (tc_merge_bulk_kernel)
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
@@ -825,8 +828,8 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                         // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
                         // the C >= 128 merge kernels round again when they load, which must be a no-op
                         if (BR == 1 || Cfg::swz_out) o = to_tf32_clean(o);
-                        if (Cfg::swz_out)    // C == 32: one 128-byte row per pixel, chunks permuted by (pixel % 8) = swizzled panel layout
-                            *reinterpret_cast<float4*>(orow - col0 + ((((col0 + c) / 4 + j) ^ (pix & 7)) << 2)) = o;
+                        if (Cfg::swz_out)    // tile of 128 consecutive pixels, swizzled panel layout (sw_off); 128 | pixels per image
+                            *reinterpret_cast<float4*>(out + ((size_t)img * npix + (pix & ~(TM - 1))) * C + sw_off(pix & (TM - 1), (col0 + c) / 4 + j)) = o;
                         else
                             *reinterpret_cast<float4*>(orow + c + 4 * j) = o;
                     }
@@ -1030,44 +1033,44 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
 }
 
 
-// ------------------------------------------------------------------------------------------ merge kernel, 3 phases (C <= 64)
-// Same mathematics as tc_merge_kernel, restructured around its latencies (it was neither issue- nor DRAM-bound: 22 % issue
-// utilisation, 28-37 % of HBM).  Three operand regions [u' | v' | x] hold a whole tile's inputs at once, so conv.0, dense2(u')
-// and dense2(v') are issued back to back in ONE phase (5 -> 3 commit / wait / barrier round trips per tile, x0 never parked
-// in TMEM).  Every global read of tile t+1 is requested during tile t: x and u' rows into registers, v' (already
-// tf32-rounded by the block-branch kernel) straight into its region with cp.async as soon as phase 1 has released it.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const uint32_t n = valid ? 16u : 0u;           // src-size 0: the 16 bytes are zero-filled, nothing is read
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int CIN, int C> struct Merge3Cfg {
+// ------------------------------------------------------------------------------------------ merge kernel with bulk-copied tiles (C <= 64)
+// The first two stages hold 64x / 16x the pixel rows of the last one and their merge kernels are the largest of the detector.
+// A first 3-phase version with per-thread loads / stores measured 4.2 ms per 64 images at C = 32 of which 1.5 ms was compute:
+// its 16-byte global accesses neither overlapped the phases nor coalesced (32 sectors per warp instruction).  Here every
+// tile-sized transfer is ONE bulk copy issued by the elected lane: u' and v' arrive from the branch kernels already
+// tf32-rounded in the swizzled panel layout, land in shared memory as valid SWIZZLE_128B operands (no thread touches
+// them) a tile ahead of their use, and q / r leave through swizzled staging tiles with bulk stores that drain under the
+// following phases.  At C = 32 (CIN = 3) x0 = ReLU(conv.0(x)) runs on the CUDA cores while the dense2 MMAs execute; at
+// C = 64 conv.0 is a third MMA of phase 1 on a register-prefetched x tile.  Consumers of r / q (pool_kernel) un-permute.
+// Regions: U | V (operands of dense2) | W (conv1 / conv2 input, then r staging) | Q (q staging) | X (conv.0 operand).
+template <int CIN, int C> struct MergeBulkCfg {
     static constexpr int CH = C / 2;
-    static constexpr bool cc0 = CIN < 8;                            // conv.0 on the CUDA cores (network input)
-    static constexpr uint32_t ubytes = (uint32_t)TM * C * 4;
+    static constexpr bool cc0 = CIN < 8;
+    static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;
     static constexpr uint32_t xbytes = cc0 ? 0u : (uint32_t)TM * tc_kin(CIN) * 4;
-    static constexpr uint32_t region = 2 * ubytes + xbytes;
-    static constexpr int col_x0 = 0, col_acc = C;
-    static constexpr int ncols = tc_cols(2 * C);
-    static constexpr int min_ctas = C <= 32 ? 3 : 2;
+    static constexpr uint32_t region = 4 * tile_bytes + xbytes;
+    static constexpr int col_acc = 0, col_x0 = C;
+    static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
+    static constexpr int min_ctas = C <= 32 ? 2 : 1;
 };
 
 template <int CIN, int C>
-__global__ void __launch_bounds__(NT2, Merge3Cfg<CIN, C>::min_ctas)
-tc_merge3_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
-                 const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
+__global__ void __launch_bounds__(NT2, MergeBulkCfg<CIN, C>::min_ctas)
+tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
+                     const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = Merge3Cfg<CIN, C>;
-    using G = MergeG<CIN, C>;
+    using Cfg = MergeBulkCfg<CIN, C>;
     constexpr int CH = Cfg::CH;
+    using G = MergeG<CIN, C>;
     const TcShared s = carve(smem, Cfg::region, plan);
     float* const regU = s.region;
     float* const regV = regU + (size_t)TM * C;
-    float* const regX = regV + (size_t)TM * C;
+    float* const regW = regV + (size_t)TM * C;
+    float* const regQ = regW + (size_t)TM * C;
+    float* const regX = regQ + (size_t)TM * C;
+    uint64_t* const ld_bar = s.aux;
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
-    const int ntiles = (geo.total_units + 1) / 2;
+    const int ntiles = geo.total_units / 2;                 // host guarantees an even unit count: whole tiles only
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     if constexpr (Cfg::cc0) conv0_stage_weights<CIN, C>(w, s.vec);
     Ring ring;
@@ -1075,162 +1078,8 @@ tc_merge3_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
-    const uint32_t u_addr = smem_u32(regU), v_addr = smem_u32(regV), x_addr = smem_u32(regX), ones_addr = smem_u32(s.ones);
-    const int ug = row >> 6, tok = row & 63;
-    const int col0 = half * CH;
-    const size_t npix = (size_t)geo.h * geo.w;
-    uint32_t phase = 0, xb = 0;
-    InputPf<CIN> pfx;                      // next tile's level input
-    InputPf<C> pfu;                        // next tile's u' rows
-    auto coords = [&](int tt, bool& vld, int& im, int& px) {
-        const int un = 2 * tt + ug;
-        vld = un < geo.total_units;
-        im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
-        px = (vld ? un - im * geo.upi : 0) * 64 + tok;
-    };
-    auto prefetch = [&](int tt) {
-        bool vld; int im, px;
-        coords(tt, vld, im, px);
-#ifdef EXP_NO_LOAD
-        vld = false;
-#endif
-        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pfx);
-        fetch_input_row<C>(uin, npix, (size_t)im, px, vld, half, pfu);
-        const float* vsrc = vin + ((size_t)im * npix + px) * C + col0;
-#pragma unroll
-        for (int j = 0; j < CH / 4; ++j)
-            cp_async16(v_addr + (uint32_t)(((col0 / 4 + j) * TM + row) * 16), vsrc + 4 * j, vld);
-        cp_async_commit();
-    };
-    if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        bool valid; int img, pix;
-        coords(t, valid, img, pix);
-        const size_t row_off = ((size_t)img * npix + pix) * C + col0;
-        float v[CH];
-        // ---- phase 1: x0 = ReLU(conv.0(x)) | acc = dense2([u', v'])
-        float4 xcur = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (Cfg::cc0) xcur = pfx.v[0];
-        else store_input_row<CIN>(pfx, regX, row, half);
-        store_input_row<C>(pfu, regU, row, half);
-        cp_async_wait_all();
-        sync_for_mma();
-        if (w0 && elect_one()) {
-            if constexpr (!Cfg::cc0) issue_linear_t<G, MG_CONV0>(ring, plan, x_addr, ones_addr, tm + Cfg::col_x0, true);
-            issue_linear_t<G, MG_PD2A>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true);
-            issue_linear_t<G, MG_PD2B>(ring, plan, v_addr, ones_addr, tm + Cfg::col_acc, false);
-            commit(s.done);
-        }
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
-        // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
-        {
-            float rstd, shift, x0[CH];
-            ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
-            if constexpr (Cfg::cc0) {
-                conv0_row<CIN, C, CH>(xcur, s.vec, col0, x0);
-            } else {
-                ld_row<CH>(lane_base + Cfg::col_x0 + col0, x0);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) x0[i] = fmaxf(x0[i], 0.f);
-            }
-            unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < CH; i += 2) {
-                const unsigned long long xz = pk2(x0[i], x0[i + 1]);
-                const unsigned long long x1 = add2(pk2(v[i], v[i + 1]), xz);
-                s2 = add2(s2, x1);
-                q2 = fma2(x1, x1, q2);
-                upk2(x1, v[i], v[i + 1]);
-                upk2(add2(x1, xz), x0[i], x0[i + 1]);
-            }
-#ifndef EXP_NO_STORE
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < CH / 4; ++j)
-                    *reinterpret_cast<float4*>(qout + row_off + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
-            }
-#endif
-            float sum, sq;
-            { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
-            norm_row<CH>(v, rstd, shift);
-            row_to_a<CH>(v, regU, row, col0);
-        }
-        sync_for_mma();
-        // ---- phase 2: conv1 -> LeakyReLU(0.2); the next tile's reads go out under it (v' / x regions were released by phase 1)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC1>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
-        if (t + (int)gridDim.x < ntiles) prefetch(t + gridDim.x);
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
-        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
-#pragma unroll
-        for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
-            float l0, l1;
-            upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
-            v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
-        }
-        row_to_a<CH>(v, regU, row, col0);
-        sync_for_mma();
-        // ---- phase 3: conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
-        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
-#pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
-            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<float4*>(regU + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
-#ifndef EXP_NO_STORE
-            if (valid) *reinterpret_cast<float4*>(rout + row_off + 4 * j) = o;
-#endif
-        }
-        __syncthreads();
-        unit_channel_sums<C>(regU, t, geo.total_units, partial);
-        __syncthreads();
-    }
-    tc_finish(tm, Cfg::ncols);
-}
-
-
-// ------------------------------------------------------------------------------------------ merge kernel of the network-input stage
-// (CIN = 3, C = 32: 64x the pixel rows of the last stage, the largest single kernel of the detector.)  The 3-phase kernel
-// above measured 4.2 ms per 64 images of which 1.5 ms was compute: its per-thread 16-byte global loads and stores neither
-// overlapped the phases nor coalesced (32 sectors per warp instruction).  Here every tile-sized transfer is ONE bulk copy
-// issued by the elected lane: u' and v' arrive from the branch kernels already tf32-rounded in the swizzled panel layout,
-// land in shared memory as valid SWIZZLE_128B operands (no thread touches them) a tile ahead of their use, and q / r leave
-// through swizzled staging tiles with bulk stores that drain under the following phases.  x0 = ReLU(conv.0(x)) is computed
-// on the CUDA cores while the dense2 MMAs run.  Consumers of r / q (pool_kernel) un-permute the chunks.
-struct MergeL1Cfg {
-    static constexpr int C = 32, CH = 16;
-    static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;        // 16 KB
-    static constexpr uint32_t region = 4 * tile_bytes;                  // U | V | W (conv1 / conv2 input, r staging) | Q (q staging)
-    static constexpr int ncols = 32;
-};
-
-template <int CIN>
-__global__ void __launch_bounds__(NT2, 2)
-tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
-                   const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = MergeL1Cfg;
-    constexpr int C = Cfg::C, CH = Cfg::CH;
-    using G = MergeG<CIN, C>;
-    static_assert(G::resident, "stage-1 weights are resident");
-    const TcShared s = carve(smem, Cfg::region, plan);
-    float* const regU = s.region;
-    float* const regV = regU + (size_t)TM * C;
-    float* const regW = regV + (size_t)TM * C;
-    float* const regQ = regW + (size_t)TM * C;
-    uint64_t* const ld_bar = s.full + 1;                    // resident plan: full[0] is the weight barrier, the other ring barriers are free
-    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
-    const int ntiles = geo.total_units / 2;                 // host guarantees an even unit count: whole tiles only
-    const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    conv0_stage_weights<CIN, C>(w, s.vec);
-    Ring ring;
-    const bool w0 = warp0_uniform();
-    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
-    const uint32_t tm = *s.tmem_slot;
-    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t u_addr = smem_u32(regU), v_addr = smem_u32(regV), w_addr = smem_u32(regW), q_addr = smem_u32(regQ);
-    const uint32_t ones_addr = smem_u32(s.ones);
+    const uint32_t x_addr = smem_u32(regX), ones_addr = smem_u32(s.ones);
     const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
     const size_t tile_floats = (size_t)TM * C;              // tile t of the batch chunk starts at float t * tile_floats in u', v', r, q
@@ -1255,17 +1104,22 @@ tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int nt = t + (int)gridDim.x;
         float v[CH], x0[CH];
-        // ---- phase 1: acc = dense2([u', v']) on the tensor core | x0 = ReLU(conv.0(x)) on the CUDA cores
+        // ---- phase 1: acc = dense2([u', v']) (+ conv.0(x) at CIN >= 8) on the tensor core | x0 on the CUDA cores at CIN < 8
+        if constexpr (!Cfg::cc0) {
+            store_input_row<CIN>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
+            sync_for_mma();
+        }
         if (w0 && elect_one()) {
+            if constexpr (!Cfg::cc0) issue_linear_t<G, MG_CONV0>(ring, plan, x_addr, ones_addr, tm + Cfg::col_x0, true);
             mbar_wait(ld_bar, ld_phase & 1);
             fence_after_sync();
-            issue_linear_t<G, MG_PD2A, true>(ring, plan, u_addr, ones_addr, tm, true);
-            issue_linear_t<G, MG_PD2B, true>(ring, plan, v_addr, ones_addr, tm, false);
+            issue_linear_t<G, MG_PD2A, true>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true);
+            issue_linear_t<G, MG_PD2B, true>(ring, plan, v_addr, ones_addr, tm + Cfg::col_acc, false);
             commit(s.done);
             bulk_wait_read();                               // the previous tile's q / r stores have left W and Q
         }
         ++ld_phase;
-        conv0_row<CIN, C, CH>(pfx.v[0], s.vec, col0, x0);
+        if constexpr (Cfg::cc0) conv0_row<CIN, C, CH>(pfx.v[0], s.vec, col0, x0);
         if (nt < ntiles) {
             int im, px;
             coords(nt, im, px);
@@ -1275,7 +1129,12 @@ tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom
         // x1 = acc + x0; q = x1 + x0 -> Q (staging); LayerNorm(x1) (affine folded into conv1) -> W
         {
             float rstd, shift;
-            ld_row<CH>(lane_base + col0, v);
+            ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+            if constexpr (!Cfg::cc0) {
+                ld_row<CH>(lane_base + Cfg::col_x0 + col0, x0);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) x0[i] = fmaxf(x0[i], 0.f);
+            }
             unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < CH; i += 2) {
@@ -1296,14 +1155,14 @@ tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom
         sync_for_mma();
         // ---- phase 2: conv1 -> LeakyReLU(0.2); q leaves, the next tile's u' / v' arrive (phase 1 released U and V)
         if (w0 && elect_one()) {
-            issue_linear_t<G, MG_RC1, true>(ring, plan, w_addr, ones_addr, tm, true);
+            issue_linear_t<G, MG_RC1, true>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
             commit(s.done);
             bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
             bulk_commit();
             if (nt < ntiles) load_tile(nt);
         }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
-        ld_row<CH>(lane_base + col0, v);
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
         for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
             float l0, l1;
@@ -1313,9 +1172,9 @@ tc_merge_l1_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom
         row_to_sw<CH, true>(v, regW, row, col0);
         sync_for_mma();
         // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, true>(ring, plan, w_addr, ones_addr, tm, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, true>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
-        ld_row<CH>(lane_base + col0, v);
+        ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
         row_to_sw<CH, false>(v, regW, row, col0);
         sync_for_mma();
         if (w0 && elect_one()) {
@@ -1530,8 +1389,8 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        m.nslot = c == 128 ? 4 : 2;                                    // mirrors MergeG::nslot / MergeG::cap
-        const int mcap = c == 64 ? 8192 : 32768;
+        m.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                      // mirrors MergeG::nslot / MergeG::cap
+        const int mcap = 32768;
         tc_add(m, MG_CONV0, off, c, cin, true, mcap);
         tc_add(m, MG_PD2A, off, c, c, false, mcap);
         tc_add(m, MG_PD2B, off, c, c, true, mcap);
@@ -1656,19 +1515,13 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
             tc_branch_kernel<CIN, C, 1><<<grid, NT2, smem, st>>>(xin, w, p, g, v);
         }
     }
-    if constexpr (C == 32) {
+    if constexpr (C <= 64) {
         const TcPlan& p = P.merge[level];
-        BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at the network-input stage");
-        const size_t smem = tc_smem_bytes(MergeL1Cfg::region, p);
-        if (int e = tc_launch_cfg(tc_merge_l1_kernel<CIN>, smem, MergeL1Cfg::ncols, ntiles, &grid)) return e;
-        ProfScope ps("det_merge_c32", st);
-        tc_merge_l1_kernel<CIN><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
-    } else if constexpr (C <= 64) {
-        const TcPlan& p = P.merge[level];
-        const size_t smem = tc_smem_bytes(Merge3Cfg<CIN, C>::region, p);
-        if (int e = tc_launch_cfg(tc_merge3_kernel<CIN, C>, smem, Merge3Cfg<CIN, C>::ncols, ntiles, &grid)) return e;
+        BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
+        const size_t smem = tc_smem_bytes(MergeBulkCfg<CIN, C>::region, p);
+        if (int e = tc_launch_cfg(tc_merge_bulk_kernel<CIN, C>, smem, MergeBulkCfg<CIN, C>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 32 ? "det_merge_c32" : "det_merge_c64", st);
-        tc_merge3_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+        tc_merge_bulk_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     } else {
         const TcPlan& p = P.merge[level];
         const size_t smem = tc_smem_bytes(MergeCfg<C>::region, p);
