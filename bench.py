@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--nms", default="windowed", choices=["windowed", "greedy"])
     p.add_argument("--precision", default=None, help="detector precision (default: the module's)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--chunk", type=int, default=0, help="development: images per internal detector pass (library default if 0)")
     return p.parse_args()
 
 
@@ -312,6 +313,8 @@ def main():
     from balf_b200.model import get_model
     from balf_b200.sharding import gather_keypoints
 
+    if a.chunk:
+        capi.debug_set(1, a.chunk)
     torch.manual_seed(0)
     det = get_model.load_model(model_cfg()).eval().to(dev)
     if a.precision:

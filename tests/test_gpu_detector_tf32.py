@@ -55,13 +55,20 @@ def test_golden_512x640(det_tc):
 def test_batches_units_and_determinism(det_tc, detector_sd):
     # odd unit counts (64x64 -> a single 64-token unit at the last stage), batches that cross the
     # internal chunk of 16 images, per-image independence and run-to-run bit reproducibility
+    import balf_b200._capi as capi
     xb = torch.rand(19, 3, 64, 64, generator=torch.Generator().manual_seed(3))
-    _, pb = run(det_tc, xb)
+    _, pb = run(det_tc, xb)                      # automatic chunk: one pass of 19 images
     _, pb2 = run(det_tc, xb)
     np.testing.assert_array_equal(pb.numpy(), pb2.numpy())
-    for i in (0, 7, 15, 16, 18):
-        _, pi = run(det_tc, xb[i:i + 1])
-        np.testing.assert_array_equal(pb[i].numpy(), pi[0].numpy())
+    capi.debug_set(1, 16)                        # pin the internal pass to 16 images: 19 = 16 + 3 crosses it
+    try:
+        _, pb3 = run(det_tc, xb)
+        np.testing.assert_array_equal(pb.numpy(), pb3.numpy())
+        for i in (0, 7, 15, 16, 18):
+            _, pi = run(det_tc, xb[i:i + 1])
+            np.testing.assert_array_equal(pb[i].numpy(), pi[0].numpy())
+    finally:
+        capi.debug_set(1, 0)
     with torch.inference_mode():
         o = odet.detector_forward(detector_sd, xb)
     np.testing.assert_allclose(pb.numpy(), o["prob"].numpy(), rtol=TF32_RTOL)
