@@ -400,10 +400,21 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- tile groups.  A CTA is NG independent groups of 256 threads (NG = 1 everywhere except the branch kernels of the
+// network-input stage): each group walks its own tiles with its own operand region, TMEM columns, completion barrier and
+// hardware named barrier (id 1 + group), and all groups share one resident copy of the weights.  This is how four tiles are
+// in flight per SM at C = 32 -- four separate CTAs would each need the 39 KB of weights.
+template <int NG>
+__device__ __forceinline__ void group_sync(int grp) {
+    if constexpr (NG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"(NT2) : "memory");
+}
+
 // LayerNorm statistics of a row whose two halves live in two threads: exchange (sum, sum of squares)
-__device__ __forceinline__ void row_stats(float sum, float sq, float2* xch, int row, int half, int C, float& rstd, float& shift) {
+template <int NG = 1>
+__device__ __forceinline__ void row_stats(float sum, float sq, float2* xch, int row, int half, int C, float& rstd, float& shift, int grp = 0) {
     xch[half * TM + row] = make_float2(sum, sq);
-    __syncthreads();
+    group_sync<NG>(grp);
     const float2 o = xch[(half ^ 1) * TM + row];
     const float inv_c = C == 32 ? 1.0f / 32 : C == 64 ? 1.0f / 64 : C == 128 ? 1.0f / 128 : 1.0f / 256;   // C is a literal at every call
     const float mean = (sum + o.x) * inv_c;
@@ -425,22 +436,25 @@ struct TcShared {
     uint64_t* done;
     uint64_t* aux;         // kernel-specific barrier (bulk-loaded tiles of tc_merge_bulk_kernel)
     uint32_t* tmem_slot;
+    uint64_t* gdone;       // [kMaxGroups] completion barriers of tile groups 1.. (group 0 uses `done`)
 };
+constexpr int kMaxGroups = 4;
 constexpr uint32_t kSchedEntries = 62;
 constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 128;
 __host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
     return p.resident ? (p.bytes + 127u) / 128u * 128u : p.nslot * p.slot_bytes;
 }
-__host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p) {
-    return region + tc_weight_bytes(p) + kOnesBytes + kXchBytes + kVecBytes + kSchedBytes + kTcTail;
+__host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p, uint32_t groups = 1) {
+    return groups * (region + kXchBytes) + tc_weight_bytes(p) + kOnesBytes + kVecBytes + kSchedBytes + kTcTail;
 }
-__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p) {
+// region / xch point at group 0's copy; group g's follow at g * region_bytes / g * kXchBytes
+__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p, uint32_t groups = 1) {
     TcShared s;
     unsigned char* q = smem;
-    s.region = reinterpret_cast<float*>(q); q += region_bytes;
+    s.region = reinterpret_cast<float*>(q); q += groups * region_bytes;
     s.wsm = smem_u32(q); q += tc_weight_bytes(p);
     s.ones = reinterpret_cast<float*>(q); q += kOnesBytes;
-    s.xch = reinterpret_cast<float2*>(q); q += kXchBytes;
+    s.xch = reinterpret_cast<float2*>(q); q += groups * kXchBytes;
     s.vec = reinterpret_cast<float*>(q); q += kVecBytes;
     s.sched = reinterpret_cast<uint2*>(q); q += kSchedBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(q);
@@ -449,6 +463,7 @@ __device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_b
     s.done = bars + 2 * kMaxSlot;
     s.aux = bars + 2 * kMaxSlot + 1;
     s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlot + 2);
+    s.gdone = bars + 2 * kMaxSlot + 3;
     return s;
 }
 
@@ -459,9 +474,10 @@ __device__ __forceinline__ void tc_prologue(const TcShared& s, uint32_t ncols, R
         for (int i = 0; i < kMaxSlot; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.done, 1);
         mbar_init(s.aux, 1);
+        for (int i = 0; i < kMaxGroups; ++i) mbar_init(&s.gdone[i], 1);
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < 2 * TM; i += NT2)
+    for (int i = threadIdx.x; i < 2 * TM; i += blockDim.x)
         reinterpret_cast<float4*>(s.ones)[i] = i < TM ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     fence_async_smem();
     fence_before_sync();
@@ -489,10 +505,11 @@ __device__ __forceinline__ void tc_finish(uint32_t tm, uint32_t ncols) {
     if (threadIdx.x < 32) tmem_dealloc(tm, ncols);
 }
 // all threads: operand region written -> visible to the tensor core, TMEM reads retired
-__device__ __forceinline__ void sync_for_mma() {
+template <int NG = 1>
+__device__ __forceinline__ void sync_for_mma(int grp = 0) {
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
+    group_sync<NG>(grp);
     fence_after_sync();
 }
 // One thread polls the mbarrier; everybody else parks on the (hardware-blocking) CTA barrier instead of
@@ -504,13 +521,13 @@ __device__ __forceinline__ void wait_done(uint64_t* done, uint32_t& phase) {
     fence_after_sync();
 }
 // same, and the issuing lane refills the (now entirely free) weight ring before joining the barrier
-template <typename G>
-__device__ __forceinline__ void wait_done_ring(uint64_t* done, uint32_t& phase, Ring& r, const TcPlan& p, bool w0) {
+template <typename G, int NG = 1>
+__device__ __forceinline__ void wait_done_ring(uint64_t* done, uint32_t& phase, Ring& r, const TcPlan& p, bool w0, int grp = 0) {
     if (w0 && elect_one()) {
         mbar_wait(done, phase & 1);
         if (!G::resident) ring_top_up<G::nslot>(r, p);
     }
-    __syncthreads();
+    group_sync<NG>(grp);
     ++phase;
     fence_after_sync();
 }
@@ -639,27 +656,40 @@ template <int C> struct BranchCfg {
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
-    static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
+    static constexpr int groups = C <= 32 ? 4 : 1;                 // tile groups per CTA (shared resident weights)
+    static constexpr int min_ctas = C <= 32 ? 1 : C <= 64 ? 2 : 1;
 };
 
 template <int CIN, int C, int BR>
-__global__ void __launch_bounds__(NT2, BranchCfg<C>::min_ctas)
+__global__ void __launch_bounds__(NT2 * BranchCfg<C>::groups, BranchCfg<C>::min_ctas)
 tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = BranchCfg<C>;
     using G = BranchG<CIN, C>;
     constexpr int CH = Cfg::CH;
-    const TcShared s = carve(smem, Cfg::region, plan);
-    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
+    constexpr int NG = Cfg::groups;
+    static_assert(NG == 1 || G::resident, "tile groups share resident weights (no ring state per group)");
+    TcShared s = carve(smem, Cfg::region, plan, NG);
+    const int grp = NG == 1 ? 0 : (int)(threadIdx.x / NT2);               // tile group (warp-uniform)
+    const int tid = threadIdx.x - grp * NT2, row = tid & (TM - 1), half = tid >> 7;
+    const int vblock = (int)blockIdx.x * NG + grp, vgrid = (int)gridDim.x * NG;   // this group as a virtual CTA
     const int ntiles = (geo.total_units + 1) / 2;
-    const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint32_t my_tiles = vblock < ntiles ? (ntiles - 1 - vblock) / vgrid + 1 : 0;
     const DownW::Branch& br = w.br[BR];
-    for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
-    if constexpr (CIN < 8) conv0_stage_weights<CIN, C>(w, s.vec);
+    if (grp == 0) {
+        for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
+        if constexpr (CIN < 8) conv0_stage_weights<CIN, C>(w, s.vec);
+    }
     Ring ring;
-    const bool w0 = warp0_uniform();
-    tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
-    const uint32_t tm = *s.tmem_slot;
+    const bool w0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;           // first warp of the group: issues its MMAs
+    tc_prologue<G::nslot>(s, Cfg::ncols * NG, ring, plan, my_tiles, w0 && grp == 0);
+    if (NG > 1) {
+        if (grp > 0 && w0 && elect_one()) mbar_wait(&s.full[0], 0);       // the resident weights (loaded by group 0) have landed
+        s.region += (size_t)grp * (Cfg::region / 4);
+        s.xch += (size_t)grp * (kXchBytes / 8);
+        if (grp > 0) s.done = &s.gdone[grp];
+    }
+    const uint32_t tm = *s.tmem_slot + (uint32_t)(grp * Cfg::ncols);
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);        // this warp's 32-lane window
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
     const int ug = (row & 31) >> 4, tok = (row >> 5) * 16 + (row & 15);   // unit / token of this lane
@@ -675,12 +705,12 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
         px = unit_pixel<BR>(geo, vld ? un - im * geo.upi : 0, tok);
     };
-    if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
+    if (InputPf<CIN>::enabled && vblock < ntiles) {
         bool vld; int im, px;
-        coords(blockIdx.x, vld, im, px);
+        coords(vblock, vld, im, px);
         fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
     }
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int t = vblock; t < ntiles; t += vgrid, ++it) {
         TC_TRACE(plan, it, 0);
         bool valid; int img, pix;
         coords(t, valid, img, pix);
@@ -689,28 +719,28 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
         if constexpr (CIN < 8) {
             const float4 xv = pf.v[0];
-            if (t + (int)gridDim.x < ntiles) {
+            if (t + vgrid < ntiles) {
                 bool vld; int im, px;
-                coords(t + gridDim.x, vld, im, px);
+                coords(t + vgrid, vld, im, px);
                 fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
             }
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
             if (InputPf<CIN>::enabled) {
                 store_input_row<CIN>(pf, s.region, row, half);
-                if (t + (int)gridDim.x < ntiles) {
+                if (t + vgrid < ntiles) {
                     bool vld; int im, px;
-                    coords(t + gridDim.x, vld, im, px);
+                    coords(t + vgrid, vld, im, px);
                     fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
                 }
             } else {
                 load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
             }
             TC_TRACE(plan, it, 1);
-            sync_for_mma();
+            sync_for_mma<NG>(grp);
             if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
             TC_TRACE(plan, it, 2);
-            wait_done_ring<G>(s.done, phase, ring, plan, w0);
+            wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
             TC_TRACE(plan, it, 3);
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
 #pragma unroll
@@ -729,16 +759,16 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                 upk2(s2, a, b); sum = a + b;
                 upk2(q2, a, b); sq = a + b;
             }
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 4);
-        sync_for_mma();
+        sync_for_mma<NG>(grp);
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
         if (w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 6);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
@@ -749,12 +779,12 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
 #pragma unroll
                 for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 7);
-        sync_for_mma();
+        sync_for_mma<NG>(grp);
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
         if (w0 && elect_one()) {
             issue_linear_t<G, BG_D1A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true);
@@ -762,7 +792,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             commit(s.done);
         }
         TC_TRACE(plan, it, 8);
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
@@ -771,7 +801,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             ld_row<CH>(lane_base + Cfg::col_y + C + col0, v);
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
             float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3) + (size_t)col0 * 4;
             norm_row<CH>(v, rstd, shift);
 #pragma unroll
@@ -784,11 +814,11 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             }
         }
         TC_TRACE(plan, it, 10);
-        sync_for_mma();
+        sync_for_mma<NG>(grp);
         // ---- token mixing, gating y1 * (y2' + 1)
         if (w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
         TC_TRACE(plan, it, 11);
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 12);
         {
             constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
@@ -804,11 +834,11 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             }
         }
         TC_TRACE(plan, it, 13);
-        sync_for_mma();
+        sync_for_mma<NG>(grp);
         // ---- dense2 + residual u -> out
         if (w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         TC_TRACE(plan, it, 14);
-        wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 15);
         {
             constexpr int SC = CH > 64 ? 64 : CH;
@@ -838,7 +868,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         }
         // the next tile's input load overwrites the region: every MMA reading it has completed (wait_done)
     }
-    tc_finish(tm, Cfg::ncols);
+    tc_finish(*s.tmem_slot, Cfg::ncols * NG);
 }
 
 
@@ -1477,13 +1507,14 @@ static int num_sms() {
 // persistent grid: one CTA per resident slot.  Resident CTAs per SM = min over shared memory (227 KB usable,
 // 1 KB reserved per CTA), registers (64 K per SM) and TMEM columns (512 per SM).
 template <typename K>
-static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* grid) {
+static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* grid, int groups = 1) {
     BALF_REQUIRE(smem <= 227 * 1024, "internal: tc kernel needs %zu bytes of shared memory", smem);
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     BALF_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
-    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT2;
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT2 * groups;
+    ntiles = (ntiles + groups - 1) / groups;                // CTAs needed
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (regs_per_cta > 0 && 65536 / regs_per_cta < per_sm) per_sm = 65536 / regs_per_cta;
     if (512 / tmem_cols < per_sm) per_sm = 512 / tmem_cols;
@@ -1503,16 +1534,17 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     BALF_REQUIRE((plan_matches<BranchG<CIN, C>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C>>(P.branch[level][1]) &&
                   plan_matches<MergeG<CIN, C>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
     for (int b = 0; b < 2; ++b) {
+        constexpr int NG = BranchCfg<C>::groups;
         const TcPlan& p = P.branch[level][b];
-        const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p);
+        const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p, NG);
         if (b == 0) {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, BranchCfg<C>::ncols * NG, ntiles, &grid, NG)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
-            tc_branch_kernel<CIN, C, 0><<<grid, NT2, smem, st>>>(xin, w, p, g, u);
+            tc_branch_kernel<CIN, C, 0><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, u);
         } else {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, BranchCfg<C>::ncols, ntiles, &grid)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, BranchCfg<C>::ncols * NG, ntiles, &grid, NG)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
-            tc_branch_kernel<CIN, C, 1><<<grid, NT2, smem, st>>>(xin, w, p, g, v);
+            tc_branch_kernel<CIN, C, 1><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, v);
         }
     }
     if constexpr (C <= 64) {
