@@ -362,3 +362,80 @@ def match_smnn(d1, d2, th=0.99, want_dm=False):
     m = int(cnt[0])
     out = (dist[:m].reshape(m, 1), ids[:m].long())
     return out + (dm,) if want_dm else out
+
+
+# ------------------------------------------------------------------------------------------ front end / multi-scale
+_rgb2gray = _sig("balf_rgb_to_gray_u8", c_int, _P, c_int, c_int, c_int, _P, _P)
+_preprocess_f32 = _sig("balf_preprocess_f32", c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P)
+_resize_pre = _sig("balf_resize_preprocess_u8", c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int,
+                   c_int, _P)
+_merge_levels = _sig("balf_merge_levels_topk", c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P)
+MAX_LEVELS = 8
+
+
+def rgb_to_gray(rgb):
+    """rgb [B,H,W,3] (or [H,W,3]) uint8 CUDA -> gray uint8, PIL 'L' arithmetic."""
+    _need_cuda(rgb, "the image")
+    single = rgb.dim() == 3
+    t = (rgb[None] if single else rgb).contiguous()
+    B, H, W, C = t.shape
+    if C != 3 or t.dtype != torch.uint8:
+        raise ValueError("rgb_to_gray expects uint8 [.., H, W, 3]")
+    gray = torch.empty(B, H, W, dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        _ok(_rgb2gray(_ptr(t), B, H, W, _ptr(gray), _stream(t.device)))
+    return gray[0] if single else gray
+
+
+def preprocess_f32(img, factor=64):
+    """img [B,H,W,C] float32 CUDA (already normalised) -> (x [B,3,Hp,Wp] fp32, (top, left))."""
+    _need_cuda(img, "the image batch")
+    img = img.contiguous().float()
+    B, H, W, C = img.shape
+    Hp, Wp, top, left = pad_geometry(H, W, factor)
+    x = torch.empty(B, 3, Hp, Wp, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _ok(_preprocess_f32(_ptr(img), B, H, W, C, _ptr(x), Hp, Wp, top, left, _stream(img.device)))
+    return x, (top, left)
+
+
+def level_size(n, scale, level):
+    """pyramid level extent: round-half-up of n * scale**level, at least 32 pixels."""
+    return max(int(n * (scale ** level) + 0.5), 32)
+
+
+def resize_preprocess_u8(img, hs, ws, factor=64):
+    """img [B,H,W,C] uint8 CUDA -> bilinear level hs x ws, /255, padded CHW: (x [B,3,Hp,Wp], (top, left))."""
+    _need_cuda(img, "the image batch")
+    img = img.contiguous()
+    B, H, W, C = img.shape
+    Hp, Wp, top, left = pad_geometry(hs, ws, factor)
+    x = torch.empty(B, 3, Hp, Wp, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _ok(_resize_pre(_ptr(img), B, H, W, C, int(hs), int(ws), _ptr(x), Hp, Wp, top, left, _stream(img.device)))
+    return x, (top, left)
+
+
+def merge_levels_topk(lists, scales, k_out):
+    """lists = [(xy int32 [B,K,2], score fp32 [B,K], count int32 [B]) per level] (CUDA), scales = [(sx, sy)] level-0
+    pixels per level pixel -> (xy fp32 [B,k_out,2] in the level-0 frame, score [B,k_out], level int32 [B,k_out],
+    count int32 [B]), ordered by (score descending, level ascending, rank inside the level)."""
+    n = len(lists)
+    if not 1 <= n <= MAX_LEVELS:
+        raise ValueError("1 .. %d levels" % MAX_LEVELS)
+    xy0, sc0, cn0 = lists[0]
+    _need_cuda(xy0, "the keypoint lists")
+    dev = xy0.device
+    B, K = sc0.shape
+    keep = [(xy.contiguous(), sc.contiguous(), cn.contiguous()) for xy, sc, cn in lists]
+    arr = lambda items: (ctypes.c_void_p * n)(*[t.data_ptr() for t in items])
+    fl = lambda items: (c_float * n)(*[float(v) for v in items])
+    xy_out = torch.empty(B, k_out, 2, dtype=torch.float32, device=dev)
+    sc_out = torch.empty(B, k_out, dtype=torch.float32, device=dev)
+    lv_out = torch.empty(B, k_out, dtype=torch.int32, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _ok(_merge_levels(n, arr([t[0] for t in keep]), arr([t[1] for t in keep]), arr([t[2] for t in keep]),
+                          fl([s[0] for s in scales]), fl([s[1] for s in scales]), B, K, int(k_out), _ptr(xy_out),
+                          _ptr(sc_out), _ptr(lv_out), _ptr(cnt), _stream(dev)))
+    return xy_out, sc_out, lv_out, cnt

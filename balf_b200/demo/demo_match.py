@@ -50,6 +50,35 @@ def detect_batch_device(args, u8, detector, nms="greedy"):
         radius=args.nms_size, subpixel_ps=args.patch_size if args.sub_pixel else 0, crop=(top, left, h, w))
 
 
+def detect_multiscale_batch_device(args, u8, detector, scale=0.7, levels=3, nms="windowed"):
+    """Multi-scale pyramid extraction (the mode the reference advertises in balf/configs/config_hpatches.py:50-82 but
+    does not implement; semantics defined in include/balf_b200.h and restated in oracle/multiscale.py).
+    u8 [B,H,W,C] uint8 CUDA.  Level l is the bilinear resize of the image to round(H s^l) x round(W s^l); every level
+    runs the detector and the per-level extraction with capacity args.num_features, and the lists are merged by score
+    into the best args.num_features keypoints in level-0 coordinates.
+    -> (xy fp32 [B,K,2], score fp32 [B,K], level int32 [B,K], count int32 [B]) on the device."""
+    B, h, w, _ = u8.shape
+    lists, scales = [], []
+    for l in range(levels):
+        hs, ws = _capi.level_size(h, scale, l), _capi.level_size(w, scale, l)
+        if l == 0:
+            x, (top, left) = _capi.preprocess_u8(u8)
+        else:
+            x, (top, left) = _capi.resize_preprocess_u8(u8, hs, ws)
+        with torch.inference_mode():
+            prob = detector(x)["prob"]
+        if nms == "windowed":
+            xy, sc, cnt = _capi.windowed_nms_topk(prob, args.num_features, border=args.border_size,
+                                                  nms_size=args.nms_size, crop=(top, left, hs, ws))
+        else:
+            xy, sc, _, cnt = _capi.greedy_nms_topk(prob, args.num_features, border=args.border_size,
+                                                   thr=args.heatmap_confidence_threshold, radius=args.nms_size,
+                                                   subpixel_ps=0, crop=(top, left, hs, ws))
+        lists.append((xy, sc, cnt))
+        scales.append((w / ws, h / hs))
+    return _capi.merge_levels_topk(lists, scales, args.num_features)
+
+
 def detect_batch(args, images, detector, device, nms="greedy"):
     """Batched ``detect`` with HOST buffers in and out: images [B,H,W,C] uint8 (NumPy array or
     torch CPU tensor, pinned for an asynchronous copy) -> (xy int32 [B,K,2], score fp32 [B,K],

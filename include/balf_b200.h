@@ -179,6 +179,34 @@ BALF_API int balf_match_smnn(const float* d1, int n1, const float* d2, int n2, i
                              float* dist, int32_t* count, float* dm_out, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * front end and multi-scale extraction (the rows next to the hot path)
+ * balf_rgb_to_gray_u8       replaces demo/demo_match.py:13-19 (PIL Image.convert('L')): rgb [B,H,W,3] uint8 ->
+ *                           gray [B,H,W] uint8 = (19595 R + 38470 G + 7471 B + 32768) >> 16.
+ * balf_preprocess_f32       replaces balf/utils/train_utils.py:417-430 (extract_detections: make_shape_even,
+ *                           mod_padding_symmetric, HWC->CHW of an already normalised float image [B,H,W,C]).
+ * balf_resize_preprocess_u8 one pyramid level of the multi-scale extraction advertised by
+ *                           balf/configs/config_hpatches.py:50-82 (the reference ships only the argument parser:
+ *                           the semantics are defined here and restated in oracle/multiscale.py, PARITY UNPINNED):
+ *                           bilinear resize of the uint8 image to Hs x Ws with half-pixel centres, no antialiasing,
+ *                           then /255, zero pad and HWC->CHW exactly as balf_preprocess_u8.
+ * balf_merge_levels_topk    per-level keypoint lists (outputs of balf_windowed_nms_topk / balf_greedy_nms_topk at each
+ *                           level, capacity K) -> the k_out best over all levels, ordered by (score descending, level
+ *                           ascending, rank inside the level); coordinates mapped back to the level-0 frame:
+ *                           x0 = (x + 0.5) * scale_x[level] - 0.5.  xy_out fp32 [B,k_out,2], score_out fp32 [B,k_out],
+ *                           level_out int32 [B,k_out], count_out int32 [B].  xy / score / count are HOST arrays of
+ *                           n_levels device pointers. */
+#define BALF_MAX_LEVELS 8
+BALF_API int balf_rgb_to_gray_u8(const uint8_t* rgb, int B, int H, int W, uint8_t* gray, void* stream);
+BALF_API int balf_preprocess_f32(const float* img, int B, int H, int W, int C, float* x, int Hp, int Wp, int top, int left,
+                                 void* stream);
+BALF_API int balf_resize_preprocess_u8(const uint8_t* img, int B, int H, int W, int C, int Hs, int Ws, float* x, int Hp,
+                                       int Wp, int top, int left, void* stream);
+BALF_API int balf_merge_levels_topk(int n_levels, const int32_t* const* xy, const float* const* score,
+                                    const int32_t* const* count, const float* scale_x, const float* scale_y, int B, int K,
+                                    int k_out, float* xy_out, float* score_out, int32_t* level_out, int32_t* count_out,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
