@@ -111,8 +111,10 @@ _workspaces = {}
 
 
 def _workspace(device, nbytes):
-    """grow-only scratch buffer per device (the C-ABI never allocates)."""
-    key = str(device)
+    """grow-only scratch buffer per (device, stream) -- the C-ABI never allocates.  Keyed by the current stream because
+    the kernels of one call use the buffer in stream order: two streams sharing it would race (DetectPipeline runs
+    beside default-stream callers)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)

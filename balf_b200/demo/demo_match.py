@@ -90,6 +90,43 @@ def detect_batch(args, images, detector, device, nms="greedy"):
     return xy.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
 
 
+class DetectPipeline:
+    """Streaming form of ``detect_batch`` for throughput serving: ``submit`` takes a HOST batch (pinned uint8
+    [B,H,W,C]) and returns a ticket, ``result`` returns that batch's (xy, score, count) NumPy arrays.  The host->device
+    copy of a batch runs on a copy stream while the kernels of the previous batch run on the compute stream, and the
+    keypoint records come back through pinned staging buffers -- every batch still crosses PCIe both ways, the copies
+    just no longer sit between the kernels of consecutive batches."""
+
+    def __init__(self, args, detector, device, nms="greedy"):
+        self.args, self.detector, self.nms = args, detector, nms
+        self.dev = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.compute_stream = torch.cuda.Stream(self.dev)
+
+    def submit(self, images):
+        t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        with torch.cuda.stream(self.copy_stream):
+            u8 = t.to(self.dev, non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(self.copy_stream)
+        u8.record_stream(self.compute_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(arrived)
+            xy, sc, _, cnt = detect_batch_device(self.args, u8, self.detector, self.nms)
+            host = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in (xy, sc, cnt)]
+            for h, o in zip(host, (xy, sc, cnt)):
+                h.copy_(o, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.compute_stream)
+        return host, done, (xy, sc, cnt)              # device tensors kept alive until the copies have run
+
+    @staticmethod
+    def result(ticket):
+        host, done, _ = ticket
+        done.synchronize()
+        return tuple(h.numpy() for h in host)
+
+
 def detect(args, im, detector, device):
     """-> [K,3] float64 rows (x, y, 1.0), score-descending, K <= args.num_features."""
     xy, dxdy, _, n = _detect_device(args, im, detector, device)

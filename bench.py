@@ -9,7 +9,7 @@ uint8 images -> /255 + pad (D0) -> detector forward (D1-D3) -> border mask + NMS
 Workload = BASELINE.json configs[1]: batch 64 synthetic grayscale 640x480 per GPU.
 
 Prints ONE JSON line (rank 0).  ``value`` = whole-job images/s with the uint8 batch already in
-HBM; ``e2e`` = the same metric through the public host-buffer API (``demo_match.detect_batch``:
+HBM; ``e2e`` = the same metric through the public host-buffer API (``demo_match.DetectPipeline``, the streaming ``detect_batch``:
 pinned host uint8 in, keypoint records back on the host, copies inside the timed region).
 ``--impl reference`` times the reference's CPU algorithm (the oracle restatement; the reference
 itself cannot travel to the GPU box) on the box's host cores.
@@ -354,16 +354,21 @@ def main():
     capi.profile_enable(False)
     clocks = sampler.stop() if sampler else None
 
-    # end to end through the host-buffer API
-    def step_host():
-        xy, sc, cnt = demo_match.detect_batch(args, host, det, dev, a.nms)
-        return xy, sc, cnt
+    # end to end through the host-buffer API: every step's uint8 batch goes pinned host -> device and its keypoint
+    # records come back device -> host inside the timed region.  DetectPipeline is the streaming form of
+    # demo_match.detect_batch: the copy of step i+1 overlaps the kernels of step i.
+    pipe = demo_match.DetectPipeline(args, det, dev, a.nms)
     for _ in range(2):
-        res = step_host()
+        res = pipe.result(pipe.submit(host))
     barrier()
     t0 = time.perf_counter()
+    prev = None
     for _ in range(a.steps):
-        res = step_host()
+        cur = pipe.submit(host)
+        if prev is not None:
+            res = pipe.result(prev)
+        prev = cur
+    res = pipe.result(prev)
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) * 1e3
     d2h = sum(int(r.nbytes) for r in res)

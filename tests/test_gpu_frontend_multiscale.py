@@ -143,3 +143,20 @@ def test_multiscale_detect_end_to_end(detector, detector_sd):
     got = set(zip(lv[0, :n].cpu().numpy().tolist(), map(tuple, xy[0, :n].cpu().numpy().tolist())))
     want = set(zip(olv.tolist(), map(tuple, oxy.tolist())))
     assert len(got & want) >= 0.99 * len(want), (len(got & want), len(want))
+
+
+def test_detect_pipeline_equals_detect_batch(detector):
+    """the streaming host-buffer API returns exactly what detect_batch returns, in submission order"""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    det = copy.deepcopy(detector).to(DEV).eval()
+    args = config.default_test_args(sub_pixel=False, num_features=256)
+    batches = [torch.from_numpy(np.stack([synth_u8(96, 128, 20 + 3 * i + j)[:, :, :1] for j in range(3)])).pin_memory() for i in range(4)]
+    for nms in ("windowed", "greedy"):
+        pipe = demo_match.DetectPipeline(args, det, DEV, nms)
+        tickets = [pipe.submit(b) for b in batches]
+        for b, t in zip(batches, tickets):
+            got = pipe.result(t)
+            want = demo_match.detect_batch(args, b, det, DEV, nms)
+            for g, w in zip(got, want):
+                np.testing.assert_array_equal(g, w)
