@@ -54,11 +54,21 @@ def launches(tag):
     print("wrote", tag + "_launches.md")
 
 
-def full(tag, report="prof.ncu-rep", suffix="_ncu_full.md", what="the dominant detector kernels"):
+def raw_page(report):
+    """raw page of a report: the CSV exported on the GPU box (gpu_check.sh) or, if the report itself is here, ncu -i"""
     rep = os.path.join(OUT, report)
-    if not os.path.exists(rep):
+    pre = rep.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(pre):
+        return open(pre).read()
+    if os.path.exists(rep):
+        return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return None
+
+
+def full(tag, report="prof.ncu-rep", suffix="_ncu_full.md", what="the dominant detector kernels"):
+    raw = raw_page(report)
+    if raw is None:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         print("no rows in report")
@@ -82,10 +92,9 @@ def traffic():
     import re
     out = {}
     for report in ("prof.ncu-rep", "prof_nms.ncu-rep"):
-        rep = os.path.join(OUT, report)
-        if not os.path.exists(rep):
+        raw = raw_page(report)
+        if raw is None:
             continue
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             continue
@@ -98,9 +107,14 @@ def traffic():
             m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
             if m:
                 name = "det_branch_%s_c%s" % ("grid" if m.group(3) == "0" else "block", m.group(2))
-            m = re.search(r"tc_merge_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
+            m = re.search(r"tc_merge(?:_bulk)?_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
             if m:
                 name = "det_merge_c%s" % m.group(2)
+            m = re.search(r"pool_kernel<\(?(?:int\))?(\d+)>", kn)
+            if m:
+                name = "det_pool_c%s" % m.group(1)
+            if "tc_head_kernel" in kn:
+                name = "det_head"
             if "nms15_kernel" in kn:
                 name = "nms_windowed"
             if "select_sort_kernel" in kn:
