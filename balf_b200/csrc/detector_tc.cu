@@ -556,6 +556,35 @@ __device__ __forceinline__ int unit_pixel(const UnitGeom& g, int u, int tok) {
     return u * 64 + tok;
 }
 
+// ---- full-sector global accesses.  A lane owns one pixel row and moves it in 16-byte chunks, so "chunk j of 32 rows"
+// is a warp instruction over 32 half-used 32-byte sectors, which the LSU serialises.  Lanes 2i / 2i+1 instead access the
+// two halves of ONE sector of row 2i, then of row 2i+1, and swap every other chunk by shuffle: 16 full sectors per
+// instruction.  (Both lanes of a pair always belong to the same unit, so `valid` is pair-uniform.)
+__device__ __forceinline__ float4 shfl_xor1(float4 v) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1),
+                       __shfl_xor_sync(0xffffffffu, v.z, 1), __shfl_xor_sync(0xffffffffu, v.w, 1));
+}
+// raw pair-layout load of N chunks: v[2k] = row 2i chunk 2k + odd, v[2k+1] = row 2i+1 chunk 2k + odd
+template <int N>
+__device__ __forceinline__ void pair_load(const float4* own, bool valid, float4 (&v)[N]) {
+    static_assert(N % 2 == 0, "pairs of chunks");
+    const bool odd = (threadIdx.x & 1) != 0;
+    const float4* oth = reinterpret_cast<const float4*>(__shfl_xor_sync(0xffffffffu, (unsigned long long)own, 1));
+    const float4* a = (odd ? oth : own) + (odd ? 1 : 0);
+    const float4* b = (odd ? own : oth) + (odd ? 1 : 0);
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        v[k] = valid ? __ldg(a + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k + 1] = valid ? __ldg(b + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// pair layout -> this lane's own chunks k, k+1 (call with the same k on every lane)
+__device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
+    const bool odd = (threadIdx.x & 1) != 0;
+    const float4 recv = shfl_xor1(odd ? c0 : c1);
+    if (odd) c0 = recv; else c1 = recv;
+}
+
 // this thread's half of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
 template <int CIN>
 __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
@@ -571,10 +600,18 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
         *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = o;
     } else {
         const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
-#pragma unroll 4
-        for (int j = 0; j < CIN / 8; ++j)
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) =
-                valid ? to_tf32(__ldg(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int N = CIN / 8, NB = N > 8 ? 8 : N;          // batches of 8 chunks bound the registers in flight
+#pragma unroll 1
+        for (int j0 = 0; j0 < N; j0 += NB) {
+            float4 v[NB];
+            pair_load<NB>(src + j0, valid, v);
+#pragma unroll
+            for (int j = 0; j < NB; j += 2) {
+                pair_unswap(v[j], v[j + 1]);
+                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j) * TM + row) * 4) = to_tf32(v[j]);
+                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j + 1) * TM + row) * 4) = to_tf32(v[j + 1]);
+            }
+        }
     }
 }
 
@@ -586,7 +623,7 @@ template <int CIN> struct InputPf {
     static constexpr int N = CIN < 8 ? 1 : CIN / 8;
     float4 v[N];
 };
-template <int CIN>
+template <int CIN, bool PAIR = true>
 __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid, int half,
                                                 InputPf<CIN>& pf) {
     if constexpr (CIN < 8) {                       // conv.0 runs on the CUDA cores: both halves of the row need the pixel
@@ -598,18 +635,26 @@ __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, s
         pf.v[0] = make_float4(v[0], v[1], v[2], v[3]);
     } else {
         const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
+        if constexpr (PAIR) {
+            pair_load<CIN / 8>(src, valid, pf.v);           // pair layout; un-swapped when stored (store_input_row)
+        } else {
 #pragma unroll
-        for (int j = 0; j < CIN / 8; ++j) pf.v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < CIN / 8; ++j) pf.v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
-template <int CIN>
+template <int CIN, bool PAIR = true>
 __device__ __forceinline__ void store_input_row(const InputPf<CIN>& pf, float* dst, int row, int half) {
     if constexpr (CIN < 8) {
         *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
     } else {
 #pragma unroll
-        for (int j = 0; j < CIN / 8; ++j)
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) = to_tf32(pf.v[j]);
+        for (int j = 0; j < CIN / 8; j += 2) {
+            float4 c0 = pf.v[j], c1 = pf.v[j + 1];
+            if constexpr (PAIR) pair_unswap(c0, c1);
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) = to_tf32(c0);
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j + 1) * TM + row) * 4) = to_tf32(c1);
+        }
     }
 }
 
@@ -842,26 +887,50 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         TC_TRACE(plan, it, 15);
         {
             constexpr int SC = CH > 64 ? 64 : CH;
+            // Full-sector stores: a lane's row chunks are 16 bytes, so a warp store of "chunk j of 32 rows" touches 32
+            // half-used sectors and the LSU serialises them (removing these stores bought 0.3-0.6 ms per kernel per 64
+            // images).  Lanes 2i / 2i+1 therefore swap every other chunk: both lanes write the two halves of one 32-byte
+            // sector of row 2i, then of row 2i+1 -- 16 full sectors per instruction.
+            const bool odd = (threadIdx.x & 1) != 0;
+            const size_t own_base = Cfg::swz_out ? ((size_t)img * npix + (pix & ~(TM - 1))) * C : ((size_t)img * npix + pix) * C;
+            const int own_sw = pix & (TM - 1);
+            const size_t oth_base = __shfl_xor_sync(0xffffffffu, (unsigned long long)own_base, 1);
+            const int oth_sw = __shfl_xor_sync(0xffffffffu, own_sw, 1);
+            const size_t base_a = odd ? oth_base : own_base, base_b = odd ? own_base : oth_base;   // rows 2i, 2i+1
+            const int sw_a = odd ? oth_sw : own_sw, sw_b = odd ? own_sw : oth_sw;
 #pragma unroll 1
             for (int c = 0; c < CH; c += SC) {
                 float a[SC], r[SC];
                 ld_row<SC>(lane_base + Cfg::col_y + col0 + c, a);
                 if (Cfg::park_u) ld_row<SC>(lane_base + Cfg::col_u + col0 + c, r);
-                if (valid) {
+                float4 o[SC / 4];
 #pragma unroll
-                    for (int j = 0; j < SC / 4; ++j) {
-                        float4 res;
-                        if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                        else res = *reinterpret_cast<const float4*>(orow + c + 4 * j);
-                        float4 o = make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
-                        // u' / v' feed nothing but the merge GEMM: rounding them here (RN, as every operand) lets the merge
-                        // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
-                        // the C >= 128 merge kernels round again when they load, which must be a no-op
-                        if (BR == 1 || Cfg::swz_out) o = to_tf32_clean(o);
-                        if (Cfg::swz_out)    // tile of 128 consecutive pixels, swizzled panel layout (sw_off); 128 | pixels per image
-                            *reinterpret_cast<float4*>(out + ((size_t)img * npix + (pix & ~(TM - 1))) * C + sw_off(pix & (TM - 1), (col0 + c) / 4 + j)) = o;
-                        else
-                            *reinterpret_cast<float4*>(orow + c + 4 * j) = o;
+                for (int j = 0; j < SC / 4; ++j) {
+                    float4 res;
+                    if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    else res = valid ? *reinterpret_cast<const float4*>(orow + c + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o[j] = make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
+                    // u' / v' feed nothing but the merge GEMM: rounding them here (RN, as every operand) lets the merge
+                    // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
+                    // the C >= 128 merge kernels round again when they load, which must be a no-op
+                    if (BR == 1 || Cfg::swz_out) o[j] = to_tf32_clean(o[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < SC / 4; j += 2) {
+                    const float4 send = odd ? o[j] : o[j + 1];
+                    float4 recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+                    const float4 to_a = odd ? recv : o[j], to_b = odd ? o[j + 1] : recv;     // (row 2i, row 2i+1), chunk j + odd
+                    const int chunk = (col0 + c) / 4 + j + (odd ? 1 : 0);
+                    if (valid) {        // both lanes of a pair belong to the same unit
+                        if (Cfg::swz_out) {
+                            *reinterpret_cast<float4*>(out + base_a + sw_off(sw_a, chunk)) = to_a;
+                            *reinterpret_cast<float4*>(out + base_b + sw_off(sw_b, chunk)) = to_b;
+                        } else {
+                            *reinterpret_cast<float4*>(out + base_a + 4 * chunk) = to_a;
+                            *reinterpret_cast<float4*>(out + base_b + 4 * chunk) = to_b;
+                        }
                     }
                 }
             }
@@ -1128,7 +1197,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     if ((int)blockIdx.x < ntiles) {
         int im, px;
         coords(blockIdx.x, im, px);
-        fetch_input_row<CIN>(xin, npix, (size_t)im, px, true, half, pfx);
+        fetch_input_row<CIN, false>(xin, npix, (size_t)im, px, true, half, pfx);
         if (w0 && elect_one()) load_tile(blockIdx.x);
     }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -1136,7 +1205,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         float v[CH], x0[CH];
         // ---- phase 1: acc = dense2([u', v']) (+ conv.0(x) at CIN >= 8) on the tensor core | x0 on the CUDA cores at CIN < 8
         if constexpr (!Cfg::cc0) {
-            store_input_row<CIN>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
+            store_input_row<CIN, false>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
             sync_for_mma();
         }
         if (w0 && elect_one()) {
@@ -1153,7 +1222,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         if (nt < ntiles) {
             int im, px;
             coords(nt, im, px);
-            fetch_input_row<CIN>(xin, npix, (size_t)im, px, true, half, pfx);
+            fetch_input_row<CIN, false>(xin, npix, (size_t)im, px, true, half, pfx);
         }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         // x1 = acc + x0; q = x1 + x0 -> Q (staging); LayerNorm(x1) (affine folded into conv1) -> W
