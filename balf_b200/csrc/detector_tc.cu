@@ -578,6 +578,24 @@ __device__ __forceinline__ void pair_load(const float4* own, bool valid, float4 
         v[k + 1] = valid ? __ldg(b + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
+// store this lane's N consecutive chunks, taken from v[4 * j ..], at out + own_off (floats) with full sectors
+template <int N>
+__device__ __forceinline__ void pair_store(float* __restrict__ out, size_t own_off, const float* v, bool valid) {
+    static_assert(N % 2 == 0, "pairs of chunks");
+    const bool odd = (threadIdx.x & 1) != 0;
+    const size_t oth_off = __shfl_xor_sync(0xffffffffu, (unsigned long long)own_off, 1);
+    const size_t off_a = (odd ? oth_off : own_off) + (odd ? 4 : 0), off_b = (odd ? own_off : oth_off) + (odd ? 4 : 0);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        const float4 c0 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        const float4 c1 = make_float4(v[4 * j + 4], v[4 * j + 5], v[4 * j + 6], v[4 * j + 7]);
+        const float4 recv = shfl_xor1(odd ? c0 : c1);
+        if (valid) {
+            *reinterpret_cast<float4*>(out + off_a + 4 * j) = odd ? recv : c0;      // row 2i,     chunk j + odd
+            *reinterpret_cast<float4*>(out + off_b + 4 * j) = odd ? c1 : recv;      // row 2i + 1, chunk j + odd
+        }
+    }
+}
 // pair layout -> this lane's own chunks k, k+1 (call with the same k on every lane)
 __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
     const bool odd = (threadIdx.x & 1) != 0;
@@ -820,10 +838,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
             if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
-            else if (valid) {
-#pragma unroll
-                for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(orow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
+            else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
             row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
@@ -904,11 +919,20 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
                 ld_row<SC>(lane_base + Cfg::col_y + col0 + c, a);
                 if (Cfg::park_u) ld_row<SC>(lane_base + Cfg::col_u + col0 + c, r);
                 float4 o[SC / 4];
+                if constexpr (!Cfg::park_u) {                // the residual u comes back from `out` (full-sector pair loads)
+                    float4* rq = reinterpret_cast<float4*>(r);
+#pragma unroll
+                    for (int j0 = 0; j0 < SC / 4; j0 += 8) {
+                        float4 t8[8];
+                        pair_load<8>(reinterpret_cast<const float4*>(orow + c) + j0, valid, t8);
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) { pair_unswap(t8[j], t8[j + 1]); rq[j0 + j] = t8[j]; rq[j0 + j + 1] = t8[j + 1]; }
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < SC / 4; ++j) {
                     float4 res;
-                    if (Cfg::park_u) res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                    else res = valid ? *reinterpret_cast<const float4*>(orow + c + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    res = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                     o[j] = make_float4(a[4 * j] + res.x, a[4 * j + 1] + res.y, a[4 * j + 2] + res.z, a[4 * j + 3] + res.w);
                     // u' / v' feed nothing but the merge GEMM: rounding them here (RN, as every operand) lets the merge
                     // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
@@ -1084,11 +1108,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                     upk2(x1, v[c + i], v[c + i + 1]);
                     upk2(add2(x1, xz), x0[i], x0[i + 1]);
                 }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < SC / 4; ++j)
-                        *reinterpret_cast<float4*>(qout + row_off + c + 4 * j) = make_float4(x0[4 * j], x0[4 * j + 1], x0[4 * j + 2], x0[4 * j + 3]);
-                }
+                pair_store<SC / 4>(qout, row_off + c, x0, valid);
             }
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
@@ -1122,8 +1142,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         for (int j = 0; j < CH / 4; ++j) {
             const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
-            if (valid) *reinterpret_cast<float4*>(rout + row_off + 4 * j) = o;
         }
+        pair_store<CH / 4>(rout, row_off, v, valid);
         __syncthreads();
         unit_channel_sums<C>(s.region, t, geo.total_units, partial);
         __syncthreads();
