@@ -1359,16 +1359,19 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
         const int img = valid ? fast_div(unit, geo.upi, geo.inv_upi) : 0, u = valid ? unit - img * geo.upi : 0;
         const int pix = u * 64 + tok;
         const size_t row_off = ((size_t)img * npix + pix) * C + col0;
-#pragma unroll 4
-        for (int j = 0; j < CH / 4; ++j) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(r + row_off) + j);
-                const float4 qv = __ldg(reinterpret_cast<const float4*>(q + row_off) + j);
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + col0) + j);
-                o = make_float4(rv.x * sv.x + qv.x, rv.y * sv.y + qv.y, rv.z * sv.z + qv.z, rv.w * sv.w + qv.w);
+#pragma unroll 1
+        for (int j0 = 0; j0 < CH / 4; j0 += 8) {            // full-sector pair loads of r and q, 8 chunks at a time
+            float4 rv[8], qv[8];
+            pair_load<8>(reinterpret_cast<const float4*>(r + row_off) + j0, valid, rv);
+            pair_load<8>(reinterpret_cast<const float4*>(q + row_off) + j0, valid, qv);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { pair_unswap(rv[j], rv[j + 1]); pair_unswap(qv[j], qv[j + 1]); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + col0) + j0 + j);
+                const float4 o = make_float4(rv[j].x * sv.x + qv[j].x, rv[j].y * sv.y + qv[j].y, rv[j].z * sv.z + qv[j].z, rv[j].w * sv.w + qv[j].w);
+                *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j0 + j) * TM + row) * 4) = to_tf32(o);
             }
-            *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = to_tf32(o);
         }
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
