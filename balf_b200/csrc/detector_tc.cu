@@ -745,7 +745,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     }
     Ring ring;
     const bool w0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;           // first warp of the group: issues its MMAs
-    tc_prologue<G::nslot>(s, Cfg::ncols * NG, ring, plan, my_tiles, w0 && grp == 0);
+    tc_prologue<G::nslot>(s, tc_cols(Cfg::ncols * NG), ring, plan, my_tiles, w0 && grp == 0);
     if (NG > 1) {
         if (grp > 0 && w0 && elect_one()) mbar_wait(&s.full[0], 0);       // the resident weights (loaded by group 0) have landed
         s.region += (size_t)grp * (Cfg::region / 4);
@@ -961,7 +961,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         }
         // the next tile's input load overwrites the region: every MMA reading it has completed (wait_done)
     }
-    tc_finish(*s.tmem_slot, Cfg::ncols * NG);
+    tc_finish(*s.tmem_slot, tc_cols(Cfg::ncols * NG));
 }
 
 
@@ -1630,11 +1630,11 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
         const TcPlan& p = P.branch[level][b];
         const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p, NG);
         if (b == 0) {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, BranchCfg<C>::ncols * NG, ntiles, &grid, NG)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, tc_cols(BranchCfg<C>::ncols * NG), ntiles, &grid, NG)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
             tc_branch_kernel<CIN, C, 0><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, u);
         } else {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, BranchCfg<C>::ncols * NG, ntiles, &grid, NG)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, tc_cols(BranchCfg<C>::ncols * NG), ntiles, &grid, NG)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
             tc_branch_kernel<CIN, C, 1><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, v);
         }
