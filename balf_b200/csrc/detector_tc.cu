@@ -156,7 +156,7 @@ __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
 // (the serial issue path sits on the critical path of every phase of every tile).  Must mirror tc_build_plans.
 template <int CIN, int C> struct BranchG {
     static constexpr int count = BG_COUNT;
-    static constexpr bool resident = C <= 32;
+    static constexpr bool resident = C <= 64;       // C = 64: 100 KB of weights shared by the two tile groups of a CTA
     static constexpr int cap = 32768;
     static constexpr int nslot = C == 64 ? 3 : C == 128 ? 4 : 2;
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
@@ -719,8 +719,8 @@ template <int C> struct BranchCfg {
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
-    static constexpr int groups = C <= 32 ? 4 : 1;                 // tile groups per CTA (shared resident weights)
-    static constexpr int min_ctas = C <= 32 ? 1 : C <= 64 ? 2 : 1;
+    static constexpr int groups = C <= 32 ? 4 : C <= 64 ? 2 : 1;   // tile groups per CTA (shared resident weights)
+    static constexpr int min_ctas = 1;
 };
 
 template <int CIN, int C, int BR>
@@ -1499,7 +1499,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         for (int b = 0; b < 2; ++b) {
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
-            p.base = base; p.ngemm = BG_COUNT; p.resident = resident;
+            p.base = base; p.ngemm = BG_COUNT; p.resident = c <= 64;       // mirrors BranchG::resident
             p.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                  // mirrors BranchG::nslot (checked by plan_matches)
             tc_add(p, BG_CONV0, off, c, cin, true);
             tc_add(p, BG_PD1, off, c, c, true);
