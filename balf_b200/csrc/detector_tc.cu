@@ -167,7 +167,7 @@ template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
     static constexpr bool resident = C <= 32;
     static constexpr int cap = 32768;
-    static constexpr int nslot = C == 64 ? 3 : C == 128 ? 4 : 2;
+    static constexpr int nslot = C == 64 ? 3 : 2;           // C = 128: two operand regions leave room for two slots
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
@@ -715,7 +715,7 @@ template <int C> struct BranchCfg {
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
-    static constexpr bool swz_out = C <= 64;                       // u' / v' leave in the swizzled panel layout (tc_merge_bulk_kernel)
+    static constexpr bool swz_out = C <= 128;                      // u' / v' leave in the swizzled panel layout (bulk-copied by the merge kernels)
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = tc_cols(col_y + 2 * C);
@@ -996,7 +996,10 @@ __device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int t
 // ------------------------------------------------------------------------------------------ merge kernel
 template <int C> struct MergeCfg {
     static constexpr int CH = C / 2;
-    static constexpr uint32_t region = (uint32_t)TM * C * 4;
+    // C = 128: u' and v' (swizzled panel tiles, tf32-rounded by the branch kernels) arrive by bulk copy -- u' into a second
+    // region a tile ahead, v' into the first as soon as conv.0 has released it -- and conv.0 shares its phase with dense2(u')
+    static constexpr bool bulk_uv = C == 128;
+    static constexpr uint32_t region = (uint32_t)TM * C * 4 * (bulk_uv ? 2 : 1);
     static constexpr int col_x0 = 0, col_acc = C;
     static constexpr int ncols = tc_cols(2 * C);
     static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
@@ -1021,6 +1024,12 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
+    const uint32_t r2_addr = region_addr + (uint32_t)TM * C * 4;            // bulk_uv: u' tiles land here
+    uint64_t* const ld_u = s.aux;
+    uint64_t* const ld_v = &s.gdone[1];
+    constexpr uint32_t kTileBytes = (uint32_t)TM * C * 4;
+    const size_t tile_floats = (size_t)TM * C;
+    uint32_t ld_phase = 0;
     const int ug = row >> 6, tok = row & 63;
     const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
@@ -1038,6 +1047,10 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         bool vld; int im, px;
         coords(blockIdx.x, vld, im, px);
         fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+    }
+    if (Cfg::bulk_uv && (int)blockIdx.x < ntiles && w0 && elect_one()) {
+        mbar_expect_tx(ld_u, kTileBytes);
+        bulk_load(r2_addr, uin + (size_t)blockIdx.x * tile_floats, kTileBytes, ld_u);
     }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         TC_TRACE(plan, it, 0);
@@ -1059,6 +1072,38 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
         sync_for_mma();
+        if constexpr (Cfg::bulk_uv) {
+            // ---- phase 1: conv.0(x) | dense2(u') (u' landed a tile ago); then v' -> region, next tile's u' -> second region
+            if (w0 && elect_one()) {
+                issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true);
+                mbar_wait(ld_u, ld_phase & 1);
+                fence_after_sync();
+                issue_linear_t<G, MG_PD2A, true>(ring, plan, r2_addr, ones_addr, tm + Cfg::col_acc, true);
+                commit(s.done);
+            }
+            wait_done_ring<G>(s.done, phase, ring, plan, w0);
+            if (w0 && elect_one()) {
+                mbar_expect_tx(ld_v, kTileBytes);
+                bulk_load(region_addr, vin + (size_t)t * tile_floats, kTileBytes, ld_v);
+                if (t + (int)gridDim.x < ntiles) {
+                    mbar_expect_tx(ld_u, kTileBytes);
+                    bulk_load(r2_addr, uin + (size_t)(t + gridDim.x) * tile_floats, kTileBytes, ld_u);
+                }
+            }
+            ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
+            // ---- phase 2: dense2(v') accumulates (no thread wrote an operand: the elected lane issues as soon as v' is in)
+            if (w0 && elect_one()) {
+                mbar_wait(ld_v, ld_phase & 1);
+                fence_after_sync();
+                issue_linear_t<G, MG_PD2B, true>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false);
+                commit(s.done);
+            }
+            ++ld_phase;
+            wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        } else {
         if (w0 && elect_one()) { issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true); commit(s.done); }
         TC_TRACE(plan, it, 2);
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
@@ -1087,6 +1132,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
         TC_TRACE(plan, it, 8);
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
+        }
         TC_TRACE(plan, it, 9);
         // x1 = acc + x0; q = x1 + x0 -> global; LayerNorm(x1) (affine folded into conv1) -> region
         {
@@ -1511,7 +1557,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        m.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                      // mirrors MergeG::nslot / MergeG::cap
+        m.nslot = c == 64 ? 3 : 2;                                     // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
         tc_add(m, MG_CONV0, off, c, cin, true, mcap);
         tc_add(m, MG_PD2A, off, c, c, false, mcap);
@@ -1648,6 +1694,7 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
         tc_merge_bulk_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     } else {
         const TcPlan& p = P.merge[level];
+        BALF_REQUIRE(!MergeCfg<C>::bulk_uv || g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
         const size_t smem = tc_smem_bytes(MergeCfg<C>::region, p);
         if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, MergeCfg<C>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 128 ? "det_merge_c128" : "det_merge_c256", st);
