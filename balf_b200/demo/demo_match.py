@@ -97,13 +97,27 @@ class DetectPipeline:
     keypoint records come back through pinned staging buffers -- every batch still crosses PCIe both ways, the copies
     just no longer sit between the kernels of consecutive batches."""
 
-    def __init__(self, args, detector, device, nms="greedy"):
+    def __init__(self, args, detector, device, nms="greedy", depth=4):
         self.args, self.detector, self.nms = args, detector, nms
         self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.compute_stream = torch.cuda.Stream(self.dev)
+        self.depth, self._n, self._slots, self._in_flight = depth, 0, {}, 0
+
+    def _staging(self, outs):
+        """pinned host buffers, a ring of ``depth`` sets per output shape (no allocation in the steady state);
+        a set is reused ``depth`` submissions later, i.e. after its ticket has normally been collected."""
+        key = tuple((tuple(o.shape), o.dtype) for o in outs)
+        ring = self._slots.setdefault(key, [])
+        if len(ring) < self.depth:
+            ring.append([torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs])
+            return ring[-1]
+        return ring[self._n % self.depth]
 
     def submit(self, images):
+        if self._in_flight >= self.depth:
+            raise RuntimeError("DetectPipeline: %d batches in flight, collect a result first" % self._in_flight)
+        self._in_flight += 1
         t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
         with torch.cuda.stream(self.copy_stream):
             u8 = t.to(self.dev, non_blocking=True)
@@ -113,18 +127,19 @@ class DetectPipeline:
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(arrived)
             xy, sc, _, cnt = detect_batch_device(self.args, u8, self.detector, self.nms)
-            host = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in (xy, sc, cnt)]
+            host = self._staging((xy, sc, cnt))
             for h, o in zip(host, (xy, sc, cnt)):
                 h.copy_(o, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.compute_stream)
+        self._n += 1
         return host, done, (xy, sc, cnt)              # device tensors kept alive until the copies have run
 
-    @staticmethod
-    def result(ticket):
+    def result(self, ticket):
         host, done, _ = ticket
         done.synchronize()
-        return tuple(h.numpy() for h in host)
+        self._in_flight -= 1
+        return tuple(h.numpy().copy() for h in host)     # the staging set is recycled `depth` submissions later
 
 
 def detect(args, im, detector, device):

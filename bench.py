@@ -358,19 +358,22 @@ def main():
     # records come back device -> host inside the timed region.  DetectPipeline is the streaming form of
     # demo_match.detect_batch: the copy of step i+1 overlaps the kernels of step i.
     pipe = demo_match.DetectPipeline(args, det, dev, a.nms)
-    for _ in range(2):
+    for _ in range(max(a.warmup, 3)):
         res = pipe.result(pipe.submit(host))
-    barrier()
-    t0 = time.perf_counter()
-    prev = None
-    for _ in range(a.steps):
-        cur = pipe.submit(host)
-        if prev is not None:
-            res = pipe.result(prev)
-        prev = cur
-    res = pipe.result(prev)
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) * 1e3
+    e2e_passes = []
+    for _ in range(2):                  # two passes of K steps; the faster one is reported, both are listed (host-side
+        barrier()                       # hiccups of 100+ ms were seen once in four runs on the shared box)
+        t0 = time.perf_counter()
+        prev = None
+        for _ in range(a.steps):
+            cur = pipe.submit(host)
+            if prev is not None:
+                res = pipe.result(prev)
+            prev = cur
+        res = pipe.result(prev)
+        torch.cuda.synchronize()
+        e2e_passes.append((time.perf_counter() - t0) * 1e3)
+    t_e2e = min(e2e_passes)
     d2h = sum(int(r.nbytes) for r in res)
 
     t = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
@@ -402,7 +405,7 @@ def main():
                    "padded": "512x640", "weights": "random-init torch.manual_seed(0)",
                    "l2": "no explicit flush: each step streams >2 GB of activations per GPU, far above the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": images * a.steps / (t_e2e * 1e-3), "unit": "images/s",
+        "e2e": {"value": images * a.steps / (t_e2e * 1e-3), "unit": "images/s", "passes_ms": [round(x, 3) for x in e2e_passes],
                 "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": roof,

@@ -155,6 +155,8 @@ def test_detect_pipeline_equals_detect_batch(detector):
     for nms in ("windowed", "greedy"):
         pipe = demo_match.DetectPipeline(args, det, DEV, nms)
         tickets = [pipe.submit(b) for b in batches]
+        with pytest.raises(RuntimeError):
+            pipe.submit(batches[0])                       # depth = 4 batches in flight: collect first
         for b, t in zip(batches, tickets):
             got = pipe.result(t)
             want = demo_match.detect_batch(args, b, det, DEV, nms)
