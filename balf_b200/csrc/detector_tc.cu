@@ -637,7 +637,7 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
 // right after the current tile's operand is stored, so the ~2000-cycle global-load latency at the top of every tile
 // (scripts/tc_trace.py) hides under the tile's six GEMM phases.
 template <int CIN> struct InputPf {
-    static constexpr bool enabled = CIN <= 32;
+    static constexpr bool enabled = CIN <= 64;
     static constexpr int N = CIN < 8 ? 1 : CIN / 8;
     float4 v[N];
 };
