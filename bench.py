@@ -358,11 +358,16 @@ def main():
     # records come back device -> host inside the timed region.  DetectPipeline is the streaming form of
     # demo_match.detect_batch: the copy of step i+1 overlaps the kernels of step i.
     pipe = demo_match.DetectPipeline(args, det, dev, a.nms)
-    for _ in range(max(a.warmup, 3)):
-        res = pipe.result(pipe.submit(host))
+    prev = None
+    for _ in range(max(a.warmup, 3) + pipe.depth):      # warm up in the pipelined pattern itself: the staging ring and the
+        cur = pipe.submit(host)                          # second in-flight device batch are allocated here, not in the timed passes
+        if prev is not None:
+            res = pipe.result(prev)
+        prev = cur
+    res = pipe.result(prev)
     e2e_passes = []
-    for _ in range(2):                  # two passes of K steps; the faster one is reported, both are listed (host-side
-        barrier()                       # hiccups of 100+ ms were seen once in four runs on the shared box)
+    for _ in range(2):                  # two passes of K steps; the faster one is reported, both are listed
+        barrier()
         t0 = time.perf_counter()
         prev = None
         for _ in range(a.steps):
