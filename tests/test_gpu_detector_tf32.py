@@ -119,3 +119,23 @@ def test_keypoint_agreement(det_tc, detector_sd):
         ww = set(map(tuple, wantw[:, :2].astype(int).tolist()))
         assert len(gotw & ww) >= 0.99 * len(ww), (seed, len(gotw & ww), len(ww))
     assert n_inter >= 0.985 * n_ref, (n_inter, n_ref)
+
+
+def test_large_shapes_tf32_vs_fp32_path(det_tc):
+    """BASELINE.json configs[2] / [3] shapes (HPatches-like 900x1200 -> 960x1216 padded, 1024x1024): the tensor-core
+    path against the library's fp32 path (itself pinned to the oracle at 2e-5) -- tolerance of the north star,
+    per-image independence across the internal pass boundary, bit reproducibility."""
+    import balf_b200._capi as capi
+    d32 = copy.deepcopy(det_tc)
+    d32.precision = "fp32"
+    for hp, wp, b in ((960, 1216, 3), (1024, 1024, 2)):
+        x = torch.rand(b, 3, hp, wp, generator=torch.Generator().manual_seed(hp))
+        _, p_tc = run(det_tc, x)
+        _, p_32 = run(d32, x)
+        np.testing.assert_allclose(p_tc.numpy(), p_32.numpy(), rtol=TF32_RTOL)
+        capi.debug_set(1, 1)                         # one image per internal pass
+        try:
+            _, p_one = run(det_tc, x)
+        finally:
+            capi.debug_set(1, 0)
+        np.testing.assert_array_equal(p_tc.numpy(), p_one.numpy())
