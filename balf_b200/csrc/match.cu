@@ -128,6 +128,20 @@ __global__ void __launch_bounds__(256) nn2_kernel(const float* __restrict__ Q, c
 }
 
 // mutual check + ratio test + ordered compaction (single CTA; n1 <= 65536)
+// Partial top-2 results of the key splits (tensor-core path) -> one (v0, v1, i0) per row, merged in split order.
+__global__ void merge_splits_kernel(float* __restrict__ v0, float* __restrict__ v1, int* __restrict__ i0, int n, int splits) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    Top2 t;
+    t.v0 = v0[r]; t.v1 = v1[r]; t.i0 = i0[r];
+    for (int s = 1; s < splits; ++s) {
+        Top2 o;
+        o.v0 = v0[(size_t)s * n + r]; o.v1 = v1[(size_t)s * n + r]; o.i0 = i0[(size_t)s * n + r];
+        t.merge(o);
+    }
+    v0[r] = t.v0; v1[r] = t.v1; i0[r] = t.i0;
+}
+
 __global__ void __launch_bounds__(1024) smnn_select_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
                                                            const int* __restrict__ ai, int n1, const float* __restrict__ b0,
                                                            const float* __restrict__ b1, const int* __restrict__ bi, int n2,
@@ -169,13 +183,25 @@ __global__ void __launch_bounds__(1024) smnn_select_kernel(const float* __restri
     if (threadIdx.x == 0) *count = base;
 }
 
+int match_tc_nn2(bool swap, const float* Q, const float* qn, int nq, const float* Kd, const float* kn, int nk, int splits,
+                 float* best0, float* best1, int* arg0, float* dm, size_t ld_q, size_t ld_k, cudaStream_t st);   // match_tc.cu
+int g_match_impl = 0;              // debug hook (balf_debug_set key 3): 0 = tensor cores (3xTF32), 1 = fp32 FFMA kernel
+constexpr int kMaxSplits = 8;
+
+// key splits of the tensor-core path: enough CTAs to cover the SMs, at least 256 keys per split
+static int match_splits(int nq, int nk) {
+    int s = 148 / cdiv(nq, 128);
+    if (s > cdiv(nk, 256)) s = cdiv(nk, 256);
+    return s < 1 ? 1 : s > kMaxSplits ? kMaxSplits : s;
+}
+
 }  // namespace balf
 
 using namespace balf;
 
 extern "C" size_t balf_match_workspace_bytes(int n1, int n2) {
     if (n1 <= 0 || n2 <= 0) return 256;
-    return 4 * align_up(sizeof(float) * (size_t)n1, 256) + 4 * align_up(sizeof(float) * (size_t)n2, 256);
+    return (1 + 3 * kMaxSplits) * align_up(sizeof(float) * (size_t)n1, 256) + (1 + 3 * kMaxSplits) * align_up(sizeof(float) * (size_t)n2, 256);
 }
 
 extern "C" int balf_match_smnn(const float* d1, int n1, const float* d2, int n2, int dim, float th, int32_t* ids,
@@ -194,21 +220,30 @@ extern "C" int balf_match_smnn(const float* d1, int n1, const float* d2, int n2,
     char* p = static_cast<char*>(workspace);
     const size_t s1 = align_up(sizeof(float) * (size_t)n1, 256), s2 = align_up(sizeof(float) * (size_t)n2, 256);
     float* n1sq = reinterpret_cast<float*>(p); p += s1;
-    float* a0 = reinterpret_cast<float*>(p); p += s1;
-    float* a1 = reinterpret_cast<float*>(p); p += s1;
-    int* ai = reinterpret_cast<int*>(p); p += s1;
+    float* a0 = reinterpret_cast<float*>(p); p += kMaxSplits * s1;        // [splits][n1] partial results, merged into split 0
+    float* a1 = reinterpret_cast<float*>(p); p += kMaxSplits * s1;
+    int* ai = reinterpret_cast<int*>(p); p += kMaxSplits * s1;
     float* n2sq = reinterpret_cast<float*>(p); p += s2;
-    float* b0 = reinterpret_cast<float*>(p); p += s2;
-    float* b1 = reinterpret_cast<float*>(p); p += s2;
+    float* b0 = reinterpret_cast<float*>(p); p += kMaxSplits * s2;
+    float* b1 = reinterpret_cast<float*>(p); p += kMaxSplits * s2;
     int* bi = reinterpret_cast<int*>(p);
     constexpr size_t kNn2Smem = sizeof(float) * kDim * (QT + 4 + KT + 4);
-    BALF_CUDA_OK(cudaFuncSetAttribute(nn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNn2Smem));
     {
         ProfScope ps("match_sqnorm", st);
         sqnorm_kernel<<<cdiv(n1, 8), 256, 0, st>>>(d1, n1, n1sq);
         sqnorm_kernel<<<cdiv(n2, 8), 256, 0, st>>>(d2, n2, n2sq);
     }
-    {
+    if (g_match_impl == 0) {
+        ProfScope ps("match_nn2", st);
+        const int sa = match_splits(n1, n2), sb = match_splits(n2, n1);
+        // NOTE: split s of direction 1 writes a0 + s * n1 (dense, not s1-strided): the merge kernel uses the same stride
+        if (int e = match_tc_nn2(false, d1, n1sq, n1, d2, n2sq, n2, sa, a0, a1, ai, dm_out, (size_t)n2, 1, st)) return e;
+        if (int e = match_tc_nn2(true, d2, n2sq, n2, d1, n1sq, n1, sb, b0, b1, bi, nullptr, 0, 0, st)) return e;
+        if (sa > 1) merge_splits_kernel<<<cdiv(n1, 256), 256, 0, st>>>(a0, a1, ai, n1, sa);
+        if (sb > 1) merge_splits_kernel<<<cdiv(n2, 256), 256, 0, st>>>(b0, b1, bi, n2, sb);
+        BALF_COUNT_LAUNCH(2);
+    } else {
+        BALF_CUDA_OK(cudaFuncSetAttribute(nn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNn2Smem));
         ProfScope ps("match_nn2", st);
         nn2_kernel<<<cdiv(n1, QT), 256, kNn2Smem, st>>>(d1, n1sq, n1, d2, n2sq, n2, a0, a1, ai, dm_out, (size_t)n2, 1);
         nn2_kernel<<<cdiv(n2, QT), 256, kNn2Smem, st>>>(d2, n2sq, n2, d1, n1sq, n1, b0, b1, bi, nullptr, 0, 0);

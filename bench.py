@@ -285,6 +285,25 @@ def extras(dev, pk):
         ms = timed(lambda: capi.match_smnn(d1, d2, 0.99))
         out["smnn"] = {"n1": 2048, "n2": 2048, "ms": ms, "pairs_per_s": 2048 * 2048 / (ms * 1e-3),
                        "note": "includes the device->host read of the match count"}
+        # F1: 2048 patches of one 900 x 1200 image (level-1 pyramid build + bilinear gather); algorithmic bytes =
+        # source read + level write/read + patches written
+        gray = torch.randint(0, 256, (900, 1200), dtype=torch.uint8, device=dev)
+        kp = torch.stack([torch.rand(2048, device=dev) * 1100 + 50, torch.rand(2048, device=dev) * 800 + 50], 1)
+        ms = timed(lambda: capi.extract_patches(gray, kp, 60.0, 32))
+        nbytes = 900 * 1200 + 2 * 4 * 450 * 600 + 4096 * 2048
+        out["patches"] = {"keypoints": 2048, "image": "900x1200", "ms": ms, "bound": "hbm", "achieved_GBs": nbytes / (ms * 1e-3) / 1e9,
+                          "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
+        # BASELINE.json configs[4] in miniature: 3-level pyramid (0.7x), 8192 keypoints per image, 8 x 1024 x 1024
+        from balf_b200.configs import config
+        from balf_b200.demo import demo_match
+        from balf_b200.model import get_model
+        torch.manual_seed(0)
+        det = get_model.load_model(model_cfg()).eval().to(dev)
+        u8 = torch.randint(0, 256, (8, 1024, 1024, 1), dtype=torch.uint8, device=dev)
+        margs = config.default_test_args(sub_pixel=False, num_features=8192)
+        ms = timed(lambda: demo_match.detect_multiscale_batch_device(margs, u8, det, scale=0.7, levels=3), n=3)
+        out["multiscale"] = {"workload": "8 x 1024x1024, 3 levels x 0.7, windowed NMS, top-8192 merged", "ms": ms,
+                             "images_per_s": 8 / (ms * 1e-3)}
     return out
 
 
