@@ -113,3 +113,27 @@ def test_test_config_defaults():
     assert (args.border_size, args.nms_size, args.num_features, args.s_mult, args.patch_size) == (15, 15, 2048, 60, 4)
     assert args.heatmap_confidence_threshold == 0.001 and args.sub_pixel is True and args.order_coord == "xysr"
     assert cfg["model"]["network_architecture"]["en_embed_dims"] == [3, 32, 64, 128, 256]
+
+
+def test_front_end_and_multiscale_host_logic():
+    """SURVEY 8(f) rows: level geometry is host arithmetic shared with the oracle; CPU tensors are refused (no fallback);
+    the --nms switch rejects what is not built before touching the device."""
+    import balf_b200._capi as c
+    from balf_b200.utils import train_utils
+    from oracle import multiscale as oms
+    for n in (1024, 900, 480, 33):
+        for s in (0.7, 0.5, 2 ** -0.5):
+            for l in range(4):
+                assert c.level_size(n, s, l) == oms.level_size(n, s, l)
+    assert [c.level_size(1024, 0.7, l) for l in range(3)] == [1024, 717, 502]
+    with pytest.raises(RuntimeError):
+        c.rgb_to_gray(torch.zeros(4, 4, 3, dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        c.preprocess_f32(torch.zeros(1, 64, 64, 3))
+    with pytest.raises(RuntimeError):
+        c.resize_preprocess_u8(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), 45, 45)
+    with pytest.raises(NotImplementedError):
+        train_utils.extract_detections_batch(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), None, nms="box_nms")
+    with pytest.raises(ValueError):
+        train_utils.extract_detections_batch(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), None, nms="bogus")
+    assert set(train_utils.NMS_BACKENDS) == {"apply_nms", "nms_fast", "apply_nms_fast"}
