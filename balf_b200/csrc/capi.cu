@@ -45,16 +45,23 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 // division followed by the fp32 cast for all 256 inputs.
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int C, float* __restrict__ x,
                                      int Hp, int Wp, int top, int left) {
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y, b = blockIdx.z;
+    // four output pixels per thread (Wp is a multiple of 64): one float4 store per plane
+    const int xo = 4 * (blockIdx.x * blockDim.x + threadIdx.x), yo = blockIdx.y, b = blockIdx.z;
     if (xo >= Wp) return;
-    const int yi = yo - top, xi = xo - left;
-    const bool in = yi >= 0 && yi < H && xi >= 0 && xi < W;
-    const uint8_t* px = img + (((size_t)b * H + (in ? yi : 0)) * W + (in ? xi : 0)) * C;
+    const int yi = yo - top;
+    const bool row_in = yi >= 0 && yi < H;
+    float v[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float v = in ? (float)px[C == 1 ? 0 : c] / 255.0f : 0.0f;
-        x[(((size_t)b * 3 + c) * Hp + yo) * Wp + xo] = v;
+    for (int k = 0; k < 4; ++k) {
+        const int xi = xo + k - left;
+        const bool in = row_in && xi >= 0 && xi < W;
+        const uint8_t* px = img + (((size_t)b * H + (in ? yi : 0)) * W + (in ? xi : 0)) * C;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c][k] = in ? (float)px[C == 1 ? 0 : c] / 255.0f : 0.0f;
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<float4*>(x + (((size_t)b * 3 + c) * Hp + yo) * Wp + xo) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
 }
 
 // tensor_op.py:1-27: out[n, c, r*i+a, r*j+b] = in[n, c*r*r + a*r + b, i, j]
@@ -136,7 +143,8 @@ extern "C" int balf_preprocess_u8(const uint8_t* img, int B, int H, int W, int C
     BALF_REQUIRE(C == 1 || C == 3, "image must have 1 or 3 channels, got %d", C);
     BALF_REQUIRE(B > 0 && H > 0 && W > 0 && top >= 0 && left >= 0 && top + H <= Hp && left + W <= Wp,
                  "image %dx%d at (%d,%d) does not fit the padded size %dx%d", H, W, top, left, Hp, Wp);
-    dim3 grid(cdiv(Wp, 128), Hp, B);
+    BALF_REQUIRE(Wp % 4 == 0, "padded width %d must be a multiple of 4", Wp);
+    dim3 grid(cdiv(Wp, 4 * 128), Hp, B);
     {
         ProfScope p("preprocess_u8", static_cast<cudaStream_t>(stream));
         preprocess_u8_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(img, H, W, C, x, Hp, Wp, top, left);
