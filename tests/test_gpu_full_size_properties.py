@@ -108,3 +108,42 @@ def test_one_full_size_image_against_the_oracle(detector, detector_sd, batch):
     ref = set(map(tuple, want[:, :2].astype(np.int32).tolist()))
     assert len(got & ref) >= 0.99 * K, len(got & ref)
     np.testing.assert_allclose(np.sort(sc[0, :n].cpu().numpy())[::-1][:K // 2], np.sort(want[:, 3])[::-1][:K // 2], rtol=2e-5)
+
+
+def test_config3_pair_properties(detector):
+    """BASELINE.json configs[2]: an HPatches-shaped pair (900x1200 -> 960x1216 padded), detector + greedy NMS (top-2048
+    binds: ~2900 survivors) + level-1 patches + HardNet + SMNN, through properties: shapes, unit-norm descriptors, matches
+    are mutual nearest neighbours passing the 0.99 ratio test under the kernel's own distance matrix, ordered by the first
+    index, each index used once; the second image is the first plus +-2 grey levels of noise, so most keypoints match."""
+    import balf_b200._capi as capi
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
+    det = copy.deepcopy(detector).to(DEV).eval()
+    torch.manual_seed(0)
+    hn = HardNet().eval().to(DEV)
+    args = config.default_test_args()
+    rgb1 = synth_u8(900, 1200, 1234)
+    noise = np.random.default_rng(5).integers(-2, 3, rgb1.shape[:2])[..., None]
+    rgb2 = np.clip(rgb1.astype(np.int64) + noise, 0, 255).astype(np.uint8)
+    g1, g2 = rgb1[..., 0].copy(), rgb2[..., 0].copy()
+    k1, d1 = demo_match.extract_features(args, rgb1, g1, det, hn, DEV)
+    k2, d2 = demo_match.extract_features(args, rgb2, g2, det, hn, DEV)
+    assert k1.shape == (2048, 2) and d1.shape == (2048, 128) and k2.shape == (2048, 2)
+    np.testing.assert_allclose(np.linalg.norm(d1, axis=1), 1.0, atol=1e-4)
+    assert (k1[:, 0] >= 15 - 2).all() and (k1[:, 0] <= 1200 - 15 + 2).all() and (k1[:, 1] >= 15 - 2).all() and (k1[:, 1] <= 900 - 15 + 2).all()
+    t1, t2 = torch.from_numpy(d1).to(DEV), torch.from_numpy(d2).to(DEV)
+    dist, ids, dm = capi.match_smnn(t1, t2, 0.99, want_dm=True)
+    ids, dm = ids.cpu().numpy(), dm.cpu().numpy()
+    assert len(ids) > 200
+    assert (np.diff(ids[:, 0]) > 0).all() and len(np.unique(ids[:, 1])) == len(ids)
+    rows, cols = dm[ids[:, 0]], dm[:, ids[:, 1]].T
+    np.testing.assert_array_equal(rows.argmin(1), ids[:, 1])                     # nearest neighbour both ways
+    np.testing.assert_array_equal(cols.argmin(1), ids[:, 0])
+    r12 = np.sort(rows, 1)[:, 0] / np.sort(rows, 1)[:, 1]
+    r21 = np.sort(cols, 1)[:, 0] / np.sort(cols, 1)[:, 1]
+    assert (r12 <= 0.99).all() and (r21 <= 0.99).all()
+    np.testing.assert_allclose(dist.cpu().numpy()[:, 0], np.maximum(r12, r21), rtol=1e-6)
+    p1, p2 = demo_match.extract_matches(args, rgb1, g1, rgb2, g2, det, hn, DEV)
+    assert p1.shape == p2.shape == (len(ids), 2)
+    assert np.median(np.abs(p1 - p2).max(1)) < 1.0                              # matched keypoints coincide (same scene)
