@@ -20,7 +20,7 @@
 // constant [1 1 0 ...] column block and whose B rows hold the bias split into tf32 hi + lo parts), and
 // the LayerNorm affine parameters that feed a Linear layer are folded into that layer's weights and bias
 // when the weights are packed (W' = W diag(gamma), b' = b + W beta).  GELU is the exact erf form,
-// evaluated as v * Phi(v) with erfc(t) = exp2(t * P(t)) (degree-6 fit, |err| < 3e-7, scripts/fit_gelu.py).
+// evaluated as v * Phi(v) with erfc(t) = exp2(t * P(t)) (degree-5 fit, |err| < 3.7e-6, scripts/fit_gelu.py).
 //
 // The 64x64 token mixing runs as two M=64 MMAs (A = mixing matrix, B = the unit's activations stored
 // [channel][token]); their accumulators interleave in the two 16-lane halves of every 32-lane TMEM
@@ -260,24 +260,13 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
 }
 
 // ------------------------------------------------------------------------------------------ epilogue pieces
-// exact-erf GELU: gelu(v) = max(v, 0) - a * e,  a = |v|,  e = 0.5 erfc(a / sqrt(2)) = exp2(R(a)) with R a degree-6
-// polynomial (R(0) = -1; scripts/fit_gelu.py, |err| < 3.1e-7 absolute).  a is clamped to 4 sqrt(2), where e < 1e-8.
-// 10 instructions: 2 FMNMX, 7 FFMA (immediate coefficients), 1 MUFU.EX2.
+// exact-erf GELU: gelu(v) = max(v, 0) - a * e,  a = |v|,  e = 0.5 erfc(a / sqrt(2)) = exp2(R(a)) with R a degree-5
+// polynomial (R(0) = -1; scripts/fit_gelu.py, |err| < 3.7e-6 absolute).  a is clamped to 4 sqrt(2), where e < 1e-8.
+// Evaluated on pairs of values, see gelu_erf2.
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-__device__ __forceinline__ float gelu_erf(float v) {
-    const float a = fminf(fabsf(v), 5.6568542494923806f);
-    float p = 3.220531653e-05f;
-    p = fmaf(p, a, -7.531010197e-04f);
-    p = fmaf(p, a, 8.000897244e-03f);
-    p = fmaf(p, a, -5.324822292e-02f);
-    p = fmaf(p, a, -4.589224458e-01f);
-    p = fmaf(p, a, -1.151143193e+00f);
-    p = fmaf(p, a, -1.0f);
-    return fmaf(-a, ex2_approx(p), fmaxf(v, 0.0f));
 }
 // ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot for two lanes-worth of work.  The
 // epilogues are issue-bound (ncu: ~50 % issue utilisation at 24 warps/SM, a third of it FFMA), so the GELU polynomial,
@@ -304,15 +293,16 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     return d;
 }
 // two GELUs: the polynomial is evaluated in t = -a (alternating coefficient signs) so that the last step is one FFMA2
-// relu(v) + t * e.  13 instructions per pair (4 FMNMX, 7 FFMA2, 2 MUFU) instead of 20.
+// relu(v) + t * e.  12 instructions per pair (4 FMNMX, 6 FFMA2, 2 MUFU) instead of 20.
 __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
     const float t0 = fmaxf(-fabsf(v0), -5.6568542494923806f), t1 = fmaxf(-fabsf(v1), -5.6568542494923806f);
     const unsigned long long t = pk2(t0, t1);
-    unsigned long long p = fma2(pk2(3.220531653e-05f, 3.220531653e-05f), t, pk2(7.531010197e-04f, 7.531010197e-04f));
-    p = fma2(p, t, pk2(8.000897244e-03f, 8.000897244e-03f));
-    p = fma2(p, t, pk2(5.324822292e-02f, 5.324822292e-02f));
-    p = fma2(p, t, pk2(-4.589224458e-01f, -4.589224458e-01f));
-    p = fma2(p, t, pk2(1.151143193e+00f, 1.151143193e+00f));
+    // degree-5 fit (scripts/fit_gelu.py): |err| < 3.7e-6 absolute, 20x below the tf32 rounding of the value it feeds;
+    // the degree-6 fit (3e-7) measured the same score-map error and keypoint agreement, one FFMA2 more per pair
+    unsigned long long p = fma2(pk2(3.586947569e-04f, 3.586947569e-04f), t, pk2(6.316647399e-03f, 6.316647399e-03f));
+    p = fma2(p, t, pk2(5.013782158e-02f, 5.013782158e-02f));
+    p = fma2(p, t, pk2(-4.613807201e-01f, -4.613807201e-01f));
+    p = fma2(p, t, pk2(1.150490999e+00f, 1.150490999e+00f));
     p = fma2(p, t, pk2(-1.0f, -1.0f));
     float p0, p1;
     upk2(p, p0, p1);

@@ -6,7 +6,7 @@ import numpy as np
 from scipy.special import erfc, erf
 
 T = 4.0
-for deg in (6, 7, 8, 9):
+for deg in (4, 5, 6, 7):
     # Chebyshev nodes on [0, T], weighted least squares on g(t) = log2(erfc(t)) / t
     k = np.arange(4000)
     t = 0.5 * T * (1 - np.cos(np.pi * (k + 0.5) / 4000))
@@ -48,3 +48,20 @@ e = np.exp2(p.astype(np.float64)).astype(np.float32)
 g = (np.maximum(v, 0) - (a * e).astype(np.float32)).astype(np.float32)
 exact = 0.5 * v.astype(np.float64) * (1 + erf(v.astype(np.float64) / np.sqrt(2)))
 print("absorbed form: max abs err %.3e" % np.abs(g - exact).max())
+
+# ---- the kernels use the DEGREE-5 fit (|err| < 3.7e-6: 20x below the tf32 rounding of the values GELU feeds; measured the
+# same score-map error and keypoint agreement as degree 6, one FFMA2 less per pair), evaluated in t = -a:
+k = np.arange(4000)
+t = 0.5 * T * (1 - np.cos(np.pi * (k + 0.5) / 4000)); t = t[t > 1e-6]
+gg = np.log2(erfc(t)) / t
+w = t * t * erfc(t) + 1e-3 * t
+c5, *_ = np.linalg.lstsq(np.vander(t, 5, increasing=True) * w[:, None], gg * w, rcond=None)
+d5 = np.array([c5[i] * s ** (i + 1) for i in range(5)]).astype(np.float32)
+print("degree-5 absorbed coefficients (a^1 .. a^5):", ", ".join("%.9ef" % x for x in d5))
+print("  as evaluated in t = -a (t^5 .. t^1):", ", ".join("%.9ef" % ((-1) ** (i + 1) * d5[i]) for i in range(4, -1, -1)))
+p = np.full_like(a, d5[4])
+for ci in list(d5[3::-1]) + [np.float32(-1.0)]:
+    p = (p * a + ci).astype(np.float32)
+e = np.exp2(p.astype(np.float64)).astype(np.float32)
+g5 = (np.maximum(v, 0) - (a * e).astype(np.float32)).astype(np.float32)
+print("degree-5 absorbed form: max abs err %.3e" % np.abs(g5 - exact).max())
