@@ -394,21 +394,32 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // network-input stage): each group walks its own tiles with its own operand region, TMEM columns, completion barrier and
 // hardware named barrier (id 1 + group), and all groups share one resident copy of the weights.  This is how four tiles are
 // in flight per SM at C = 32 -- four separate CTAs would each need the 39 KB of weights.
-template <int NG>
+template <int NG, int NTG = NT2>
 __device__ __forceinline__ void group_sync(int grp) {
     if constexpr (NG == 1) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"(NT2) : "memory");
+    else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"(NTG) : "memory");
 }
 
-// LayerNorm statistics of a row whose two halves live in two threads: exchange (sum, sum of squares)
-template <int NG = 1>
+// LayerNorm statistics of a row whose TPR parts live in TPR threads: exchange (sum, sum of squares).  TPR = 1: the thread
+// owns the whole row, no exchange and no barrier.  TPR = 4: every thread adds the four partials in part order, so all
+// threads of a row normalise with bit-identical statistics.
+template <int NG = 1, int TPR = 2>
 __device__ __forceinline__ void row_stats(float sum, float sq, float2* xch, int row, int half, int C, float& rstd, float& shift, int grp = 0) {
-    xch[half * TM + row] = make_float2(sum, sq);
-    group_sync<NG>(grp);
-    const float2 o = xch[(half ^ 1) * TM + row];
+    if constexpr (TPR == 2) {
+        xch[half * TM + row] = make_float2(sum, sq);
+        group_sync<NG, TM * TPR>(grp);
+        const float2 o = xch[(half ^ 1) * TM + row];
+        sum += o.x; sq += o.y;
+    } else if constexpr (TPR > 2) {
+        xch[half * TM + row] = make_float2(sum, sq);
+        group_sync<NG, TM * TPR>(grp);
+        sum = 0.f; sq = 0.f;
+#pragma unroll
+        for (int p = 0; p < TPR; ++p) { const float2 o = xch[p * TM + row]; sum += o.x; sq += o.y; }
+    }
     const float inv_c = C == 32 ? 1.0f / 32 : C == 64 ? 1.0f / 64 : C == 128 ? 1.0f / 128 : 1.0f / 256;   // C is a literal at every call
-    const float mean = (sum + o.x) * inv_c;
-    const float var = fmaxf((sq + o.y) * inv_c - mean * mean, 0.f);
+    const float mean = sum * inv_c;
+    const float var = fmaxf(sq * inv_c - mean * mean, 0.f);
     rstd = rsqrtf(var + 1e-5f);                        // MUFU.RSQ, 2 ulp: far inside the tf32 operand rounding that follows
     shift = -mean * rstd;                              // normalised value = v * rstd + shift
 }
@@ -428,23 +439,23 @@ struct TcShared {
     uint32_t* tmem_slot;
     uint64_t* gdone;       // [kMaxGroups] completion barriers of tile groups 1.. (group 0 uses `done`)
 };
-constexpr int kMaxGroups = 4;
+constexpr int kMaxGroups = 8;
 constexpr uint32_t kSchedEntries = 62;
-constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 128;
+constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 256;
 __host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
     return p.resident ? (p.bytes + 127u) / 128u * 128u : p.nslot * p.slot_bytes;
 }
-__host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p, uint32_t groups = 1) {
-    return groups * (region + kXchBytes) + tc_weight_bytes(p) + kOnesBytes + kVecBytes + kSchedBytes + kTcTail;
+__host__ __device__ inline uint32_t tc_smem_bytes(uint32_t region, const TcPlan& p, uint32_t groups = 1, uint32_t xchb = kXchBytes) {
+    return groups * (region + xchb) + tc_weight_bytes(p) + kOnesBytes + kVecBytes + kSchedBytes + kTcTail;
 }
 // region / xch point at group 0's copy; group g's follow at g * region_bytes / g * kXchBytes
-__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p, uint32_t groups = 1) {
+__device__ __forceinline__ TcShared carve(unsigned char* smem, uint32_t region_bytes, const TcPlan& p, uint32_t groups = 1, uint32_t xchb = kXchBytes) {
     TcShared s;
     unsigned char* q = smem;
     s.region = reinterpret_cast<float*>(q); q += groups * region_bytes;
     s.wsm = smem_u32(q); q += tc_weight_bytes(p);
     s.ones = reinterpret_cast<float*>(q); q += kOnesBytes;
-    s.xch = reinterpret_cast<float2*>(q); q += groups * kXchBytes;
+    s.xch = reinterpret_cast<float2*>(q); q += groups * xchb;
     s.vec = reinterpret_cast<float*>(q); q += kVecBytes;
     s.sched = reinterpret_cast<uint2*>(q); q += kSchedBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(q);
@@ -495,11 +506,11 @@ __device__ __forceinline__ void tc_finish(uint32_t tm, uint32_t ncols) {
     if (threadIdx.x < 32) tmem_dealloc(tm, ncols);
 }
 // all threads: operand region written -> visible to the tensor core, TMEM reads retired
-template <int NG = 1>
+template <int NG = 1, int NTG = NT2>
 __device__ __forceinline__ void sync_for_mma(int grp = 0) {
     fence_async_smem();
     fence_before_sync();
-    group_sync<NG>(grp);
+    group_sync<NG, NTG>(grp);
     fence_after_sync();
 }
 // One thread polls the mbarrier; everybody else parks on the (hardware-blocking) CTA barrier instead of
@@ -511,13 +522,13 @@ __device__ __forceinline__ void wait_done(uint64_t* done, uint32_t& phase) {
     fence_after_sync();
 }
 // same, and the issuing lane refills the (now entirely free) weight ring before joining the barrier
-template <typename G, int NG = 1>
+template <typename G, int NG = 1, int NTG = NT2>
 __device__ __forceinline__ void wait_done_ring(uint64_t* done, uint32_t& phase, Ring& r, const TcPlan& p, bool w0, int grp = 0) {
     if (w0 && elect_one()) {
         mbar_wait(done, phase & 1);
         if (!G::resident) ring_top_up<G::nslot>(r, p);
     }
-    group_sync<NG>(grp);
+    group_sync<NG, NTG>(grp);
     ++phase;
     fence_after_sync();
 }
@@ -593,11 +604,11 @@ __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
     if (odd) c0 = recv; else c1 = recv;
 }
 
-// this thread's half of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
-template <int CIN>
+// this thread's part (1 / TPR) of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
+template <int CIN, int TPR = 2>
 __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
                                                float* dst, int row, int half) {
-    if constexpr (CIN < 8) {                       // NCHW network input: half 0 gathers the planes, half 1 zero-fills
+    if constexpr (CIN < 8) {                       // NCHW network input: part 0 gathers the planes, part 1 zero-fills
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (half == 0 && valid) {
             float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -605,10 +616,10 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
             for (int c = 0; c < CIN; ++c) v[c] = __ldg(xin + (img * CIN + c) * npix + pix);
             o = to_tf32(make_float4(v[0], v[1], v[2], v[3]));
         }
-        *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = o;
+        if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = o;
     } else {
-        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
-        constexpr int N = CIN / 8, NB = N > 8 ? 8 : N;          // batches of 8 chunks bound the registers in flight
+        constexpr int N = CIN / (4 * TPR), NB = N > 8 ? 8 : N;          // batches of 8 chunks bound the registers in flight
+        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * N;
 #pragma unroll 1
         for (int j0 = 0; j0 < N; j0 += NB) {
             float4 v[NB];
@@ -623,18 +634,18 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
     }
 }
 
-// Software prefetch of the level input (CIN <= 32: at most 4 float4 per thread): the next tile's rows are requested
+// Software prefetch of the level input (CIN <= 64: at most 8 float4 per thread): the next tile's rows are requested
 // right after the current tile's operand is stored, so the ~2000-cycle global-load latency at the top of every tile
 // (scripts/tc_trace.py) hides under the tile's six GEMM phases.
-template <int CIN> struct InputPf {
+template <int CIN, int TPR = 2> struct InputPf {
+    static constexpr int N = CIN < 8 ? 1 : CIN / (4 * TPR);
     static constexpr bool enabled = CIN <= 64;
-    static constexpr int N = CIN < 8 ? 1 : CIN / 8;
     float4 v[N];
 };
-template <int CIN, bool PAIR = true>
+template <int CIN, bool PAIR = true, int TPR = 2>
 __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid, int half,
-                                                InputPf<CIN>& pf) {
-    if constexpr (CIN < 8) {                       // conv.0 runs on the CUDA cores: both halves of the row need the pixel
+                                                InputPf<CIN, TPR>& pf) {
+    if constexpr (CIN < 8) {                       // conv.0 runs on the CUDA cores: every part of the row needs the pixel
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid) {
 #pragma unroll
@@ -642,26 +653,28 @@ __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, s
         }
         pf.v[0] = make_float4(v[0], v[1], v[2], v[3]);
     } else {
-        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * (CIN / 8);
+        constexpr int N = InputPf<CIN, TPR>::N;
+        const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * N;
         if constexpr (PAIR) {
-            pair_load<CIN / 8>(src, valid, pf.v);           // pair layout; un-swapped when stored (store_input_row)
+            pair_load<N>(src, valid, pf.v);           // pair layout; un-swapped when stored (store_input_row)
         } else {
 #pragma unroll
-            for (int j = 0; j < CIN / 8; ++j) pf.v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < N; ++j) pf.v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
-template <int CIN, bool PAIR = true>
-__device__ __forceinline__ void store_input_row(const InputPf<CIN>& pf, float* dst, int row, int half) {
+template <int CIN, bool PAIR = true, int TPR = 2>
+__device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, float* dst, int row, int half) {
     if constexpr (CIN < 8) {
-        *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
+        if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
     } else {
+        constexpr int N = InputPf<CIN, TPR>::N;
 #pragma unroll
-        for (int j = 0; j < CIN / 8; j += 2) {
+        for (int j = 0; j < N; j += 2) {
             float4 c0 = pf.v[j], c1 = pf.v[j + 1];
             if constexpr (PAIR) pair_unswap(c0, c1);
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j) * TM + row) * 4) = to_tf32(c0);
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * (CIN / 8) + j + 1) * TM + row) * 4) = to_tf32(c1);
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j) * TM + row) * 4) = to_tf32(c0);
+            *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j + 1) * TM + row) * 4) = to_tf32(c1);
         }
     }
 }
@@ -699,8 +712,14 @@ __device__ __forceinline__ void conv0_row(const float4 x, const float* vec, int 
 }
 
 // ------------------------------------------------------------------------------------------ branch kernel
-template <int C> struct BranchCfg {
-    static constexpr int CH = C / 2;
+// TPR = threads per pixel row (each owns C / TPR channels).  The default variant of a stage ("V0") is the round-1 layout
+// (two threads per row); variant 1 is one thread per row at C = 32 (half the per-row overhead instructions -- address
+// arithmetic, barriers, LayerNorm exchanges -- of a kernel that is bound by instruction issue) and four threads per row at
+// C >= 128 (16 epilogue warps instead of 8 on an SM whose epilogues are latency-bound).
+template <int C, int TPR_, int NG_> struct BranchCfgT {
+    static constexpr int TPR = TPR_;
+    static constexpr int NTG = TM * TPR;                           // threads per tile group
+    static constexpr int CH = C / TPR;
     static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
@@ -708,30 +727,33 @@ template <int C> struct BranchCfg {
     static constexpr bool swz_out = C <= 128;                      // u' / v' leave in the swizzled panel layout (bulk-copied by the merge kernels)
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
-    static constexpr int ncols = tc_cols(col_y + 2 * C);
-    static constexpr int groups = C <= 32 ? 4 : C <= 64 ? 2 : 1;   // tile groups per CTA (shared resident weights)
-    static constexpr int min_ctas = 1;
+    static constexpr int ncols = NG_ * tc_cols(col_y + 2 * C) > 512 ? col_y + 2 * C : tc_cols(col_y + 2 * C);   // TMEM columns per group
+    static constexpr int groups = NG_;                             // tile groups per CTA (shared resident weights)
+    static constexpr uint32_t xch = TPR == 1 ? 0u : 2u * TPR * TM * 8u;   // LayerNorm exchange buffers per group
+    static constexpr int SC = TPR == 1 ? 16 : TPR == 4 ? 32 : (CH > 64 ? 64 : CH);   // sub-chunks bound the live registers
 };
+template <int C> struct BranchCfg : BranchCfgT<C, 2, (C <= 32 ? 4 : C <= 64 ? 2 : 1)> {};
 
-template <int CIN, int C, int BR>
-__global__ void __launch_bounds__(NT2 * BranchCfg<C>::groups, BranchCfg<C>::min_ctas)
-tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = BranchCfg<C>;
+template <int CIN, int C, int BR, typename Cfg>
+__device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, const DownW& w, const TcPlan& plan, const UnitGeom& geo,
+                                               float* __restrict__ out, unsigned char* smem) {
     using G = BranchG<CIN, C>;
-    constexpr int CH = Cfg::CH;
-    constexpr int NG = Cfg::groups;
+    constexpr int CH = Cfg::CH, NG = Cfg::groups, TPR = Cfg::TPR, NTG = Cfg::NTG, SC = Cfg::SC;
     static_assert(NG == 1 || G::resident, "tile groups share resident weights (no ring state per group)");
-    TcShared s = carve(smem, Cfg::region, plan, NG);
-    const int grp = NG == 1 ? 0 : (int)(threadIdx.x / NT2);               // tile group (warp-uniform)
-    const int tid = threadIdx.x - grp * NT2, row = tid & (TM - 1), half = tid >> 7;
+    static_assert(CH % SC == 0 && SC % 16 == 0, "sub-chunking");
+    TcShared s = carve(smem, Cfg::region, plan, NG, Cfg::xch);
+    const int grp = NG == 1 ? 0 : (int)(threadIdx.x / NTG);               // tile group (warp-uniform)
+    const int tid = threadIdx.x - grp * NTG, row = tid & (TM - 1), half = tid >> 7;   // half = which part of the row
     const int vblock = (int)blockIdx.x * NG + grp, vgrid = (int)gridDim.x * NG;   // this group as a virtual CTA
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = vblock < ntiles ? (ntiles - 1 - vblock) / vgrid + 1 : 0;
     const DownW::Branch& br = w.br[BR];
     if (grp == 0) {
-        for (int i = tid; i < C; i += NT2) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
-        if constexpr (CIN < 8) conv0_stage_weights<CIN, C>(w, s.vec);
+        for (int i = tid; i < C; i += NTG) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
+        if constexpr (CIN < 8) {
+            for (int i = tid; i < CIN * C; i += NTG) s.vec[kConv0Off + i] = __ldg(w.conv0_w + i);
+            for (int i = tid; i < C; i += NTG) s.vec[kConv0Off + CIN * C + i] = __ldg(w.conv0_b + i);
+        }
     }
     Ring ring;
     const bool w0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;           // first warp of the group: issues its MMAs
@@ -739,7 +761,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     if (NG > 1) {
         if (grp > 0 && w0 && elect_one()) mbar_wait(&s.full[0], 0);       // the resident weights (loaded by group 0) have landed
         s.region += (size_t)grp * (Cfg::region / 4);
-        s.xch += (size_t)grp * (kXchBytes / 8);
+        s.xch += (size_t)grp * (Cfg::xch / 8);
         if (grp > 0) s.done = &s.gdone[grp];
     }
     const uint32_t tm = *s.tmem_slot + (uint32_t)(grp * Cfg::ncols);
@@ -751,17 +773,28 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
     int it = 0;
-    InputPf<CIN> pf;
+    InputPf<CIN, TPR> pf;
     auto coords = [&](int tt, bool& vld, int& im, int& px) {
         const int un = 2 * tt + ug;
         vld = un < geo.total_units;
         im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
         px = unit_pixel<BR>(geo, vld ? un - im * geo.upi : 0, tok);
     };
-    if (InputPf<CIN>::enabled && vblock < ntiles) {
+    auto stats_of = [&](const float (&v)[CH], float& sum, float& sq) {
+        unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < CH; i += 2) {
+            const unsigned long long x = pk2(v[i], v[i + 1]);
+            s2 = add2(s2, x); q2 = fma2(x, x, q2);
+        }
+        float a, b;
+        upk2(s2, a, b); sum = a + b;
+        upk2(q2, a, b); sq = a + b;
+    };
+    if (InputPf<CIN, TPR>::enabled && vblock < ntiles) {
         bool vld; int im, px;
         coords(vblock, vld, im, px);
-        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+        fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
     }
     for (int t = vblock; t < ntiles; t += vgrid, ++it) {
         TC_TRACE(plan, it, 0);
@@ -775,53 +808,43 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             if (t + vgrid < ntiles) {
                 bool vld; int im, px;
                 coords(t + vgrid, vld, im, px);
-                fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+                fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
             }
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
-            if (InputPf<CIN>::enabled) {
-                store_input_row<CIN>(pf, s.region, row, half);
+            if (InputPf<CIN, TPR>::enabled) {
+                store_input_row<CIN, true, TPR>(pf, s.region, row, half);
                 if (t + vgrid < ntiles) {
                     bool vld; int im, px;
                     coords(t + vgrid, vld, im, px);
-                    fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+                    fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
                 }
             } else {
-                load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+                load_input_row<CIN, TPR>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
             }
             TC_TRACE(plan, it, 1);
-            sync_for_mma<NG>(grp);
+            sync_for_mma<NG, NTG>(grp);
             if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
             TC_TRACE(plan, it, 2);
-            wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
+            wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
             TC_TRACE(plan, it, 3);
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         {
-            float sum = 0.f, sq = 0.f;
-            {
-                unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < CH; i += 2) {
-                    const unsigned long long x = pk2(v[i], v[i + 1]);
-                    s2 = add2(s2, x); q2 = fma2(x, x, q2);
-                }
-                float a, b;
-                upk2(s2, a, b); sum = a + b;
-                upk2(q2, a, b); sq = a + b;
-            }
-            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
+            float sum, sq;
+            stats_of(v, sum, sq);
+            row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 4);
-        sync_for_mma<NG>(grp);
+        sync_for_mma<NG, NTG>(grp);
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
         if (w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
-        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 6);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
@@ -829,12 +852,12 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             gelu_row<CH, true>(v, sum, sq);
             if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
             else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
-            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
+            row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 7);
-        sync_for_mma<NG>(grp);
+        sync_for_mma<NG, NTG>(grp);
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
         if (w0 && elect_one()) {
             issue_linear_t<G, BG_D1A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true);
@@ -842,7 +865,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             commit(s.done);
         }
         TC_TRACE(plan, it, 8);
-        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
@@ -851,7 +874,7 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             ld_row<CH>(lane_base + Cfg::col_y + C + col0, v);
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
-            row_stats<NG>(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift, grp);
+            row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3) + (size_t)col0 * 4;
             norm_row<CH>(v, rstd, shift);
 #pragma unroll
@@ -864,14 +887,13 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             }
         }
         TC_TRACE(plan, it, 10);
-        sync_for_mma<NG>(grp);
+        sync_for_mma<NG, NTG>(grp);
         // ---- token mixing, gating y1 * (y2' + 1)
         if (w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
         TC_TRACE(plan, it, 11);
-        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 12);
         {
-            constexpr int SC = CH > 64 ? 64 : CH;                  // sub-chunks bound the live registers at C = 256
 #pragma unroll 1
             for (int c = 0; c < CH; c += SC) {
                 float y1[SC], y2[SC];
@@ -884,14 +906,13 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
             }
         }
         TC_TRACE(plan, it, 13);
-        sync_for_mma<NG>(grp);
+        sync_for_mma<NG, NTG>(grp);
         // ---- dense2 + residual u -> out
         if (w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         TC_TRACE(plan, it, 14);
-        wait_done_ring<G, NG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 15);
         {
-            constexpr int SC = CH > 64 ? 64 : CH;
             // Full-sector stores: a lane's row chunks are 16 bytes, so a warp store of "chunk j of 32 rows" touches 32
             // half-used sectors and the LSU serialises them (removing these stores bought 0.3-0.6 ms per kernel per 64
             // images).  Lanes 2i / 2i+1 therefore swap every other chunk: both lanes write the two halves of one 32-byte
@@ -952,6 +973,20 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
         // the next tile's input load overwrites the region: every MMA reading it has completed (wait_done)
     }
     tc_finish(*s.tmem_slot, tc_cols(Cfg::ncols * NG));
+}
+
+// V = 0: the round-1 layout; V = 1: see BranchCfgT
+template <int C, int V> struct BranchSel { using Cfg = BranchCfg<C>; };
+template <> struct BranchSel<32, 1> { using Cfg = BranchCfgT<32, 1, 5>; };
+template <> struct BranchSel<32, 2> { using Cfg = BranchCfgT<32, 1, 4>; };
+template <> struct BranchSel<128, 1> { using Cfg = BranchCfgT<128, 4, 1>; };
+template <> struct BranchSel<256, 1> { using Cfg = BranchCfgT<256, 4, 1>; };
+
+template <int CIN, int C, int BR, int V>
+__global__ void __launch_bounds__(BranchSel<C, V>::Cfg::NTG * BranchSel<C, V>::Cfg::groups, 1)
+tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    tc_branch_body<CIN, C, BR, typename BranchSel<C, V>::Cfg>(xin, w, plan, geo, out, smem);
 }
 
 
@@ -1635,13 +1670,13 @@ static int num_sms() {
 // persistent grid: one CTA per resident slot.  Resident CTAs per SM = min over shared memory (227 KB usable,
 // 1 KB reserved per CTA), registers (64 K per SM) and TMEM columns (512 per SM).
 template <typename K>
-static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* grid, int groups = 1) {
+static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* grid, int groups = 1, int group_threads = NT2) {
     BALF_REQUIRE(smem <= 227 * 1024, "internal: tc kernel needs %zu bytes of shared memory", smem);
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BALF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     BALF_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
-    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * NT2 * groups;
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * group_threads * groups;
     ntiles = (ntiles + groups - 1) / groups;                // CTAs needed
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (regs_per_cta > 0 && 65536 / regs_per_cta < per_sm) per_sm = 65536 / regs_per_cta;
@@ -1650,6 +1685,44 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
     const int cap = num_sms() * per_sm;
     *grid = ntiles < cap ? ntiles : cap;
     return 0;
+}
+
+
+int g_tc_variant = 0;      // debug hook (balf_debug_set key 4): per-stage branch-kernel variant, 2 bits per stage (BranchSel)
+
+template <int CIN, int C, int V>
+static int tc_launch_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
+                              float* u, float* v, cudaStream_t st) {
+    using Cfg = typename BranchSel<C, V>::Cfg;
+    constexpr int NG = Cfg::groups;
+    int grid = 0;
+    for (int b = 0; b < 2; ++b) {
+        const TcPlan& p = P.branch[level][b];
+        const size_t smem = tc_smem_bytes(Cfg::region, p, NG, Cfg::xch);
+        if (b == 0) {
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0, V>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
+            ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
+            tc_branch_kernel<CIN, C, 0, V><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, u);
+        } else {
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1, V>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
+            ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
+            tc_branch_kernel<CIN, C, 1, V><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, v);
+        }
+    }
+    return 0;
+}
+template <int CIN, int C>
+static int tc_run_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
+                           float* u, float* v, cudaStream_t st) {
+    const int var = (g_tc_variant >> (2 * level)) & 3;
+    if constexpr (C == 32) {
+        if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 2) return tc_launch_branches<CIN, C, 2>(xin, w, P, level, g, ntiles, u, v, st);
+    }
+    if constexpr (C == 128 || C == 256) {
+        if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
+    }
+    return tc_launch_branches<CIN, C, 0>(xin, w, P, level, g, ntiles, u, v, st);
 }
 
 template <int CIN, int C>
@@ -1661,20 +1734,7 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     int grid = 0;
     BALF_REQUIRE((plan_matches<BranchG<CIN, C>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C>>(P.branch[level][1]) &&
                   plan_matches<MergeG<CIN, C>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
-    for (int b = 0; b < 2; ++b) {
-        constexpr int NG = BranchCfg<C>::groups;
-        const TcPlan& p = P.branch[level][b];
-        const size_t smem = tc_smem_bytes(BranchCfg<C>::region, p, NG);
-        if (b == 0) {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0>, smem, tc_cols(BranchCfg<C>::ncols * NG), ntiles, &grid, NG)) return e;
-            ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
-            tc_branch_kernel<CIN, C, 0><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, u);
-        } else {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1>, smem, tc_cols(BranchCfg<C>::ncols * NG), ntiles, &grid, NG)) return e;
-            ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
-            tc_branch_kernel<CIN, C, 1><<<grid, NT2 * NG, smem, st>>>(xin, w, p, g, v);
-        }
-    }
+    if (int e = tc_run_branches<CIN, C>(xin, w, P, level, g, ntiles, u, v, st)) return e;
     if constexpr (C <= 64) {
         const TcPlan& p = P.merge[level];
         BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
