@@ -8,8 +8,8 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(ROOT, "build", "obj")
-LIB = os.path.join(PKG, "libbalf_b200.so")
+OBJ = os.environ.get("BALF_OBJ_DIR") or os.path.join(ROOT, "build", "obj")
+LIB = os.environ.get("BALF_LIB_OUT") or os.path.join(PKG, "libbalf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("NVCC_FLAGS", "").split()

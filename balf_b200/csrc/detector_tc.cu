@@ -35,6 +35,12 @@
 namespace balf {
 using namespace umma;
 
+// development experiments (NVCC_FLAGS=-DBALF_EXP=mask; results are WRONG, the timings show what a piece costs):
+// 1 no GELU math, 2 no shared-memory operand stores, 4 no TMEM loads, 8 no global stores of the branch kernels,
+// 16 no MMA issue / completion wait in the branch kernels
+#ifndef BALF_EXP
+#define BALF_EXP 0
+#endif
 constexpr int TM = 128;                 // pixel rows per tile
 constexpr int NT2 = 256;                // threads per CTA (two per row)
 constexpr int kMaxSlot = 4;              // ring slots: per kernel family (G::nslot), sized from the shared-memory budget
@@ -295,6 +301,7 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 // two GELUs: the polynomial is evaluated in t = -a (alternating coefficient signs) so that the last step is one FFMA2
 // relu(v) + t * e.  12 instructions per pair (4 FMNMX, 6 FFMA2, 2 MUFU) instead of 20.
 __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
+    if (BALF_EXP & 1) return;
     const float t0 = fmaxf(-fabsf(v0), -5.6568542494923806f), t1 = fmaxf(-fabsf(v1), -5.6568542494923806f);
     const unsigned long long t = pk2(t0, t1);
     // degree-5 fit (scripts/fit_gelu.py): |err| < 3.7e-6 absolute, 20x below the tf32 rounding of the value it feeds;
@@ -332,6 +339,11 @@ __device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f *
 // CH consecutive accumulator columns of this thread's row -> registers (tcgen05.ld is warp-collective)
 template <int CH>
 __device__ __forceinline__ void ld_row(uint32_t taddr, float (&v)[CH]) {
+    if (BALF_EXP & 4) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(taddr + i) * 1e-30f;
+        return;
+    }
     if constexpr (CH == 16) {
         tmem_ld16(taddr, v);
     } else {
@@ -360,6 +372,7 @@ __device__ __forceinline__ void st_row(uint32_t taddr, const float (&v)[CH]) {
 // this thread's CH values -> A operand (chunk-major, 128 rows), columns [col0, col0 + CH), tf32-rounded
 template <int CH>
 __device__ __forceinline__ void row_to_a(const float (&v)[CH], float* region, int row, int col0) {
+    if (BALF_EXP & 2) { if (v[0] == 12345.678f) region[row] = v[1]; return; }
 #pragma unroll
     for (int j = 0; j < CH / 4; ++j)
         *reinterpret_cast<float4*>(region + ((size_t)(col0 / 4 + j) * TM + row) * 4) =
@@ -522,10 +535,21 @@ __device__ __forceinline__ void wait_done(uint64_t* done, uint32_t& phase) {
     fence_after_sync();
 }
 // same, and the issuing lane refills the (now entirely free) weight ring before joining the barrier
-template <typename G, int NG = 1, int NTG = NT2>
+// WW: every warp waits on the completion barrier itself (one polling lane per warp) -- no CTA / group barrier after the MMAs
+template <typename G, int NG = 1, int NTG = NT2, bool WW = false>
 __device__ __forceinline__ void wait_done_ring(uint64_t* done, uint32_t& phase, Ring& r, const TcPlan& p, bool w0, int grp = 0) {
+    if constexpr (WW) {
+        if (elect_one()) {
+            if (!(BALF_EXP & 16)) mbar_wait(done, phase & 1);
+            if (w0 && !G::resident) ring_top_up<G::nslot>(r, p);
+        }
+        __syncwarp();
+        ++phase;
+        fence_after_sync();
+        return;
+    }
     if (w0 && elect_one()) {
-        mbar_wait(done, phase & 1);
+        if (!(BALF_EXP & 16)) mbar_wait(done, phase & 1);
         if (!G::resident) ring_top_up<G::nslot>(r, p);
     }
     group_sync<NG, NTG>(grp);
@@ -716,7 +740,8 @@ __device__ __forceinline__ void conv0_row(const float4 x, const float* vec, int 
 // (two threads per row); variant 1 is one thread per row at C = 32 (half the per-row overhead instructions -- address
 // arithmetic, barriers, LayerNorm exchanges -- of a kernel that is bound by instruction issue) and four threads per row at
 // C >= 128 (16 epilogue warps instead of 8 on an SM whose epilogues are latency-bound).
-template <int C, int TPR_, int NG_> struct BranchCfgT {
+template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
+    static constexpr bool WW = WW_;                                // warps wait on the MMA completion barrier directly
     static constexpr int TPR = TPR_;
     static constexpr int NTG = TM * TPR;                           // threads per tile group
     static constexpr int CH = C / TPR;
@@ -824,9 +849,9 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             }
             TC_TRACE(plan, it, 1);
             sync_for_mma<NG, NTG>(grp);
-            if (w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+            if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_linear_t<G, BG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
             TC_TRACE(plan, it, 2);
-            wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
+            wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
             TC_TRACE(plan, it, 3);
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
 #pragma unroll
@@ -842,9 +867,9 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
         TC_TRACE(plan, it, 4);
         sync_for_mma<NG, NTG>(grp);
         // ---- this branch's half of dense1 -> GELU = u (residual, parked) -> LayerNorm (affine folded into gMLP dense1)
-        if (w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
+        if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_linear_t<G, BG_PD1>(ring, plan, region_addr, ones_addr, tm + Cfg::col_u, true); commit(s.done); }
         TC_TRACE(plan, it, 5);
-        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 6);
         {
             ld_row<CH>(lane_base + Cfg::col_u + col0, v);
@@ -859,13 +884,13 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
         TC_TRACE(plan, it, 7);
         sync_for_mma<NG, NTG>(grp);
         // ---- gMLP dense1 (two halves) -> GELU; y1 parked, y2 -> LayerNorm -> [channel][token] operand
-        if (w0 && elect_one()) {
+        if (!(BALF_EXP & 16) && w0 && elect_one()) {
             issue_linear_t<G, BG_D1A>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true);
             issue_linear_t<G, BG_D1B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y + C, true);
             commit(s.done);
         }
         TC_TRACE(plan, it, 8);
-        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 9);
         {
             ld_row<CH>(lane_base + Cfg::col_y + col0, v);
@@ -882,16 +907,18 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 const float2 gw = *reinterpret_cast<const float2*>(s.vec + col0 + i), gb = *reinterpret_cast<const float2*>(s.vec + 256 + col0 + i);
                 float o0, o1;
                 upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), o0, o1);
-                yt[(size_t)i * 4] = to_tf32(o0);
-                yt[(size_t)(i + 1) * 4] = to_tf32(o1);
+                if (!(BALF_EXP & 2) || o0 == 12345.678f) {
+                    yt[(size_t)i * 4] = to_tf32(o0);
+                    yt[(size_t)(i + 1) * 4] = to_tf32(o1);
+                }
             }
         }
         TC_TRACE(plan, it, 10);
         sync_for_mma<NG, NTG>(grp);
         // ---- token mixing, gating y1 * (y2' + 1)
-        if (w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
+        if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
         TC_TRACE(plan, it, 11);
-        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 12);
         {
 #pragma unroll 1
@@ -908,9 +935,9 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
         TC_TRACE(plan, it, 13);
         sync_for_mma<NG, NTG>(grp);
         // ---- dense2 + residual u -> out
-        if (w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
+        if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_linear_t<G, BG_D2>(ring, plan, region_addr, ones_addr, tm + Cfg::col_y, true); commit(s.done); }
         TC_TRACE(plan, it, 14);
-        wait_done_ring<G, NG, NTG>(s.done, phase, ring, plan, w0, grp);
+        wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 15);
         {
             // Full-sector stores: a lane's row chunks are 16 bytes, so a warp store of "chunk j of 32 rows" touches 32
@@ -958,7 +985,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                     recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
                     const float4 to_a = odd ? recv : o[j], to_b = odd ? o[j + 1] : recv;     // (row 2i, row 2i+1), chunk j + odd
                     const int chunk = (col0 + c) / 4 + j + (odd ? 1 : 0);
-                    if (valid) {        // both lanes of a pair belong to the same unit
+                    if (valid && (!(BALF_EXP & 8) || to_a.x == 12345.678f)) {        // both lanes of a pair belong to the same unit
                         if (Cfg::swz_out) {
                             *reinterpret_cast<float4*>(out + base_a + sw_off(sw_a, chunk)) = to_a;
                             *reinterpret_cast<float4*>(out + base_b + sw_off(sw_b, chunk)) = to_b;
@@ -978,7 +1005,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
 // V = 0: the round-1 layout; V = 1: see BranchCfgT
 template <int C, int V> struct BranchSel { using Cfg = BranchCfg<C>; };
 template <> struct BranchSel<32, 1> { using Cfg = BranchCfgT<32, 1, 5>; };
-template <> struct BranchSel<32, 2> { using Cfg = BranchCfgT<32, 1, 4>; };
+template <> struct BranchSel<32, 2> { using Cfg = BranchCfgT<32, 1, 5, true>; };
 template <> struct BranchSel<128, 1> { using Cfg = BranchCfgT<128, 4, 1>; };
 template <> struct BranchSel<256, 1> { using Cfg = BranchCfgT<256, 4, 1>; };
 
@@ -1688,7 +1715,7 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
 }
 
 
-int g_tc_variant = 0;      // debug hook (balf_debug_set key 4): per-stage branch-kernel variant, 2 bits per stage (BranchSel)
+int g_tc_variant = 0x41;     // debug hook (balf_debug_set key 4): per-stage branch-kernel variant, 2 bits per stage (BranchSel)
 
 template <int CIN, int C, int V>
 static int tc_launch_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,

@@ -16,11 +16,15 @@ cfg = test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)
 torch.manual_seed(0)
 det = get_model.load_model(cfg["model"]).eval().to(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-masks = [int(a, 0) for a in sys.argv[2:]] or [0, 0x01, 0x02, 0x10, 0x40, 0x51]
+masks = [int(a, 0) for a in sys.argv[2:]] or [0, 0x01, 0x02, 0x40, 0x41]
 g = torch.Generator().manual_seed(1234)
 u8 = torch.randint(0, 256, (B, 480, 640, 1), dtype=torch.uint8, generator=g).to(dev)
 x, _ = c.preprocess_u8(u8)
 ref = None
+import copy
+d32 = copy.deepcopy(det); d32.precision = "fp32"
+with torch.inference_mode():
+    p32 = d32(x[:2])["prob"].double()
 for m in masks:
     c.debug_set(4, m)
     with torch.inference_mode():
@@ -41,6 +45,8 @@ for m in masks:
         ref = p.clone()
     rel = ((p - ref).abs() / ref).max().item()
     bad = int((~torch.isfinite(p)).sum().item())
+    r32 = ((p[:2].double() - p32).abs() / p32)
+    print("          vs fp32 path (2 images): max rel %.3e  mean %.3e" % (r32.max().item(), r32.mean().item()))
     print("mask 0x%02x: %.3f ms / %d images = %.1f img/s   max rel vs mask 0: %.3e  nonfinite %d" % (m, ms, B, B / ms * 1e3, rel, bad))
     rows = sorted(rep.items(), key=lambda kv: -kv[1][1]) if isinstance(rep, dict) else []
     for name, (n, tot) in rows[:16]:
