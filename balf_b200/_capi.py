@@ -441,3 +441,74 @@ def merge_levels_topk(lists, scales, k_out):
                           fl([s[0] for s in scales]), fl([s[1] for s in scales]), B, K, int(k_out), _ptr(xy_out),
                           _ptr(sc_out), _ptr(lv_out), _ptr(cnt), _stream(dev)))
     return xy_out, sc_out, lv_out, cnt
+
+
+# ------------------------------------------------------------------------------------------ repeatability metrics
+c_double = ctypes.c_double
+_homog_pts = _sig("balf_apply_homography_to_points", c_int, _P, c_int, ctypes.POINTER(c_double), _P, _P)
+_common_masks = _sig("balf_common_region_masks", c_int, ctypes.POINTER(c_double), c_int, c_int, c_int, c_int, c_int, _P, _P, _P)
+_rep_ws = _sig("balf_repeatability_workspace_bytes", c_size_t, c_int, c_int)
+_compute_rep = _sig("balf_compute_repeatability", c_int, _P, c_int, _P, c_int, c_double, c_double, c_double, c_double, _P, _P,
+                    _P, _P, _P, c_size_t, _P)
+_resize_rep = _sig("balf_resize_repeatability", c_int, _P, c_int, _P, c_int, ctypes.POINTER(c_double), c_int, c_int, c_int,
+                   c_int, c_int, c_double, _P, _P, c_size_t, _P)
+
+
+def _h9(h):
+    import numpy as np
+    a = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(9))
+    return (c_double * 9)(*a.tolist())
+
+
+def apply_homography_to_points(points, h):
+    """points [n,4] float64 CUDA (x, y, radius, score), h 3x3 (host) -> [n,4] float64 CUDA."""
+    _need_cuda(points, "the points")
+    p = points.contiguous().double()
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        _ok(_homog_pts(_ptr(p), p.shape[0], _h9(h), _ptr(out), _stream(p.device)))
+    return out
+
+
+def common_region_masks(h_dst_2_src, shape_src, shape_dst, device, border=15):
+    """-> (mask_src uint8 [Hs,Ws], mask_dst uint8 [Hd,Wd]) CUDA."""
+    ms = torch.empty(int(shape_src[0]), int(shape_src[1]), dtype=torch.uint8, device=device)
+    md = torch.empty(int(shape_dst[0]), int(shape_dst[1]), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _ok(_common_masks(_h9(h_dst_2_src), ms.shape[0], ms.shape[1], md.shape[0], md.shape[1], int(border), _ptr(ms), _ptr(md),
+                          _stream(device)))
+    return ms, md
+
+
+def compute_repeatability(src, dst, overlap_err=0.4, eps=1e-6, dist_match_thresh=3, radious_size=30.0):
+    """src [n1,4], dst [n2,4] float64 CUDA -> (scalars float64 [8] CUDA, corr_s int32 [m,2], corr_m int32 [m,2], overflow int32 [1])
+    (see include/balf_b200.h; the first scalars[2] / scalars[3] rows of corr_s / corr_m are valid)."""
+    _need_cuda(src, "the points")
+    s, d = src.contiguous().double(), dst.contiguous().double()
+    n1, n2 = s.shape[0], d.shape[0]
+    dev = s.device
+    m = max(min(n1, n2), 1)
+    scalars = torch.zeros(8, dtype=torch.float64, device=dev)
+    cs = torch.zeros(m, 2, dtype=torch.int32, device=dev)
+    cm = torch.zeros(m, 2, dtype=torch.int32, device=dev)
+    ov = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = _rep_ws(n1, n2)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _ok(_compute_rep(_ptr(s), n1, _ptr(d), n2, float(overlap_err), float(eps), float(dist_match_thresh), float(radious_size),
+                         _ptr(scalars), _ptr(cs), _ptr(cm), _ptr(ov), _ptr(ws), nbytes, _stream(dev)))
+    return scalars, cs, cm, ov
+
+
+def resize_repeatability(kp, wkp, h, shape_src, shape_dst, keep_k_points=1000, distance_thresh=5):
+    """kp [n1,3], wkp [n2,3] float64 CUDA (row, col, prob) -> float64 [6] CUDA (see include/balf_b200.h)."""
+    _need_cuda(kp, "the keypoints")
+    a, b = kp.contiguous().double(), wkp.contiguous().double()
+    dev = a.device
+    out = torch.zeros(6, dtype=torch.float64, device=dev)
+    nbytes = _rep_ws(a.shape[0], b.shape[0])
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _ok(_resize_rep(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _h9(h), int(shape_src[0]), int(shape_src[1]), int(shape_dst[0]),
+                        int(shape_dst[1]), int(keep_k_points), float(distance_thresh), _ptr(out), _ptr(ws), nbytes, _stream(dev)))
+    return out

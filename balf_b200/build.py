@@ -15,6 +15,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-li
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("NVCC_FLAGS", "").split()
 
 
+# per-source flags: the float64 metric kernels follow the reference's unfused Python / NumPy arithmetic
+EXTRA = {"metrics.cu": ["-fmad=false"]}
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -34,7 +38,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(OBJ, src[:-3] + ".o")
         if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
-            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+            jobs.append([NVCC] + FLAGS + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) +
                         ["-c", os.path.join(CSRC, src), "-o", obj])
 
     def run(cmd):

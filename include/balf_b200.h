@@ -207,6 +207,37 @@ BALF_API int balf_merge_levels_topk(int n_levels, const int32_t* const* xy, cons
                                     int k_out, float* xy_out, float* score_out, int32_t* level_out, int32_t* count_out,
                                     void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * repeatability metrics and their homography helpers.  float64 throughout (the reference works
+ * on Python floats); point arrays are [n,4] = (x, y, radius, score) unless stated.  Homographies are HOST arrays of 9
+ * doubles (row-major 3x3).
+ * balf_apply_homography_to_points  replaces balf/benchmark_test/geometry_tools.py:43-64 (+ getAff :66-84): positions through
+ *     H, radii through the local affine approximation of H.
+ * balf_common_region_masks         replaces geometry_tools.py:7-27 (create_common_region_masks): uint8 masks [src_h,src_w]
+ *     and [dst_h,dst_w]; cv2.warpPerspective (INTER_LINEAR, 1/32-pixel grid, zero border) of border-masked ones, >= 0.75,
+ *     border mask again.
+ * balf_compute_repeatability       replaces balf/benchmark_test/repeatability_tools.py:379-490 (+ :492-513): scalars[8]
+ *     (device) = rep_single_scale, rep_multi_scale, num_points_single_scale, num_points_multi_scale,
+ *     error_overlap_single_scale, error_overlap_multi_scale, total_num_points, possible_matches; corr_s / corr_m
+ *     int32 [min(n1,n2),2] = (index in dst, index in src) in the order the reference appends them.  *overflow (device)
+ *     is set when more candidate pairs than the workspace holds (64 per point) reached the overlap threshold.
+ * balf_resize_repeatability        replaces repeatability_tools.py:516-614 (compute_resize_repeatability): kp / wkp [n,3]
+ *     = (row, col, prob), H maps (x, y) of the first image to the second; out6 (device) = repeatability,
+ *     localization_err, common_src_num, common_dst_num, rep_src_num, rep_dst_num.  The inputs are not modified (the
+ *     reference overwrites `keypoints` in place, :560-561).
+ * Ties in every sort resolve in index order (the canonical rule of this library). */
+BALF_API int balf_apply_homography_to_points(const double* pts, int n, const double* h_host, double* out, void* stream);
+BALF_API int balf_common_region_masks(const double* h_dst_2_src_host, int src_h, int src_w, int dst_h, int dst_w, int border,
+                                      uint8_t* mask_src, uint8_t* mask_dst, void* stream);
+BALF_API size_t balf_repeatability_workspace_bytes(int n1, int n2);
+BALF_API int balf_compute_repeatability(const double* src, int n1, const double* dst, int n2, double overlap_err, double eps,
+                                        double dist_match_thresh, double radius_size, double* scalars, int32_t* corr_s,
+                                        int32_t* corr_m, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+BALF_API int balf_resize_repeatability(const double* kp, int n1, const double* wkp, int n2, const double* h_host, int src_h,
+                                       int src_w, int dst_h, int dst_w, int keep_k, double dist_thresh, double* out6,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,5 +195,146 @@ def main():
         print("  %-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 
 
+def ref_metric_modules():
+    """balf/benchmark_test/{repeatability_tools,geometry_tools}.py imported from /root/reference (they import
+    torchvision, which is present, and torchgeometry.core.warp_perspective, which is stubbed: unused by the functions run)."""
+    import importlib.util
+    tgm = sys.modules.get("torchgeometry") or types.ModuleType("torchgeometry")
+    core = types.ModuleType("torchgeometry.core")
+    core.warp_perspective = None
+    tgm.core = core
+    sys.modules["torchgeometry"] = tgm
+    sys.modules["torchgeometry.core"] = core
+    sys.modules.pop("cv2", None)                     # the real OpenCV (create_common_region_masks needs warpPerspective)
+    import cv2  # noqa: F401
+    mods = []
+    for name in ("repeatability_tools", "geometry_tools"):
+        path = os.path.join(REF, "balf/benchmark_test", name + ".py")
+        # the metric functions sort with the ndarray METHOD ``x.argsort()`` (repeatability_tools.py:433, :456, :551), which
+        # the np.argsort shim cannot reach: the module is executed from its source with exactly that call made stable
+        # (same canonical tie rule as everywhere else); nothing else is changed
+        src = open(path).read().replace(".argsort()", ".argsort(kind='stable')")
+        m = types.ModuleType("ref_" + name)
+        m.__file__ = path
+        exec(compile(src, path, "exec"), m.__dict__)
+        mods.append(m)
+    return mods
+
+
+def metric_inputs():
+    """seeded keypoint sets and homographies for the repeatability goldens (also rebuilt by the tests)."""
+    rng = np.random.default_rng(2024)
+    Hm = np.array([[1.02, 0.03, 5.0], [-0.02, 0.98, -3.0], [1e-5, -2e-5, 1.0]])
+    hs, ws = 240, 320
+    n1 = 300
+    src = np.stack([rng.integers(16, ws - 16, n1), rng.integers(16, hs - 16, n1), np.ones(n1), rng.random(n1)], 1).astype(np.float64)
+    # dst image points: 200 true correspondences (src -> dst through H^-1, rounded to the pixel grid) + 80 random ones
+    inv = np.linalg.inv(Hm)
+    p = (inv @ np.stack([src[:200, 0], src[:200, 1], np.ones(200)], 0)).T
+    corr = np.round(p[:, :2] / p[:, 2:]) + rng.integers(-2, 3, (200, 2))
+    rnd = np.stack([rng.integers(16, ws - 16, 80), rng.integers(16, hs - 16, 80)], 1)
+    dst_xy = np.concatenate([corr, rnd], 0)
+    dst = np.concatenate([dst_xy, np.ones((280, 1)), rng.random((280, 1))], 1).astype(np.float64)
+    src_ms = src.copy(); src_ms[:, 2] = rng.uniform(0.6, 3.0, n1)
+    dst_ms = dst.copy(); dst_ms[:, 2] = rng.uniform(0.6, 3.0, 280)
+    return Hm, (hs, ws), src, dst, src_ms, dst_ms
+
+
+def main_r2():
+    """Round-2 vectors (separate files; the round-1 files above stay bit-identical):
+    r2_media.npz          media/im1.jpg, im2.jpg decoded by PIL (RGB and convert('L')) and the reference detect() on them
+    r2_detector_large.npz reference score maps at 960x1216 (configs[2]) and 1024x1024 (configs[3]) + reference detect()
+                          on the two 900x1200 images of configs[2]
+    r2_hardnet2048.npz    reference HardNet on 2048 seeded patches
+    r2_metrics.npz        reference repeatability metrics / homography helpers on seeded keypoint sets"""
+    get_model, tu, HardNet, demo_match, cfg = ref_modules()
+    from PIL import Image
+    torch.set_num_threads(8)
+    torch.manual_seed(0)
+    det = get_model.load_model(cfg["model"]).eval()
+    args = types.SimpleNamespace(border_size=15, nms_size=15, num_features=2048, s_mult=60, order_coord="xysr",
+                                 heatmap_confidence_threshold=0.001, sub_pixel=False, patch_size=4)
+    m = {}
+    for name in ("im1", "im2"):
+        im = Image.open(os.path.join(REF, "media", name + ".jpg"))          # demo_match.load_im (:13-19)
+        rgb = np.asarray(im.convert("RGB")).copy()
+        gray = np.asarray(im.convert("L")).copy()
+        m["rgb_" + name], m["gray_" + name] = rgb, gray
+        with stable_argsort():
+            m["detect_" + name] = demo_match.detect(args, rgb, det, "cpu")
+        pad = tu.mod_padding_symmetric(tu.make_shape_even(rgb / 255.0), 64)
+        x = torch.tensor(pad, dtype=torch.float32).permute(2, 0, 1).unsqueeze(0)
+        with torch.inference_mode():
+            prob = det(x)["prob"][0].numpy()
+        hs = prob.shape[0] // 2 - rgb.shape[0] // 2
+        ws_ = prob.shape[1] // 2 - rgb.shape[1] // 2
+        sc = tu.remove_borders(prob[hs:hs + rgb.shape[0], ws_:ws_ + rgb.shape[1]], 15)
+        m["candidates_" + name] = np.array([(sc >= np.float32(0.001)).sum()])
+        m["prob_sub8_" + name] = prob[::8, ::8].copy()
+        m["prob_stats_" + name] = np.array([prob.astype(np.float64).sum(), prob.min(), prob.max()])
+    np.savez_compressed(os.path.join(OUT, "r2_media.npz"), **m)
+
+    d = {}
+    for (h, w, seed) in ((900, 1200, 1234), (900, 1200, 1235), (1024, 1024, 1234)):
+        im = synth_image_u8(h, w, seed)
+        pad = tu.mod_padding_symmetric(tu.make_shape_even(im / 255.0), 64)
+        x = torch.tensor(pad, dtype=torch.float32).permute(2, 0, 1).unsqueeze(0)
+        with torch.inference_mode():
+            prob = det(x)["prob"][0].numpy()
+        key = "%dx%d_s%d" % (h, w, seed)
+        d["pad_shape_" + key] = np.array(pad.shape)
+        d["prob_sub8_" + key] = prob[::8, ::8].copy()
+        d["prob_row_" + key] = prob[prob.shape[0] // 2 - 1].copy()
+        d["prob_stats_" + key] = np.array([prob.astype(np.float64).sum(), prob.min(), prob.max()])
+        if h == 900:
+            with stable_argsort():
+                d["detect_" + key] = demo_match.detect(args, im, det, "cpu")
+    np.savez_compressed(os.path.join(OUT, "r2_detector_large.npz"), **d)
+
+    torch.manual_seed(0)
+    hn = HardNet().eval()
+    xh = torch.rand(2048, 1, 32, 32, generator=torch.Generator().manual_seed(4321))
+    with torch.inference_mode():
+        oh = torch.cat([hn(xh[i:i + 256]) for i in range(0, 2048, 256)])
+    np.savez(os.path.join(OUT, "r2_hardnet2048.npz"), out=oh.numpy())
+
+    rt, gt = ref_metric_modules()
+    Hm, (hs, ws), src, dst, src_ms, dst_ms = metric_inputs()
+    r = {"H": Hm}
+    with stable_argsort():
+        d2s = gt.apply_homography_to_points(dst, Hm)
+        r["dst_to_src"] = d2s
+        r["dst_to_src_ms"] = gt.apply_homography_to_points(dst_ms, Hm)
+        for tag, a_, b_ in (("unit", src, d2s), ("ms", src_ms, r["dst_to_src_ms"]), ("raw", src, dst)):
+            for oe in (0.4, 0.2):
+                res = rt.compute_repeatability(a_.copy(), b_.copy(), overlap_err=oe)
+                pre = "rep_%s_oe%d_" % (tag, int(oe * 10))
+                r[pre + "scalars"] = np.array([res["rep_single_scale"], res["rep_multi_scale"], res["num_points_single_scale"],
+                                               res["num_points_multi_scale"], res["error_overlap_single_scale"],
+                                               res["error_overlap_multi_scale"], res["total_num_points"], res["possible_matches"]], np.float64)
+                r[pre + "corr"] = np.asarray(res["correspondences"], np.int64).reshape(-1, 2)
+                r[pre + "corr_m"] = np.asarray(res["correspondences_m"], np.int64).reshape(-1, 2)
+        kp = np.stack([src[:, 1], src[:, 0], src[:, 3]], 1)            # (row, col, prob)
+        wkp = np.stack([dst[:, 1], dst[:, 0], dst[:, 3]], 1)
+        # compute_resize_repeatability maps keypoints (x, y) -> H (x, y): the homography from the first image to the second
+        Hs2d = np.linalg.inv(Hm)
+        for k, thr in ((1000, 5), (150, 3), (50, 1)):
+            res = rt.compute_resize_repeatability(kp.copy(), wkp.copy(), Hs2d, (hs, ws), (hs, ws), keep_k_points=k, distance_thresh=thr)
+            r["resize_k%d_t%d" % (k, thr)] = np.array([res["repeatability"], res["localization_err"], res["common_src_num"],
+                                                        res["common_dst_num"], res["rep_src_num"], res["rep_dst_num"]], np.float64)
+    for i, Hx in enumerate((Hm, np.array([[0.9, -0.1, 30.0], [0.12, 1.05, -12.0], [2e-4, 1e-4, 1.0]]))):
+        ms_, md_ = gt.create_common_region_masks(Hx, (hs, ws, 3), (hs + 16, ws - 24, 3))
+        r["mask_H%d" % i] = Hx
+        r["mask_src_%d" % i] = ms_.astype(np.uint8)
+        r["mask_dst_%d" % i] = md_.astype(np.uint8)
+    np.savez_compressed(os.path.join(OUT, "r2_metrics.npz"), **r)
+    for f in sorted(os.listdir(OUT)):
+        if f.startswith("r2_"):
+            print("  %-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":
+        main_r2()
+    else:
+        main()
