@@ -512,3 +512,20 @@ def resize_repeatability(kp, wkp, h, shape_src, shape_dst, keep_k_points=1000, d
         _ok(_resize_rep(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _h9(h), int(shape_src[0]), int(shape_src[1]), int(shape_dst[0]),
                         int(shape_dst[1]), int(keep_k_points), float(distance_thresh), _ptr(out), _ptr(ws), nbytes, _stream(dev)))
     return out
+
+
+_box_nms = _sig("balf_box_nms_map", c_int, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, c_size_t, _P)
+
+
+def box_nms_map(prob, size=4, iou=0.1, min_prob=0.015, keep_top_k=-1):
+    """prob [B,H,W] float32 CUDA -> [B,H,W]: repeatability_tools.box_nms on every map of the batch."""
+    _need_cuda(prob, "the score map")
+    p = prob.contiguous().float()
+    B, H, W = p.shape
+    out = torch.empty_like(p)
+    k = int(keep_top_k) if keep_top_k and keep_top_k > 0 else 0
+    nbytes = _nms_ws(B, H, W, max(k, 1)) + 12 * B * k + 256
+    ws = _workspace(p.device, nbytes)
+    with torch.cuda.device(p.device):
+        _ok(_box_nms(_ptr(p), B, H, W, float(size), float(iou), float(min_prob), k, _ptr(out), _ptr(ws), nbytes, _stream(p.device)))
+    return out

@@ -46,3 +46,11 @@ def compute_resize_repeatability(keypoints, warped_keypoints, h, shape_src, shap
     o = _capi.resize_repeatability(kp, wkp, h, shape_src, shape_dst, keep_k_points, distance_thresh).cpu().numpy()
     return {'repeatability': float(o[0]), 'localization_err': float(o[1]) if o[1] >= 0 else -1,
             'common_src_num': int(o[2]), 'common_dst_num': int(o[3]), 'rep_src_num': int(o[4]), 'rep_dst_num': int(o[5])}
+
+
+def box_nms(prob, size=4, iou=0.1, min_prob=0.015, keep_top_k=-1):
+    """repeatability_tools.py:227-255.  prob: torch tensor [1,H,W] (any device; the reference moves the boxes to the GPU
+    itself) -> tensor [1,H,W] on prob's device."""
+    assert prob.shape[0] == 1 and len(prob.shape) == 3
+    dev = prob.device if prob.is_cuda else _dev(None)
+    return _capi.box_nms_map(prob.to(dev), size, iou, min_prob, keep_top_k).to(prob.device)

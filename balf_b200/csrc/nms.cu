@@ -21,6 +21,7 @@
 namespace balf {
 
 typedef unsigned long long u64;
+int g_greedy_impl = 0;     // development switch (balf_debug_set key 5): 1 = the round-1 one-CTA-per-image greedy kernel
 
 // ------------------------------------------------------------------------------------------ keys
 // key = (sortable(score) << 32) | ~raster : descending key order == score desc, raster asc.
@@ -495,6 +496,247 @@ __global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W,
     }
 }
 
+// ------------------------------------------------------------------------------------------ greedy NMS on cells
+// The same greedy result (nms_fast, test_utils.py:130-168; torchvision.ops.nms for box_nms, repeatability_tools.py:227-255)
+// with work proportional to the ALIVE pixels instead of whole-image window maxima, spread over the whole GPU.
+// The map is cut into S x S cells, S chosen so that (1) any two pixels of one cell exclude each other and (2) the exclusion
+// footprint of a pixel stays inside its 3 x 3 cell neighbourhood (square radius r: S = r + 1).  Then
+//   * at most one pixel per cell is ever kept, and a pixel can only be kept while it is the maximum alive key of its cell;
+//   * per round, one warp per cell: the cell maximum p is KEPT when no alive pixel with a larger key lies inside its footprint:
+//     the eight neighbour maxima decide almost every case (smaller -> cannot interfere; larger and inside the footprint ->
+//     blocked), the rest scans the alive pixels of that neighbour; a kept pixel clears the alive bits of its footprint
+//     (atomicAnd on 256-bit cell masks) and marks the touched cells dirty;
+//   * dirty cells recompute their maximum from their alive pixels only (first round: threshold + border mask).
+// Every decision is monotone -- alive bits only ever clear, a stale cell maximum is an upper bound -- so concurrent warps
+// can only be conservative (a pixel waits one more round), never wrong; two cell maxima inside each other's footprint
+// always see each other, so exactly the larger one proceeds.  Rounds run as kernel pairs over all cells of the batch; a
+// one-CTA-per-image kernel finishes pathological maps (long monotone ramps need one round per kept pixel).
+struct Footprint {
+    int S;              // cell size (<= 16)
+    int reach;          // largest |dy| of the footprint (<= S)
+    int hw[17];         // half width at |dy| (-1: empty row)
+};
+struct CellWs {
+    uint32_t* alive;    // [B][cells][8]   bit ly * 16 + lx of cell pixel (ly, lx)
+    u64* cmax;          // [B][cells]      maximum alive key, 0 = none
+    int* dirty;         // [B][cells]
+    int cx, cy;         // cells per row / column
+};
+__device__ __forceinline__ bool fp_inside(const Footprint& f, int dy, int dx) {
+    const int ay = abs(dy);
+    return ay <= f.reach && abs(dx) <= f.hw[ay];
+}
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+// this lane's 8 pixels of a cell: row ly = lane >> 1, columns (lane & 1) * 8 .. + 7
+// (re)compute the maximum alive key of cell c; init: alive = masked score >= thr
+__device__ __forceinline__ void cell_refresh(const MapView& mv, const CellWs& cw, const Footprint& f, int b, int c, bool init,
+                                             float thr) {
+    const int lane = threadIdx.x & 31;
+    const size_t cell = (size_t)b * cw.cx * cw.cy + c;
+    if (!init) {
+        if (!cw.dirty[cell]) return;                 // warp-uniform
+        __syncwarp();
+        if (lane == 0) cw.dirty[cell] = 0;
+    }
+    const int cyi = c / cw.cx, cxi = c - cyi * cw.cx;
+    const int ly = lane >> 1, lx0 = (lane & 1) * 8;
+    const int y = cyi * f.S + ly;
+    uint32_t word = 0;
+    if (!init && lane < 8) word = cw.alive[cell * 8 + lane];
+    uint32_t bits = init ? 0xFFu : (__shfl_sync(0xffffffffu, word, ly >> 1) >> ((ly & 1) * 16 + lx0)) & 0xFFu;
+    u64 best = 0;
+    uint32_t mine = 0;
+    if (ly < f.S && y < mv.H && bits) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int lx = lx0 + j, x = cxi * f.S + lx;
+            if (((bits >> j) & 1u) && lx < f.S && x < mv.W) {
+                const float sc = mv.masked(b, y, x);
+                if (!init || sc >= thr) {
+                    mine |= 1u << j;
+                    const u64 k = make_key(sc, (uint32_t)(y * mv.W + x));
+                    best = k > best ? k : best;
+                }
+            }
+        }
+    }
+    best = warp_max_u64(best);
+    if (init) {
+        uint32_t w = mine << ((ly & 1) * 16 + lx0);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        if ((lane & 3) == 0) cw.alive[cell * 8 + (lane >> 2)] = w;
+    }
+    if (lane == 0) cw.cmax[cell] = best;
+}
+// decide the maximum of cell c; returns true when it was kept
+__device__ __forceinline__ bool cell_decide(const MapView& mv, const CellWs& cw, const Footprint& f, const NmsWs& ws, int b, int c) {
+    const int lane = threadIdx.x & 31;
+    const size_t cell0 = (size_t)b * cw.cx * cw.cy;
+    const u64 p = cw.cmax[cell0 + c];
+    if (p == 0ull) return false;
+    const int cyi = c / cw.cx, cxi = c - cyi * cw.cx;
+    const int pr = (int)key_raster(p), py = pr / mv.W, px = pr - py * mv.W;
+    bool fast = false, slow = false;
+    int ncell = -1;
+    if (lane < 9 && lane != 4) {
+        const int ny = cyi + lane / 3 - 1, nx = cxi + lane % 3 - 1;
+        if (ny >= 0 && ny < cw.cy && nx >= 0 && nx < cw.cx) {
+            ncell = ny * cw.cx + nx;
+            const u64 m = cw.cmax[cell0 + ncell];
+            if (m > p) {
+                const int qr = (int)key_raster(m), qy = qr / mv.W, qx = qr - qy * mv.W;
+                if (fp_inside(f, qy - py, qx - px)) fast = true; else slow = true;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, fast)) return false;
+    unsigned todo = __ballot_sync(0xffffffffu, slow);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int nc = __shfl_sync(0xffffffffu, ncell, src);
+        const int ny = nc / cw.cx, nx = nc - ny * cw.cx;
+        uint32_t word = lane < 8 ? cw.alive[(cell0 + nc) * 8 + lane] : 0u;
+        const int ly = lane >> 1, lx0 = (lane & 1) * 8, y = ny * f.S + ly;
+        const uint32_t bits = (__shfl_sync(0xffffffffu, word, ly >> 1) >> ((ly & 1) * 16 + lx0)) & 0xFFu;
+        bool hit = false;
+        if (bits && abs(y - py) <= f.reach) {
+            const int hwid = f.hw[abs(y - py)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = nx * f.S + lx0 + j;
+                if (((bits >> j) & 1u) && abs(x - px) <= hwid) {
+                    const u64 k = make_key(mv.masked(b, y, x), (uint32_t)(y * mv.W + x));
+                    hit = hit || k > p;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, hit)) return false;
+    }
+    // kept
+    if (lane == 0) {
+        const unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+        if (slot < ws.cap) ws.keys[(size_t)b * ws.cap + slot] = p; else atomicOr(ws.flags + b, 1);
+    }
+    for (int t = lane; t < 72; t += 32) {
+        const int n = t >> 3, j = t & 7;
+        const int ny = cyi + n / 3 - 1, nx = cxi + n % 3 - 1;
+        if (ny < 0 || ny >= cw.cy || nx < 0 || nx >= cw.cx) continue;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ly = 2 * j + h, y = ny * f.S + ly, ady = abs(y - py);
+            if (ly >= f.S || ady > f.reach) continue;
+            const int hwid = f.hw[ady];
+            if (hwid < 0) continue;
+            const int lo = max(px - hwid - nx * f.S, 0), hi = min(px + hwid - nx * f.S, f.S - 1);
+            if (lo <= hi) mask |= (((1u << (hi - lo + 1)) - 1u) << lo) << (h * 16);
+        }
+        if (mask) {
+            const size_t nc = cell0 + (size_t)ny * cw.cx + nx;
+            atomicAnd(&cw.alive[nc * 8 + j], ~mask);
+            cw.dirty[nc] = 1;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) greedy_cells_refresh_kernel(MapView mv, CellWs cw, Footprint f, int init, float thr) {
+    __shared__ Footprint fs;
+    if (threadIdx.x == 0) fs = f;
+    __syncthreads();
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
+    if (c >= cw.cx * cw.cy) return;
+    cell_refresh(mv, cw, fs, b, c, init != 0, thr);
+}
+__global__ void __launch_bounds__(256) greedy_cells_decide_kernel(MapView mv, CellWs cw, Footprint f, NmsWs ws) {
+    __shared__ Footprint fs;
+    if (threadIdx.x == 0) fs = f;
+    __syncthreads();
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
+    if (c >= cw.cx * cw.cy) return;
+    cell_decide(mv, cw, fs, ws, b, c);
+}
+// one CTA per image: runs rounds until no cell has an alive pixel (returns at once when the multi-CTA rounds finished the job)
+__global__ void __launch_bounds__(1024) greedy_cells_finish_kernel(MapView mv, CellWs cw, Footprint f, NmsWs ws) {
+    __shared__ Footprint fs;
+    __shared__ int alive_cells;
+    if (threadIdx.x == 0) fs = f;
+    const int b = blockIdx.x, nc = cw.cx * cw.cy, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const size_t cell0 = (size_t)b * nc;
+    for (int round = 0; round < (1 << 24); ++round) {          // every round keeps at least the largest alive key
+        __syncthreads();
+        if (threadIdx.x == 0) alive_cells = 0;
+        __syncthreads();
+        for (int c = warp; c < nc; c += nw) cell_refresh(mv, cw, fs, b, c, false, 0.f);
+        __syncthreads();
+        int loc = 0;
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) loc += cw.cmax[cell0 + c] != 0ull ? 1 : 0;
+        if (loc) atomicAdd(&alive_cells, loc);
+        __syncthreads();
+        if (alive_cells == 0) break;
+        for (int c = warp; c < nc; c += nw) cell_decide(mv, cw, fs, ws, b, c);
+        __threadfence_block();
+    }
+    if (threadIdx.x == 0) {
+        const int n = ws.count[b];
+        if (n > (int)ws.cap) { ws.count[b] = (int)ws.cap; ws.flags[b] |= 1; }
+    }
+}
+
+constexpr int kGreedyCellRounds = 8;        // multi-CTA rounds before the per-image finisher (typical maps need 5-7)
+
+static void square_footprint(int r, Footprint* f) {
+    f->S = r + 1;
+    f->reach = r;
+    for (int i = 0; i < 17; ++i) f->hw[i] = i <= r ? r : -1;
+}
+// The kept list needs one slot per cell, so in cell mode the key area is re-cut: [B][cells] keys, then the cell structures
+// (52 bytes per cell against the 12 bytes per pixel of the key + alive areas: any S >= 3 fits).
+static bool cells_layout(const NmsWs& ws, int B, int H, int W, int S, NmsWs* ws2, CellWs* cw) {
+    const int cx = cdiv(W, S), cy = cdiv(H, S);
+    const size_t cells = (size_t)B * cx * cy;
+    const size_t o_alive = align_up(cells * 8, 256), o_cmax = o_alive + align_up(cells * 32, 256);
+    const size_t o_dirty = o_cmax + align_up(cells * 8, 256), need = o_dirty + align_up(cells * 4, 256);
+    const size_t have = align_up(sizeof(u64) * (size_t)H * W * B, 256) + sizeof(float) * (size_t)H * W * B;
+    if (S < 3 || S > 16 || need > have) return false;
+    char* p = reinterpret_cast<char*>(ws.keys);
+    *ws2 = ws;
+    ws2->cap = (size_t)cx * cy;
+    cw->alive = reinterpret_cast<uint32_t*>(p + o_alive);
+    cw->cmax = reinterpret_cast<u64*>(p + o_cmax);
+    cw->dirty = reinterpret_cast<int*>(p + o_dirty);
+    cw->cx = cx;
+    cw->cy = cy;
+    return true;
+}
+static int run_greedy_cells(const MapView& mv, const NmsWs& ws, const CellWs& cw, const Footprint& f, int B, float thr,
+                            cudaStream_t st) {
+    const int nc = cw.cx * cw.cy;
+    dim3 grid(cdiv(nc, 8), B);
+    BALF_CUDA_OK(cudaMemsetAsync(cw.dirty, 0, sizeof(int) * (size_t)nc * B, st));
+    {
+        ProfScope p("nms_greedy_init", st);
+        greedy_cells_refresh_kernel<<<grid, 256, 0, st>>>(mv, cw, f, 1, thr);
+    }
+    {
+        ProfScope p("nms_greedy_rounds", st);
+        for (int r = 0; r < kGreedyCellRounds; ++r) {
+            if (r) greedy_cells_refresh_kernel<<<grid, 256, 0, st>>>(mv, cw, f, 0, thr);
+            greedy_cells_decide_kernel<<<grid, 256, 0, st>>>(mv, cw, f, ws);
+        }
+        greedy_cells_finish_kernel<<<B, 1024, 0, st>>>(mv, cw, f, ws);
+    }
+    BALF_COUNT_LAUNCH(2 * kGreedyCellRounds + 1);
+    BALF_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ select + sort
 // k-th largest value of field(key) among keys satisfying pred -- MSB-first byte-wise radix select.
 template <typename Pred, typename Field>
@@ -810,16 +1052,26 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
     nms_ws_layout(B, H, W, &ws, workspace);
     MapView mv{score, Hs, Ws, top, left, H, W, border};
     BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
-    {
-        dim3 grid(cdiv(W, 128), H, B);
-        ProfScope p("nms_greedy_init", st);
-        greedy_init_kernel<<<grid, 128, 0, st>>>(mv, ws, thr);
-        BALF_COUNT_LAUNCH(1);
+    CellWs cw;
+    Footprint fp;
+    NmsWs wsc;
+    square_footprint(radius, &fp);
+    if (radius >= 2 && radius <= 15 && g_greedy_impl == 0 && cells_layout(ws, B, H, W, fp.S, &wsc, &cw)) {
+        ws = wsc;                                     // kept list: one slot per cell
+        if (int e = run_greedy_cells(mv, ws, cw, fp, B, thr, st)) return e;
+    } else {
+        // radii outside [2, 15] (and the development switch balf_debug_set(5, 1)): whole-image rounds, one CTA per image
+        {
+            dim3 grid(cdiv(W, 128), H, B);
+            ProfScope p("nms_greedy_init", st);
+            greedy_init_kernel<<<grid, 128, 0, st>>>(mv, ws, thr);
+            BALF_COUNT_LAUNCH(1);
+            BALF_LAUNCH_OK();
+        }
+        int e = radius == 15 ? launch_greedy<15>(ws, B, H, W, radius, st) : launch_greedy<0>(ws, B, H, W, radius, st);
+        if (e) return e;
         BALF_LAUNCH_OK();
     }
-    int e = radius == 15 ? launch_greedy<15>(ws, B, H, W, radius, st) : launch_greedy<0>(ws, B, H, W, radius, st);
-    if (e) return e;
-    BALF_LAUNCH_OK();
     if (int e2 = run_select(ws, 1, B, H, W, k, xy, out_score, count, st)) return e2;
     if (subpixel_ps > 0) {
         dim3 grid(cdiv(k, 128), B);
@@ -828,6 +1080,75 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
         BALF_COUNT_LAUNCH(1);
         BALF_LAUNCH_OK();
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ box_nms
+// balf/benchmark_test/repeatability_tools.py:227-255: every pixel with prob >= min_prob is the centre of a size x size box;
+// torchvision.ops.nms keeps boxes in descending score order, dropping a box whose IoU with a kept one exceeds `iou`.  All
+// boxes have the same size, so "IoU > iou" is a fixed set of pixel offsets: the same greedy NMS with that footprint.  IoU is
+// evaluated in float32 exactly like torchvision's kernel: inter / (area_a + area_b - inter) > iou.
+__global__ void box_scatter_keys_kernel(const u64* __restrict__ keys, const int32_t* __restrict__ count, size_t cap, int HW,
+                                        float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= count[b]) return;
+    const u64 k = keys[(size_t)b * cap + i];
+    out[(size_t)b * HW + key_raster(k)] = key_score(k);
+}
+__global__ void box_scatter_xy_kernel(const int32_t* __restrict__ xy, const float* __restrict__ sc, const int32_t* __restrict__ count,
+                                      int k, int W, int HW, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= count[b]) return;
+    out[(size_t)b * HW + (size_t)xy[((size_t)b * k + i) * 2 + 1] * W + xy[((size_t)b * k + i) * 2]] = sc[(size_t)b * k + i];
+}
+
+extern "C" int balf_box_nms_map(const float* prob, int B, int H, int W, float size, float iou, float min_prob, int keep_top_k,
+                                float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    BALF_REQUIRE(prob && out && workspace, "null pointer argument");
+    BALF_REQUIRE(B > 0 && H > 0 && W > 0 && size > 0.f, "bad box_nms arguments");
+    BALF_REQUIRE((size_t)H * W < 0x7FFFFFFFull, "map too large");
+    BALF_REQUIRE(keep_top_k <= 16384, "keep_top_k = %d exceeds the supported maximum of 16384", keep_top_k);
+    const size_t top_bytes = keep_top_k > 0 ? align_up((size_t)B * keep_top_k * 12, 256) : 0;
+    BALF_REQUIRE(workspace_bytes >= nms_ws_layout(B, H, W, nullptr, nullptr) + top_bytes, "workspace too small");
+    Footprint fp;
+    const float area2 = size * size + size * size;
+    int diag = -1;
+    fp.reach = -1;
+    for (int dy = 0; dy < 17; ++dy) {
+        fp.hw[dy] = -1;
+        for (int dx = 0; dx < 17; ++dx) {
+            const float inter = fmaxf(size - (float)dy, 0.f) * fmaxf(size - (float)dx, 0.f);
+            if (inter / (area2 - inter) > iou) fp.hw[dy] = dx;
+        }
+        if (fp.hw[dy] >= 0) fp.reach = dy;
+        if (fp.hw[dy] >= dy) diag = dy;
+    }
+    // cells of S = diag + 1: every two pixels of a cell exclude each other; the footprint must stay within one cell of reach
+    fp.S = diag + 1;
+    BALF_REQUIRE(diag >= 2 && fp.S <= 16 && fp.reach <= fp.S && fp.hw[0] <= fp.S,
+                 "box_nms: size %.2f / iou %.3f gives an exclusion footprint this kernel does not tile (reach %d, full square %d; "
+                 "needs 2 <= square <= 15 and reach <= square + 1)", size, iou, fp.reach, diag);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    NmsWs ws, wsc;
+    nms_ws_layout(B, H, W, &ws, workspace);
+    CellWs cw;
+    BALF_REQUIRE(cells_layout(ws, B, H, W, fp.S, &wsc, &cw), "internal: box_nms cell layout");
+    MapView mv{prob, H, W, 0, 0, H, W, 0};
+    BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
+    BALF_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, st));
+    if (int e = run_greedy_cells(mv, wsc, cw, fp, B, min_prob, st)) return e;
+    if (keep_top_k > 0) {
+        char* extra = static_cast<char*>(workspace) + nms_ws_layout(B, H, W, nullptr, nullptr);
+        int32_t* xy = reinterpret_cast<int32_t*>(extra);
+        float* sc = reinterpret_cast<float*>(extra + (size_t)B * keep_top_k * 8);
+        int32_t* cnt = wsc.flags;                         // reused as the selected count
+        if (int e = run_select(wsc, 1, B, H, W, keep_top_k, xy, sc, cnt, st)) return e;
+        box_scatter_xy_kernel<<<dim3(cdiv(keep_top_k, 256), B), 256, 0, st>>>(xy, sc, cnt, keep_top_k, W, H * W, out);
+    } else {
+        box_scatter_keys_kernel<<<dim3(cdiv((int)wsc.cap, 256), B), 256, 0, st>>>(wsc.keys, wsc.count, wsc.cap, H * W, out);
+    }
+    BALF_COUNT_LAUNCH(1);
+    BALF_LAUNCH_OK();
     return 0;
 }
 

@@ -134,6 +134,14 @@ BALF_API int balf_apply_nms_map(const float* score, int B, int H, int W, int bor
 BALF_API int balf_subpixel_refine(const float* score, int B, int Hs, int Ws, int top, int left, int H, int W,
                                   int border, const int32_t* xy, int n, int ps, float* dxdy, void* stream);
 
+/* balf_box_nms_map  replaces balf/benchmark_test/repeatability_tools.py:227-255 (box_nms, the fourth back end of the --nms
+ *     switch of balf/configs/config_hpatches.py:25-26): prob [B,H,W] -> out [B,H,W] = prob at the pixels torchvision.ops.nms
+ *     keeps (size x size boxes centred on every pixel with prob >= min_prob, IoU threshold `iou`, float32 IoU arithmetic),
+ *     optionally only the keep_top_k best (<= 0: all), zero elsewhere.  Equal scores resolve in raster order.
+ *     Workspace: balf_nms_workspace_bytes(B, H, W, k) + 12 * B * keep_top_k (when keep_top_k > 0). */
+BALF_API int balf_box_nms_map(const float* prob, int B, int H, int W, float size, float iou, float min_prob, int keep_top_k,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * F1  keypoints -> descriptor patches
  *     replaces: demo/demo_match.py:62-69 (kornia laf_from_center_scale_ori with scale s_mult and angle

@@ -328,6 +328,30 @@ def main_r2():
         r["mask_src_%d" % i] = ms_.astype(np.uint8)
         r["mask_dst_%d" % i] = md_.astype(np.uint8)
     np.savez_compressed(os.path.join(OUT, "r2_metrics.npz"), **r)
+
+    # box_nms (repeatability_tools.py:227-255) with torchvision's CPU nms in place of the hard-coded .cuda() call
+    import torchvision
+    bx = {}
+    rngb = np.random.default_rng(99)
+    for name, prob in (("rand", rngb.random((60, 80), dtype=np.float32) * 0.05),
+                       ("ref", det(torch.rand(1, 3, 64, 128, generator=torch.Generator().manual_seed(5)))["prob"][0].detach().numpy())):
+        for size, iou_, top in ((4, 0.1, -1), (4, 0.1, 40), (6, 0.3, -1)):
+            p = torch.from_numpy(prob)
+            pts = torch.stack(torch.where(p >= 0.015)).t()
+            boxes = torch.cat((pts - size / 2.0, pts + size / 2.0), dim=1).to(torch.float32)
+            scores = p[pts[:, 0], pts[:, 1]]
+            # stable descending order first so that torchvision's own sort sees the canonical tie order
+            order = torch.from_numpy(np.argsort(-scores.numpy(), kind="stable"))
+            ind = torchvision.ops.nms(boxes[order], scores[order], iou_)
+            ind = order[ind]
+            if top > 0:
+                ind = ind[:min(top, len(ind))]
+            out = torch.zeros_like(p)
+            out[pts[ind, 0], pts[ind, 1]] = scores[ind]
+            key = "%s_s%d_i%d_k%d" % (name, size, int(iou_ * 10), max(top, 0))
+            bx["prob_" + name] = prob
+            bx["keep_" + key] = np.flatnonzero(out.numpy()).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "r2_boxnms.npz"), **bx)
     for f in sorted(os.listdir(OUT)):
         if f.startswith("r2_"):
             print("  %-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

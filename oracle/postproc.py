@@ -199,3 +199,45 @@ def select_top(pts, num_features):
     if pts.size == 0:
         return np.zeros((0, 3))
     return pts[np.argsort(-pts[:, 3], kind="stable")][:num_features, 0:3]
+
+
+def box_nms(prob, size=4, iou=0.1, min_prob=0.015, keep_top_k=-1):
+    """balf/benchmark_test/repeatability_tools.py:227-255 (box_nms) on one map [H,W] -> [H,W].
+
+    torchvision.ops.nms restated: boxes (y - size/2, x - size/2, y + size/2, x + size/2) in float32 around every pixel with
+    prob >= min_prob, visited in descending score order (ties: raster order -- the canonical rule), a box is dropped when its
+    float32 IoU ``inter / (area_a + area_b - inter)`` with an already kept box exceeds ``iou``.  PINNED against
+    ``torchvision.ops.nms`` (installed) by tests/test_oracle_golden.py and tests/golden/r2_boxnms.npz."""
+    prob = np.asarray(prob, np.float32)
+    h, w = prob.shape
+    ys, xs = np.where(prob >= np.float32(min_prob))
+    sc = prob[ys, xs]
+    order = np.argsort(-sc, kind="stable")
+    half = np.float32(size / 2.0)
+    y1, x1 = ys.astype(np.float32) - half, xs.astype(np.float32) - half
+    y2, x2 = ys.astype(np.float32) + half, xs.astype(np.float32) + half
+    area = (y2 - y1) * (x2 - x1)
+    reach = int(np.ceil(size))
+    kept_grid = -np.ones((h, w), np.int64)
+    keep = []
+    thr = np.float32(iou)
+    for i in order:
+        y, x = int(ys[i]), int(xs[i])
+        win = kept_grid[max(y - reach, 0):y + reach + 1, max(x - reach, 0):x + reach + 1]
+        ok = True
+        for j in win[win >= 0]:
+            ih = max(np.float32(0), min(y2[i], y2[j]) - max(y1[i], y1[j]))
+            iw = max(np.float32(0), min(x2[i], x2[j]) - max(x1[i], x1[j]))
+            inter = np.float32(ih * iw)
+            if np.float32(inter / np.float32(area[i] + area[j] - inter)) > thr:
+                ok = False
+                break
+        if ok:
+            kept_grid[y, x] = i
+            keep.append(i)
+    keep = np.asarray(keep, np.int64)
+    if keep_top_k > 0 and len(keep) > keep_top_k:
+        keep = keep[:keep_top_k]                      # already in descending score order
+    out = np.zeros_like(prob)
+    out[ys[keep], xs[keep]] = sc[keep]
+    return out

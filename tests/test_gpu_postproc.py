@@ -223,3 +223,59 @@ def test_windowed15_two_level_edge_cases():
                       (27, 27, 3.0), (28, 28, 3.1), (40, 8, 1.0), (40, 16, 1.0), (47, 12, 1.0)):
         m[0, y, x] = v
     np.testing.assert_array_equal(gpu_windowed(m, 64, 0, 15)[0], postproc.windowed_detect(m[0], 0, 15, 64))
+
+
+# ----------------------------------------------------------------------------- cell-based greedy NMS (round 2) and box_nms
+def test_greedy_cells_vs_whole_image_kernel_and_oracle():
+    """the multi-CTA cell rounds, the one-CTA-per-image finisher (long monotone ramps need one round per kept pixel, far
+    more than the fixed multi-CTA rounds) and the round-1 whole-image kernel agree with the oracle on every radius"""
+    rng = np.random.default_rng(21)
+    ramp = np.tile(np.linspace(1.0, 0.2, 700, dtype=np.float32), (90, 1))            # strictly decreasing along x
+    ramp += (np.arange(90, dtype=np.float32) * 1e-4)[:, None]
+    maps = {"rand": rng.random((200, 333), dtype=np.float32),
+            "quant": (rng.integers(0, 9, (150, 260)) / 8.0).astype(np.float32),        # heavy ties
+            "ramp": ramp,
+            "sparse": (rng.random((170, 190), dtype=np.float32) * (rng.random((170, 190)) > 0.98)).astype(np.float32)}
+    for name, m in maps.items():
+        for r in (15, 9, 4, 2, 1):
+            border = 15 if name != "ramp" else 3
+            want = oracle_greedy(m, border, 0.015, r, 16384)
+            got = gpu_greedy(m, 16384, border, 0.015, r)[0]
+            np.testing.assert_array_equal(got, want, err_msg="%s r=%d" % (name, r))
+            capi().debug_set(5, 1)
+            try:
+                old = gpu_greedy(m, 16384, border, 0.015, r)[0]
+            finally:
+                capi().debug_set(5, 0)
+            np.testing.assert_array_equal(old, want, err_msg="whole-image kernel %s r=%d" % (name, r))
+
+
+def test_greedy_cells_batch_crop_and_subpixel():
+    g = load_golden("postproc_480x640.npz")
+    score = g["score_480x640"]
+    rng = np.random.default_rng(2)
+    batch = np.stack([score, score[::-1].copy(), np.roll(score, 37, 1), rng.random((480, 640), dtype=np.float32) * 0.03])
+    padded = np.zeros((4, 512, 704), np.float32)
+    padded[:, 16:496, 33:673] = batch
+    got = gpu_greedy(padded, 2048, 15, 0.001, 15, ps=4, crop=(16, 33, 480, 640))
+    for b in range(4):
+        want = oracle_greedy(batch[b], 15, 0.001, 15, 2048, ps=4)
+        np.testing.assert_array_equal(got[b][:, 3], want[:, 3])
+        np.testing.assert_allclose(got[b][:, :2], want[:, :2], atol=SUBPIX_ATOL)
+
+
+def test_box_nms_vs_torchvision_golden():
+    from balf_b200.benchmark_test import repeatability_tools as rt
+    g = load_golden("r2_boxnms.npz")
+    for key in [k for k in g.files if k.startswith("keep_")]:
+        _, name, s, i, kk = key.split("_")
+        size, iou, top = int(s[1:]), int(i[1:]) / 10, int(kk[1:]) or -1
+        prob = torch.from_numpy(g["prob_" + name])[None]
+        out = rt.box_nms(prob.to(dev()), size=size, iou=iou, min_prob=0.015, keep_top_k=top)
+        assert out.shape == prob.shape and out.is_cuda
+        out = out[0].cpu().numpy()
+        np.testing.assert_array_equal(np.flatnonzero(out).astype(np.int32), g[key], err_msg=key)
+        np.testing.assert_array_equal(out[out != 0], g["prob_" + name][out != 0])
+        np.testing.assert_array_equal(out, postproc.box_nms(g["prob_" + name], size, iou, 0.015, top))
+    with pytest.raises(ValueError):                        # boxes that exclude less than a 3 x 3 square are not tiled
+        rt.box_nms(torch.rand(1, 32, 32, device=dev()), size=2, iou=0.6)
