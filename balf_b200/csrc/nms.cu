@@ -389,6 +389,19 @@ __global__ void windowed_nms_generic_kernel(MapView mv, NmsWs ws, int lo, int hi
     else atomicOr(ws.flags + b, 1);
 }
 
+// exclusion footprint of a kept pixel: rows |dy| <= reach, half width hw[|dy|] (a square of radius r for nms_fast; the
+// offsets whose box IoU exceeds the threshold for box_nms)
+constexpr int kFpMax = 64;
+struct Footprint {
+    int S;              // cell size of the cell kernels (<= 16)
+    int reach;          // largest |dy| of the footprint
+    int hw[kFpMax + 1]; // half width at |dy| (-1: empty row)
+};
+__device__ __forceinline__ bool fp_inside(const Footprint& f, int dy, int dx) {
+    const int ay = abs(dy);
+    return ay <= f.reach && abs(dx) <= f.hw[ay];
+}
+
 // ------------------------------------------------------------------------------------------ greedy NMS
 // One CTA per image.  Rounds: every alive pixel whose 64-bit key is the maximum of the alive keys in
 // its (2r+1)^2 window is kept; everything alive within r of a kept pixel dies; repeat until nothing
@@ -424,20 +437,22 @@ __device__ __forceinline__ void greedy_round_tiles(u64* smem, float* alive, int 
     }
 }
 
-__device__ __forceinline__ void greedy_round_generic(float* alive, int H, int W, int r, u64* kept, int cap,
+__device__ __forceinline__ void greedy_round_generic(float* alive, int H, int W, const Footprint& f, u64* kept, int cap,
                                                      int* n_kept, int* n_new, int* sh_new, int sh_cap) {
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         float a = alive[i];
         if (!(a > kNegInf)) continue;
         int y = i / W, x = i - y * W;
         u64 me = make_key(a, (uint32_t)i);
-        int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+        int y0 = max(y - f.reach, 0), y1 = min(y + f.reach, H - 1);
         bool top = true;
-        for (int yy = y0; yy <= y1 && top; ++yy)
-            for (int xx = x0; xx <= x1; ++xx) {
+        for (int yy = y0; yy <= y1 && top; ++yy) {
+            const int hw = f.hw[abs(yy - y)];
+            for (int xx = max(x - hw, 0); xx <= min(x + hw, W - 1); ++xx) {
                 float q = alive[(size_t)yy * W + xx];
                 if (q > kNegInf && make_key(q, (uint32_t)(yy * W + xx)) > me) { top = false; break; }
             }
+        }
         if (top) {
             int slot = atomicAdd(n_kept, 1);
             if (slot < cap) kept[slot] = me;
@@ -446,46 +461,46 @@ __device__ __forceinline__ void greedy_round_generic(float* alive, int H, int W,
         }
     }
 }
+// one warp clears the footprint of a kept pixel
+__device__ __forceinline__ void greedy_suppress(float* alive, int H, int W, const Footprint& f, int p) {
+    const int y = p / W, x = p - y * W;
+    for (int yy = max(y - f.reach, 0); yy <= min(y + f.reach, H - 1); ++yy) {
+        const int hw = f.hw[abs(yy - y)];
+        for (int xx = max(x - hw, 0) + (threadIdx.x & 31); xx <= min(x + hw, W - 1); xx += 32) alive[(size_t)yy * W + xx] = kNegInf;
+    }
+}
 
 constexpr int kGreedyNewCap = 4096;   // kept pixels per round staged in shared memory
 
-template <int R>   // R > 0: tile engine with radius R;  R == 0: generic radius r
-__global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W, int r) {
+template <int R>   // R > 0: tile engine with square radius R;  R == 0: any footprint, direct window scans
+__global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W, Footprint fp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_kept, n_new;
     __shared__ int sh_new[kGreedyNewCap];
+    __shared__ Footprint f;
     const int b = blockIdx.x;
     float* alive = ws.alive + (size_t)b * H * W;
     u64* kept = ws.keys + (size_t)b * ws.cap;
-    if (threadIdx.x == 0) n_kept = 0;
+    if (threadIdx.x == 0) { n_kept = 0; f = fp; }
     __syncthreads();
-    for (int round = 0; round < (1 << 20); ++round) {      // bounded: every round keeps >= 1 pixel or ends
+    for (int round = 0; round < (1 << 24); ++round) {      // bounded: every round keeps >= 1 pixel or ends
         if (threadIdx.x == 0) n_new = 0;
         __syncthreads();
         if constexpr (R > 0) greedy_round_tiles<(R > 0 ? R : 1)>(reinterpret_cast<u64*>(smem_raw), alive, H, W, kept, (int)ws.cap,
                                                        &n_kept, &n_new, sh_new, kGreedyNewCap);
-        else greedy_round_generic(alive, H, W, r, kept, (int)ws.cap, &n_kept, &n_new, sh_new, kGreedyNewCap);
+        else greedy_round_generic(alive, H, W, f, kept, (int)ws.cap, &n_kept, &n_new, sh_new, kGreedyNewCap);
         __syncthreads();
         const int nn = n_new;
         if (nn == 0) break;
         if (nn <= kGreedyNewCap) {
-            // suppression: one warp clears the (2r+1)^2 box of each newly kept pixel
-            for (int i = threadIdx.x >> 5; i < nn; i += blockDim.x >> 5) {
-                int p = sh_new[i], y = p / W, x = p - y * W;
-                int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
-                for (int yy = y0; yy <= y1; ++yy)
-                    for (int xx = x0 + (threadIdx.x & 31); xx <= x1; xx += 32) alive[(size_t)yy * W + xx] = kNegInf;
-            }
+            for (int i = threadIdx.x >> 5; i < nn; i += blockDim.x >> 5) greedy_suppress(alive, H, W, f, sh_new[i]);
         } else {
-            // more new keeps than the staging list holds (tiny radius): re-derive them from the
+            // more new keeps than the staging list holds (tiny footprint): re-derive them from the
             // kept list itself -- the last nn entries were appended this round.
             const int total = min(n_kept, (int)ws.cap);
             for (int i = total - nn + (threadIdx.x >> 5); i < total; i += blockDim.x >> 5) {
                 if (i < 0) continue;
-                int p = (int)key_raster(kept[i]), y = p / W, x = p - y * W;
-                int y0 = max(y - r, 0), y1 = min(y + r, H - 1), x0 = max(x - r, 0), x1 = min(x + r, W - 1);
-                for (int yy = y0; yy <= y1; ++yy)
-                    for (int xx = x0 + (threadIdx.x & 31); xx <= x1; xx += 32) alive[(size_t)yy * W + xx] = kNegInf;
+                greedy_suppress(alive, H, W, f, (int)key_raster(kept[i]));
             }
         }
         __syncthreads();
@@ -511,21 +526,12 @@ __global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W,
 // can only be conservative (a pixel waits one more round), never wrong; two cell maxima inside each other's footprint
 // always see each other, so exactly the larger one proceeds.  Rounds run as kernel pairs over all cells of the batch; a
 // one-CTA-per-image kernel finishes pathological maps (long monotone ramps need one round per kept pixel).
-struct Footprint {
-    int S;              // cell size (<= 16)
-    int reach;          // largest |dy| of the footprint (<= S)
-    int hw[17];         // half width at |dy| (-1: empty row)
-};
 struct CellWs {
     uint32_t* alive;    // [B][cells][8]   bit ly * 16 + lx of cell pixel (ly, lx)
     u64* cmax;          // [B][cells]      maximum alive key, 0 = none
     int* dirty;         // [B][cells]
     int cx, cy;         // cells per row / column
 };
-__device__ __forceinline__ bool fp_inside(const Footprint& f, int dy, int dx) {
-    const int ay = abs(dy);
-    return ay <= f.reach && abs(dx) <= f.hw[ay];
-}
 __device__ __forceinline__ u64 warp_max_u64(u64 v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
@@ -694,7 +700,7 @@ constexpr int kGreedyCellRounds = 8;        // multi-CTA rounds before the per-i
 static void square_footprint(int r, Footprint* f) {
     f->S = r + 1;
     f->reach = r;
-    for (int i = 0; i < 17; ++i) f->hw[i] = i <= r ? r : -1;
+    for (int i = 0; i <= kFpMax; ++i) f->hw[i] = i <= r ? r : -1;
 }
 // The kept list needs one slot per cell, so in cell mode the key area is re-cut: [B][cells] keys, then the cell structures
 // (52 bytes per cell against the 12 bytes per pixel of the key + alive areas: any S >= 3 fits).
@@ -962,13 +968,13 @@ static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStre
 }
 
 template <int R>
-static int launch_greedy(const NmsWs& ws, int B, int H, int W, int r, cudaStream_t st) {
+static int launch_greedy(const NmsWs& ws, int B, int H, int W, const Footprint& fp, cudaStream_t st) {
     size_t smem = R > 0 ? Tile<(R > 0 ? R : 1), (R > 0 ? R : 1), u64>::smem_bytes : 0;
     if (smem > 48 * 1024)
         BALF_CUDA_OK(cudaFuncSetAttribute(greedy_nms_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope p("nms_greedy_rounds", st);
-        greedy_nms_kernel<R><<<B, 256, smem, st>>>(ws, H, W, r);
+        greedy_nms_kernel<R><<<B, 256, smem, st>>>(ws, H, W, fp);
     }
     BALF_COUNT_LAUNCH(1);
     return 0;
@@ -1044,7 +1050,7 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
                                     float* out_score, float* dxdy, int32_t* count, void* workspace,
                                     size_t workspace_bytes, void* stream) {
     if (int e = check_common(score, B, Hs, Ws, top, left, H, W, border, k, xy, out_score, count, workspace, workspace_bytes)) return e;
-    BALF_REQUIRE(radius >= 0, "radius must be >= 0");
+    BALF_REQUIRE(radius >= 0 && radius <= kFpMax, "radius must be in [0, %d]", kFpMax);
     BALF_REQUIRE(subpixel_ps >= 0 && subpixel_ps <= 15, "sub-pixel patch size must be in [0, 15]");
     BALF_REQUIRE(subpixel_ps == 0 || dxdy != nullptr, "dxdy must be given when sub-pixel refinement is on");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1068,7 +1074,7 @@ extern "C" int balf_greedy_nms_topk(const float* score, int B, int Hs, int Ws, i
             BALF_COUNT_LAUNCH(1);
             BALF_LAUNCH_OK();
         }
-        int e = radius == 15 ? launch_greedy<15>(ws, B, H, W, radius, st) : launch_greedy<0>(ws, B, H, W, radius, st);
+        int e = radius == 15 ? launch_greedy<15>(ws, B, H, W, fp, st) : launch_greedy<0>(ws, B, H, W, fp, st);
         if (e) return e;
         BALF_LAUNCH_OK();
     }
@@ -1114,29 +1120,41 @@ extern "C" int balf_box_nms_map(const float* prob, int B, int H, int W, float si
     const float area2 = size * size + size * size;
     int diag = -1;
     fp.reach = -1;
-    for (int dy = 0; dy < 17; ++dy) {
+    for (int dy = 0; dy <= kFpMax; ++dy) {
         fp.hw[dy] = -1;
-        for (int dx = 0; dx < 17; ++dx) {
+        for (int dx = 0; dx <= kFpMax; ++dx) {
             const float inter = fmaxf(size - (float)dy, 0.f) * fmaxf(size - (float)dx, 0.f);
             if (inter / (area2 - inter) > iou) fp.hw[dy] = dx;
         }
         if (fp.hw[dy] >= 0) fp.reach = dy;
         if (fp.hw[dy] >= dy) diag = dy;
     }
-    // cells of S = diag + 1: every two pixels of a cell exclude each other; the footprint must stay within one cell of reach
-    fp.S = diag + 1;
-    BALF_REQUIRE(diag >= 2 && fp.S <= 16 && fp.reach <= fp.S && fp.hw[0] <= fp.S,
-                 "box_nms: size %.2f / iou %.3f gives an exclusion footprint this kernel does not tile (reach %d, full square %d; "
-                 "needs 2 <= square <= 15 and reach <= square + 1)", size, iou, fp.reach, diag);
+    BALF_REQUIRE(size < (float)kFpMax, "box_nms: box size %.2f exceeds the supported maximum of %d", size, kFpMax);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     NmsWs ws, wsc;
     nms_ws_layout(B, H, W, &ws, workspace);
     CellWs cw;
-    BALF_REQUIRE(cells_layout(ws, B, H, W, fp.S, &wsc, &cw), "internal: box_nms cell layout");
     MapView mv{prob, H, W, 0, 0, H, W, 0};
     BALF_CUDA_OK(cudaMemsetAsync(ws.count, 0, align_up(sizeof(int32_t) * B, 256) + sizeof(int32_t) * B, st));
     BALF_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, st));
-    if (int e = run_greedy_cells(mv, wsc, cw, fp, B, min_prob, st)) return e;
+    // cells of S = diag + 1 (every two pixels of a cell exclude each other) tile the problem when the footprint stays within
+    // one cell of reach; other footprints (e.g. size 6 at iou 0.3: a plus-shaped set) run the whole-image kernel
+    fp.S = diag + 1;
+    if (fp.reach < 0) {                                   // iou >= 1: nothing is ever suppressed
+        fp.reach = 0; fp.hw[0] = 0; fp.S = 1;
+    }
+    if (diag >= 2 && fp.S <= 16 && fp.reach <= fp.S && fp.hw[0] <= fp.S && g_greedy_impl == 0 &&
+        cells_layout(ws, B, H, W, fp.S, &wsc, &cw)) {
+        if (int e = run_greedy_cells(mv, wsc, cw, fp, B, min_prob, st)) return e;
+    } else {
+        wsc = ws;
+        dim3 grid(cdiv(W, 128), H, B);
+        greedy_init_kernel<<<grid, 128, 0, st>>>(mv, ws, min_prob);
+        BALF_COUNT_LAUNCH(1);
+        BALF_LAUNCH_OK();
+        if (int e = launch_greedy<0>(ws, B, H, W, fp, st)) return e;
+        BALF_LAUNCH_OK();
+    }
     if (keep_top_k > 0) {
         char* extra = static_cast<char*>(workspace) + nms_ws_layout(B, H, W, nullptr, nullptr);
         int32_t* xy = reinterpret_cast<int32_t*>(extra);

@@ -277,5 +277,7 @@ def test_box_nms_vs_torchvision_golden():
         np.testing.assert_array_equal(np.flatnonzero(out).astype(np.int32), g[key], err_msg=key)
         np.testing.assert_array_equal(out[out != 0], g["prob_" + name][out != 0])
         np.testing.assert_array_equal(out, postproc.box_nms(g["prob_" + name], size, iou, 0.015, top))
-    with pytest.raises(ValueError):                        # boxes that exclude less than a 3 x 3 square are not tiled
-        rt.box_nms(torch.rand(1, 32, 32, device=dev()), size=2, iou=0.6)
+    small = torch.rand(1, 40, 56, generator=torch.Generator().manual_seed(8)) * 0.05       # footprints the cells do not tile
+    for size, iou in ((2, 0.6), (3, 0.05), (9, 0.5)):
+        got = rt.box_nms(small.to(dev()), size=size, iou=iou)[0].cpu().numpy()
+        np.testing.assert_array_equal(got, postproc.box_nms(small[0].numpy(), size, iou, 0.015, -1), err_msg="%s %s" % (size, iou))
