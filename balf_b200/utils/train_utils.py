@@ -14,8 +14,8 @@ from .. import _capi
 #   nms_fast        repeatability_tools.py:138+   greedy, candidates >= threshold                 -> greedy
 #   apply_nms_fast  repeatability_tools.py:25+    greedy over every pixel of the map; the validation loop
 #                   (train_utils.py:165-170) then keeps the points >= 0.015                       -> greedy
-#   box_nms         repeatability_tools.py:227+   torchvision.ops.nms on 4x4 boxes (IoU 0.1): not built
-NMS_BACKENDS = {"apply_nms": "windowed", "nms_fast": "greedy", "apply_nms_fast": "greedy"}
+#   box_nms         repeatability_tools.py:227+   torchvision.ops.nms on 4x4 boxes (IoU 0.1), then the k best  -> box
+NMS_BACKENDS = {"apply_nms": "windowed", "nms_fast": "greedy", "apply_nms_fast": "greedy", "box_nms": "box"}
 
 
 def _points(xy, sc, n):
@@ -38,7 +38,7 @@ def extract_detections(image_RGB_norm, model, device, cell_size=8, nms_size=15, 
     img = torch.as_tensor(np.ascontiguousarray(image_RGB_norm), dtype=torch.float32).to(dev)[None]
     h, w = img.shape[1], img.shape[2]
     x, (top, left) = _capi.preprocess_f32(img)
-    prob = model(x)["prob"]
+    prob = model(x, precision=model.resolve_precision("windowed"))["prob"]
     xy, sc, cnt = _capi.windowed_nms_topk(prob, num_points, border=border_size, nms_size=nms_size, crop=(top, left, h, w))
     n = int(cnt[0])
     return _points(xy[0].cpu().numpy(), sc[0].cpu().numpy(), n), prob[:, top:top + h, left:left + w]
@@ -46,18 +46,24 @@ def extract_detections(image_RGB_norm, model, device, cell_size=8, nms_size=15, 
 
 @torch.no_grad()
 def extract_detections_batch(images_u8, model, nms="nms_fast", nms_size=15, num_points=1000, border_size=15,
-                             heatmap_confidence_threshold=0.015, sub_pixel=False, patch_size=5):
+                             heatmap_confidence_threshold=0.015, sub_pixel=False, patch_size=5, box_size=4, box_iou=0.1):
     """Batched evaluation-time extraction with the reference's evaluation defaults (config_hpatches.py:25-44).
     images_u8 [B,H,W,C] uint8 CUDA -> (xy int32 [B,K,2], score fp32 [B,K], dxdy fp32 [B,K,2] | None, count int32 [B])
     on the device."""
-    if nms == "box_nms":
-        raise NotImplementedError("box_nms (torchvision.ops.nms on 4x4 boxes) is not built; use nms_fast or apply_nms")
     if nms not in NMS_BACKENDS:
         raise ValueError("nms must be one of %s" % sorted(NMS_BACKENDS))
     _, h, w, _ = images_u8.shape
     x, (top, left) = _capi.preprocess_u8(images_u8)
-    prob = model(x)["prob"]
-    if NMS_BACKENDS[nms] == "windowed":
+    kind = NMS_BACKENDS[nms]
+    prob = model(x, precision=model.resolve_precision("windowed" if kind == "windowed" else "greedy"))["prob"]
+    if kind == "box":
+        # repeatability_tools.box_nms(prob, size=4, iou=0.1, min_prob, keep_top_k) on the border-masked crop, then the
+        # surviving pixels as points (get_point_coordinates): a 1 x 1 "window" keeps every positive pixel
+        crop = _capi.apply_nms_map(prob[:, top:top + h, left:left + w].contiguous(), 1, border=border_size)
+        kept = _capi.box_nms_map(crop, size=box_size, iou=box_iou, min_prob=heatmap_confidence_threshold, keep_top_k=num_points)
+        xy, sc, cnt = _capi.windowed_nms_topk(kept, num_points, border=0, nms_size=1)
+        return xy, sc, None, cnt
+    if kind == "windowed":
         xy, sc, cnt = _capi.windowed_nms_topk(prob, num_points, border=border_size, nms_size=nms_size, crop=(top, left, h, w))
         return xy, sc, None, cnt
     return _capi.greedy_nms_topk(prob, num_points, border=border_size, thr=heatmap_confidence_threshold, radius=nms_size,

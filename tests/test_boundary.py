@@ -132,8 +132,6 @@ def test_front_end_and_multiscale_host_logic():
         c.preprocess_f32(torch.zeros(1, 64, 64, 3))
     with pytest.raises(RuntimeError):
         c.resize_preprocess_u8(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), 45, 45)
-    with pytest.raises(NotImplementedError):
-        train_utils.extract_detections_batch(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), None, nms="box_nms")
     with pytest.raises(ValueError):
         train_utils.extract_detections_batch(torch.zeros(1, 64, 64, 1, dtype=torch.uint8), None, nms="bogus")
-    assert set(train_utils.NMS_BACKENDS) == {"apply_nms", "nms_fast", "apply_nms_fast"}
+    assert set(train_utils.NMS_BACKENDS) == {"apply_nms", "nms_fast", "apply_nms_fast", "box_nms"}

@@ -97,42 +97,62 @@ def test_keypoint_agreement(det_tc, detector_sd):
         n_inter += len(inter)
         n_ref += len(ref)
     assert n_inter >= 0.99 * n_ref, (n_inter, n_ref)
-    # 480x640, greedy (demo) path.  With random-init weights the score map is nearly flat (0.010-0.023), so the greedy
-    # NMS turns 1e-4 score perturbations into different suppression chains: agreement of the tf32 path is a noisy
-    # per-image statistic -- measured 0.975-0.997 per image and 0.989 over six seeds (scripts/tc_precision.py; the
-    # fp32 path of the same library gives 1.000, tests/test_gpu_detector.py).  Bounds: every image >= 0.97, the
-    # aggregate >= 0.985; the windowed (validation / benchmark) extraction >= 0.99 on every image.
+    # 480x640.  The demo path (demo_match.detect: greedy nms_fast) runs the detector in its DEFAULT precision ('auto' ->
+    # fp32-class FFMA kernels for this path, see MLP_MA_DECODER.resolve_precision): >= 99 % on EVERY image, all six seeds
+    # of scripts/tc_precision.py.  Opting into tf32 on the greedy path is allowed but documented as below the target:
+    # random-init score maps are nearly flat (0.010-0.023) and the greedy suppression chains amplify 1e-4 score
+    # perturbations (measured 0.975-0.997 per image, 0.989 over six seeds); the windowed extraction -- the throughput /
+    # benchmark path, whose default IS tf32 -- keeps >= 99 % on every image.
+    d_auto = copy.deepcopy(det_tc)
+    d_auto.precision = "auto"
     n_inter = n_ref = 0
-    for seed in (1234, 1, 2):
+    for seed in (1234, 1, 2, 3, 4, 5):
         im = synth_u8(480, 640, seed)
-        got = demo_match.detect(args, im, det_tc, "cuda:0")
         want = pipeline.detect(args, detector_sd, im, nms=postproc_c.greedy_nms)
-        inter = set(map(tuple, got[:, :2])) & set(map(tuple, want[:, :2]))
-        assert len(inter) >= 0.97 * len(want), (seed, len(inter), len(want))
-        n_inter += len(inter)
-        n_ref += len(want)
-        # windowed path (validation extraction), top-2048
+        ws = set(map(tuple, want[:, :2]))
+        got = demo_match.detect(args, im, d_auto, "cuda:0")
+        inter = set(map(tuple, got[:, :2])) & ws
+        assert len(inter) >= 0.99 * len(want), ("default precision, greedy", seed, len(inter), len(want))
+        if seed in (1234, 1, 2):
+            got = demo_match.detect(args, im, det_tc, "cuda:0")                 # explicit tf32 opt-in
+            inter = set(map(tuple, got[:, :2])) & ws
+            assert len(inter) >= 0.97 * len(want), (seed, len(inter), len(want))
+            n_inter += len(inter)
+            n_ref += len(want)
+        # windowed path (validation extraction), top-2048, default precision of that path = tf32
         xy, sc, _, cnt = demo_match.detect_batch_device(config.default_test_args(sub_pixel=False), torch.from_numpy(im[None, :, :, :1].copy()).to("cuda:0"),
-                                                        det_tc, nms="windowed")
+                                                        d_auto, nms="windowed")
         wantw = pipeline.detect_windowed(detector_sd, im, 15, 15, 2048)
         gotw = set(map(tuple, xy[0, :int(cnt[0])].cpu().numpy().tolist()))
         ww = set(map(tuple, wantw[:, :2].astype(int).tolist()))
         assert len(gotw & ww) >= 0.99 * len(ww), (seed, len(gotw & ww), len(ww))
     assert n_inter >= 0.985 * n_ref, (n_inter, n_ref)
+    assert d_auto.resolve_precision("windowed") == "tf32" and d_auto.resolve_precision("greedy") == "fp32" \
+        and d_auto.resolve_precision() == "fp32" and det_tc.resolve_precision("greedy") == "tf32"
 
 
-def test_large_shapes_tf32_vs_fp32_path(det_tc):
-    """BASELINE.json configs[2] / [3] shapes (HPatches-like 900x1200 -> 960x1216 padded, 1024x1024): the tensor-core
-    path against the library's fp32 path (itself pinned to the oracle at 2e-5) -- tolerance of the north star,
-    per-image independence across the internal pass boundary, bit reproducibility."""
+def test_large_shapes_vs_reference_maps(det_tc):
+    """BASELINE.json configs[2] / [3] shapes against the REFERENCE's own score maps (tests/golden/r2_detector_large.npz:
+    900x1200 -> 960x1216 padded, 1024x1024, written by oracle/make_golden.py from /root/reference): tolerance of the
+    north star for the tensor-core path, 2e-5 for the fp32 path; per-image independence across the internal pass
+    boundary and bit reproducibility."""
     import balf_b200._capi as capi
+    g = load_golden("r2_detector_large.npz")
     d32 = copy.deepcopy(det_tc)
     d32.precision = "fp32"
-    for hp, wp, b in ((960, 1216, 3), (1024, 1024, 2)):
-        x = torch.rand(b, 3, hp, wp, generator=torch.Generator().manual_seed(hp))
+    for h, w, seeds in ((900, 1200, (1234, 1235)), (1024, 1024, (1234,))):
+        ims = np.stack([synth_u8(h, w, s)[:, :, :1] for s in seeds])
+        x, _ = capi.preprocess_u8(torch.from_numpy(ims).to("cuda:0"))
+        assert tuple(x.shape[2:]) == tuple(g["pad_shape_%dx%d_s%d" % (h, w, seeds[0])][:2])
         _, p_tc = run(det_tc, x)
         _, p_32 = run(d32, x)
-        np.testing.assert_allclose(p_tc.numpy(), p_32.numpy(), rtol=TF32_RTOL)
+        for i, s in enumerate(seeds):
+            key = "%dx%d_s%d" % (h, w, s)
+            for p, tol in ((p_tc, TF32_RTOL), (p_32, 2e-5)):
+                pi = p[i].numpy()
+                np.testing.assert_allclose(pi[::8, ::8], g["prob_sub8_" + key], rtol=tol)
+                np.testing.assert_allclose(pi[pi.shape[0] // 2 - 1], g["prob_row_" + key], rtol=tol)
+                assert abs(pi.astype(np.float64).sum() - g["prob_stats_" + key][0]) < (0.5 if tol > 1e-4 else 0.02)
         capi.debug_set(1, 1)                         # one image per internal pass
         try:
             _, p_one = run(det_tc, x)
