@@ -529,3 +529,46 @@ def box_nms_map(prob, size=4, iou=0.1, min_prob=0.015, keep_top_k=-1):
     with torch.cuda.device(p.device):
         _ok(_box_nms(_ptr(p), B, H, W, float(size), float(iou), float(min_prob), k, _ptr(out), _ptr(ws), nbytes, _stream(p.device)))
     return out
+
+
+# ------------------------------------------------------------------------------------------ NCCL gather
+_nccl_uid = _sig("balf_nccl_unique_id", c_int, _P)
+_nccl_create = _sig("balf_nccl_comm_create", c_int, _P, c_int, c_int, ctypes.POINTER(c_void_p))
+_nccl_destroy = _sig("balf_nccl_comm_destroy", c_int, _P)
+_gather_ws = _sig("balf_gather_workspace_bytes", c_size_t, c_int, c_int, c_int)
+_gather_kp = _sig("balf_gather_keypoints", c_int, _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, c_size_t, _P)
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (bytes); rank 0 creates it and the caller distributes it."""
+    buf = ctypes.create_string_buffer(128)
+    _ok(_nccl_uid(buf))
+    return buf.raw
+
+
+def nccl_comm_create(uid, world, rank, device):
+    comm = c_void_p()
+    with torch.cuda.device(device):
+        _ok(_nccl_create(ctypes.create_string_buffer(bytes(uid), 128), int(world), int(rank), ctypes.byref(comm)))
+    return comm
+
+
+def nccl_comm_destroy(comm):
+    _ok(_nccl_destroy(comm))
+
+
+def gather_keypoints(comm, world, xy, score, count):
+    """this rank's (xy int32 [B,K,2], score fp32 [B,K], count int32 [B]) -> the records of every rank, in rank order."""
+    _need_cuda(xy, "the keypoint records")
+    xy, score, count = xy.contiguous(), score.contiguous(), count.contiguous()
+    B, K, _ = xy.shape
+    dev = xy.device
+    xy_all = torch.empty(world * B, K, 2, dtype=torch.int32, device=dev)
+    sc_all = torch.empty(world * B, K, dtype=torch.float32, device=dev)
+    cn_all = torch.empty(world * B, dtype=torch.int32, device=dev)
+    nbytes = _gather_ws(world, B, K)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _ok(_gather_kp(comm, world, _ptr(xy), _ptr(score), _ptr(count), B, K, _ptr(xy_all), _ptr(sc_all), _ptr(cn_all), _ptr(ws),
+                       nbytes, _stream(dev)))
+    return xy_all, sc_all, cn_all

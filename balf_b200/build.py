@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in sources()]
     if force or jobs or _stale(LIB, objs):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                   "-Xcompiler", "-fPIC"])
+                                                   "-Xcompiler", "-fPIC", "-ldl"])
     return LIB
 
 

@@ -6,6 +6,8 @@ pipeline locally, and ONE collective gathers the fixed-size keypoint records.  T
 exchange inside the network (the squeeze-excite mean and the grid gate are per image).
 
 ``torch.distributed`` is the plumbing: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+``KeypointGather`` is the C-ABI form of the same collective (``balf_gather_keypoints`` on an ``ncclComm_t`` owned by the
+library's caller, include/balf_b200.h): the unique id travels through ``torch.distributed``, the data path does not.
 """
 import torch
 import torch.distributed as dist
@@ -46,6 +48,28 @@ def gather_keypoints(xy, score, count, group=None):
     out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)
     return unpack_records(out)
+
+
+class KeypointGather:
+    """NCCL all-gather of keypoint records through the C-ABI (``balf_gather_keypoints``).  Needs an initialised
+    ``torch.distributed`` group only to hand the 128-byte ncclUniqueId from rank 0 to the other ranks."""
+
+    def __init__(self, device, group=None):
+        from . import _capi
+        self._capi = _capi
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        uid = [_capi.nccl_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=group)
+        self.comm = _capi.nccl_comm_create(uid[0], self.world, self.rank, device)
+
+    def __call__(self, xy, score, count):
+        return self._capi.gather_keypoints(self.comm, self.world, xy, score, count)
+
+    def close(self):
+        if self.comm is not None:
+            self._capi.nccl_comm_destroy(self.comm)
+            self.comm = None
 
 
 def gather_matches(ids, n_matches, group=None):

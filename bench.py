@@ -53,6 +53,14 @@ def workload_name(a):
             % (a.batch, a.nms, K_FEATURES))
 
 
+def config_of(a):
+    """the `config` object of the JSON line -- identical for both arms (the reference arm runs the same workload one image
+    at a time, the reference's own batching)."""
+    return {"workload": workload_name(a), "batch_per_gpu": a.batch, "nms": a.nms, "k": K_FEATURES,
+            "padded": "512x640", "weights": "random-init torch.manual_seed(0)",
+            "l2": "no explicit flush: each step streams >2 GB of activations per GPU, far above the 126 MB L2"}
+
+
 def synth_batch(batch, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.randint(0, 256, (batch, H, W, 1), generator=g, dtype=torch.uint8)
@@ -113,21 +121,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_pipeline(a):
-    """-> callable(image index) running the reference algorithm (oracle port) on one image."""
-    from oracle import pipeline, postproc, detector as odet          # the CPU arm only
-    from balf_b200.model import get_model                             # weights only (same init as the reference)
-    torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in get_model.load_model(model_cfg()).state_dict().items()}
+def cpu_pipeline(a, nms=None, greedy_impl="python"):
+    """-> callable(image index) running the reference algorithm (oracle port) on one image.  Imports nothing of the
+    product: the weights are the oracle's own seeded replay of the reference constructors (oracle/weights.py)."""
+    from oracle import pipeline, postproc, weights                    # the CPU arm only
+    sd = weights.detector_state_dict(0)
     args = pipeline.default_args(sub_pixel=False)
     imgs = synth_batch(8, 1234).expand(8, H, W, 3).contiguous().numpy()
+    nms = nms or a.nms
+    greedy = postproc.greedy_nms                                       # the reference's Python loops (test_utils.py:130-168)
+    if greedy_impl == "c":
+        from oracle import postproc_c
+        greedy = postproc_c.greedy_nms
 
     def one(i):
         im = imgs[i % len(imgs)]
         score = pipeline.score_map(sd, im)
-        if a.nms == "windowed":
+        if nms == "windowed":
             return postproc.windowed_detect(score, args.border_size, args.nms_size, K_FEATURES)
-        return pipeline.detect_from_score_map(args, score)[0]
+        return pipeline.detect_from_score_map(args, score, nms=greedy)[0]
     return one
 
 
@@ -152,25 +164,26 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "nms": a.nms, "k": K_FEATURES},
+        "config": config_of(a),
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def cpu_baseline(a):
+def cpu_baseline(a, nms=None, greedy_impl="python", budget_s=10.0, max_images=32):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    one = cpu_pipeline(a)
+    one = cpu_pipeline(a, nms, greedy_impl)
     one(0)
     n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 32):
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < max_images):
         one(n)
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d images of the same workload, batch 1 each, %.1f s" % (n, dt)}
+            "sample": "%d images of the same workload (%s NMS%s), batch 1 each, %.1f s" %
+                      (n, nms or a.nms, ", greedy loop = %s port" % greedy_impl if (nms or a.nms) == "greedy" else "", dt)}
 
 
 # ------------------------------------------------------------------------------------------ roofline
@@ -253,57 +266,187 @@ def roofline_of(name, launches, total_ms, steps, images, pk):
     return out
 
 
-def extras(dev, pk):
-    """Secondary rows of the hot path (BASELINE.json configs[2] shapes), not part of `value`:
-    HardNet on 4096 patches and SMNN on 2048 x 2048 descriptors, device-resident, CUDA-event timed."""
+def cuda_timed(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def kernel_work_nms_greedy(images):
+    """greedy path: the score map is read once by the first (threshold) pass; later rounds touch alive pixels only."""
+    return images * (4 * H * W + 16 * K_FEATURES)
+
+
+def extras_greedy(a, dev, pk, det, args, u8):
+    """configs[1] with the demo path's NMS (greedy nms_fast, demo/demo_match.py:44-57): the same batch, device-timed, in the
+    default precision of that path (fp32-class) and with tf32 opted in; per-kernel times of the NMS stage and its HBM
+    fraction (algorithmic bytes: score map read once + 16 bytes per keypoint)."""
+    import copy
+    import balf_b200._capi as capi
+    from balf_b200.demo import demo_match
+    out = {}
+    for prec in ("auto", "tf32"):
+        d = copy.copy(det)
+        d.precision = prec
+        ms = cuda_timed(lambda: demo_match.detect_batch_device(args, u8, d, "greedy"), n=3 if prec == "auto" else 5)
+        out["detector_%s" % d.resolve_precision("greedy")] = {"ms_per_step": ms, "images_per_s": a.batch / (ms * 1e-3)}
+    with torch.inference_mode():
+        x, (top, left) = capi.preprocess_u8(u8)
+        prob = det(x, precision="tf32")["prob"]
+    capi.profile_enable(True)
+    capi.profile_report(reset=True)
+    n = 10
+    for _ in range(n):
+        capi.greedy_nms_topk(prob, K_FEATURES, border=args.border_size, thr=args.heatmap_confidence_threshold,
+                             radius=args.nms_size, subpixel_ps=0, crop=(top, left, H, W))
+    prof = capi.profile_report(reset=True)
+    capi.profile_enable(False)
+    stage_ms = sum(v[1] for k, v in prof.items() if k.startswith("nms_")) / n
+    nbytes = kernel_work_nms_greedy(a.batch)
+    out["nms_stage"] = {"ms": stage_ms, "kernels": {k: v[1] / n for k, v in prof.items() if k.startswith("nms_")},
+                        "bound": "hbm", "achieved": nbytes / (stage_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": nbytes / (stage_ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"]}
+    return out
+
+
+def extras_pair(dev, det, n_pairs=4):
+    """BASELINE.json configs[2]: HPatches-shaped synthetic pairs 1200x900 through demo_match.extract_matches end to end
+    (HOST uint8 images in, matched point arrays out): detector x2, greedy NMS + sub-pixel, level-1 patches, HardNet x2,
+    SMNN.  pairs/s over `n_pairs` pairs after one warm-up pair."""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
+    torch.manual_seed(0)
+    hn = HardNet().eval().to(dev)
+    args = config.default_test_args()
+    rng = np.random.default_rng(0)
+    pairs = []
+    for i in range(n_pairs + 1):
+        g = torch.Generator().manual_seed(1234 + i)
+        a_ = torch.randint(0, 256, (900, 1200, 1), generator=g, dtype=torch.uint8).expand(900, 1200, 3).contiguous().numpy()
+        b_ = np.clip(a_.astype(np.int64) + rng.integers(-2, 3, (900, 1200, 1)), 0, 255).astype(np.uint8)
+        pairs.append((a_, a_[..., 0].copy(), b_, b_[..., 0].copy()))
+    res = {}
+    for prec in ("auto", "tf32"):
+        import copy
+        d = copy.copy(det)
+        d.precision = prec
+        demo_match.extract_matches(args, *pairs[0], d, hn, dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nm = 0
+        for pr in pairs[1:]:
+            p1, _ = demo_match.extract_matches(args, *pr, d, hn, dev)
+            nm += len(p1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res["detector_%s" % d.resolve_precision("greedy")] = {"pairs_per_s": n_pairs / dt, "ms_per_pair": dt / n_pairs * 1e3,
+                                                                 "matches_per_pair": nm / n_pairs}
+    res["workload"] = "configs[2]: %d synthetic pairs 1200x900 (second image = first + noise), extract_matches, host buffers" % n_pairs
+    res["h2d_bytes_per_pair"] = 2 * (900 * 1200 * 3 + 900 * 1200)
+    return res
+
+
+def extras_cfg3(dev, det, world, rank, gather, total=1024, chunk=64):
+    """BASELINE.json configs[3]: `total` synthetic 1024x1024 images STRONG-scaled over the ranks (rank r takes a contiguous
+    share), detector + windowed NMS + top-2048, keypoint records all-gathered per chunk through the C-ABI NCCL entry."""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.sharding import shard_range
+    args = config.default_test_args(sub_pixel=False, num_features=K_FEATURES)
+    lo, hi = shard_range(total, rank, world)
+    n_local = hi - lo
+    g = torch.Generator().manual_seed(1234 + rank)
+    u8 = torch.randint(0, 256, (min(n_local, chunk), 1024, 1024, 1), generator=g, dtype=torch.uint8).to(dev)
+    e_g0, e_g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run_pass(timed):
+        gms = 0.0
+        done = 0
+        while done < n_local:
+            b = min(chunk, n_local - done)
+            xy, sc, _, cnt = demo_match.detect_batch_device(args, u8[:b], det, "windowed")
+            if gather is not None and b == chunk:
+                if timed:
+                    e_g0.record()
+                gather(xy, sc, cnt)
+                if timed:
+                    e_g1.record()
+                    torch.cuda.synchronize()
+                    gms += e_g0.elapsed_time(e_g1)
+            done += b
+        return gms
+    run_pass(False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gms = run_pass(True)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), gms, n_local
+
+
+def extras_cfg4(dev, det, world, rank, total=256, chunk=32):
+    """BASELINE.json configs[4]: 3-level pyramid (0.7x), 8192 keypoints per image, `total` 1024x1024 images over the ranks."""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.sharding import shard_range
+    margs = config.default_test_args(sub_pixel=False, num_features=8192)
+    lo, hi = shard_range(total, rank, world)
+    n_local = hi - lo
+    g = torch.Generator().manual_seed(4321 + rank)
+    u8 = torch.randint(0, 256, (min(n_local, chunk), 1024, 1024, 1), generator=g, dtype=torch.uint8).to(dev)
+
+    def run_pass():
+        done = 0
+        while done < n_local:
+            b = min(chunk, n_local - done)
+            demo_match.detect_multiscale_batch_device(margs, u8[:b], det, scale=0.7, levels=3)
+            done += b
+    run_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), n_local
+
+
+def extras(dev, pk, det):
+    """Secondary rows of the hot path, not part of `value`: HardNet on 4096 patches, SMNN on
+    2048 x 2048 descriptors, patch sampling, device-resident, CUDA-event timed."""
     import balf_b200._capi as capi
     from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
     torch.manual_seed(0)
     hn = HardNet().eval().to(dev)
     x = torch.rand(4096, 1, 32, 32, device=dev)
-
-    def timed(fn, n=5):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
-
-    from balf_b200.configs import config
-    from balf_b200.demo import demo_match
-    from balf_b200.model import get_model
-    torch.manual_seed(0)
-    det = get_model.load_model(model_cfg()).eval().to(dev)       # outside inference_mode: its weight cache reads ._version
     out = {}
     with torch.inference_mode():
-        ms = timed(lambda: hn(x))
+        ms = cuda_timed(lambda: hn(x))
         tf = 4096 * 78.184e6 / (ms * 1e-3) / 1e12
         out["hardnet"] = {"patches": 4096, "ms": ms, "patches_per_s": 4096 / (ms * 1e-3), "tflops": tf, "dtype": hn.precision,
                           "frac_of_tf32_peak": tf / (pk["tensor"] / 2), "peak": "half of the bf16 figure (%s)" % pk["src"]}
         d1 = torch.nn.functional.normalize(torch.randn(2048, 128, device=dev), dim=1)
         d2 = torch.nn.functional.normalize(d1 + 0.05 * torch.randn(2048, 128, device=dev), dim=1)
-        ms = timed(lambda: capi.match_smnn(d1, d2, 0.99))
+        ms = cuda_timed(lambda: capi.match_smnn(d1, d2, 0.99))
         out["smnn"] = {"n1": 2048, "n2": 2048, "ms": ms, "pairs_per_s": 2048 * 2048 / (ms * 1e-3),
                        "note": "includes the device->host read of the match count"}
         # F1: 2048 patches of one 900 x 1200 image (level-1 pyramid build + bilinear gather); algorithmic bytes =
         # source read + level write/read + patches written (SURVEY.md 8d)
         gray = torch.randint(0, 256, (900, 1200), dtype=torch.uint8, device=dev)
         kp = torch.stack([torch.rand(2048, device=dev) * 1100 + 50, torch.rand(2048, device=dev) * 800 + 50], 1)
-        ms = timed(lambda: capi.extract_patches(gray, kp, 60.0, 32))
+        ms = cuda_timed(lambda: capi.extract_patches(gray, kp, 60.0, 32))
         nbytes = 900 * 1200 + 2 * 4 * 450 * 600 + 4096 * 2048
         out["patches"] = {"keypoints": 2048, "image": "900x1200", "ms": ms, "bound": "hbm", "achieved_GBs": nbytes / (ms * 1e-3) / 1e9,
                           "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
-        # BASELINE.json configs[4] in miniature: 3-level pyramid (0.7x), 8192 keypoints per image, 8 x 1024 x 1024
-        u8 = torch.randint(0, 256, (8, 1024, 1024, 1), dtype=torch.uint8, device=dev)
-        margs = config.default_test_args(sub_pixel=False, num_features=8192)
-        ms = timed(lambda: demo_match.detect_multiscale_batch_device(margs, u8, det, scale=0.7, levels=3), n=3)
-        out["multiscale"] = {"workload": "8 x 1024x1024, 3 levels x 0.7, windowed NMS, top-8192 merged", "ms": ms,
-                             "images_per_s": 8 / (ms * 1e-3)}
     return out
 
 
@@ -330,7 +473,7 @@ def main():
     from balf_b200.configs import config
     from balf_b200.demo import demo_match
     from balf_b200.model import get_model
-    from balf_b200.sharding import gather_keypoints
+    from balf_b200.sharding import KeypointGather
 
     if a.chunk:
         capi.debug_set(1, a.chunk)
@@ -341,11 +484,12 @@ def main():
     args = config.default_test_args(sub_pixel=False, num_features=K_FEATURES)
     host = synth_batch(a.batch, 1234 + rank).pin_memory()
     u8 = host.to(dev)
+    gather = KeypointGather(dev) if world > 1 else None           # the C-ABI collective (balf_gather_keypoints on an ncclComm_t)
 
     def step_device():
         xy, sc, _, cnt = demo_match.detect_batch_device(args, u8, det, a.nms)
-        if world > 1:
-            return gather_keypoints(xy, sc, cnt)
+        if gather is not None:
+            return gather(xy, sc, cnt)
         return xy, sc, cnt
 
     def barrier():
@@ -385,7 +529,7 @@ def main():
         prev = cur
     res = pipe.result(prev)
     e2e_passes = []
-    for _ in range(2):                  # two passes of K steps; the faster one is reported, both are listed
+    for _ in range(3):                  # three passes of K steps; the MEDIAN is reported, all are listed
         barrier()
         t0 = time.perf_counter()
         prev = None
@@ -397,14 +541,20 @@ def main():
         res = pipe.result(prev)
         torch.cuda.synchronize()
         e2e_passes.append((time.perf_counter() - t0) * 1e3)
-    t_e2e = min(e2e_passes)
+    t_e2e = float(np.median(e2e_passes))
     d2h = sum(int(r.nbytes) for r in res)
 
-    t = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
+    # the other BASELINE.json configs (every rank takes part: cfg3 / cfg4 are sharded over the ranks)
+    c3_ms, c3_gather_ms, c3_local = extras_cfg3(dev, det, world, rank, gather)
+    c4_ms, c4_local = extras_cfg4(dev, det, world, rank)
+
+    t = torch.tensor([ms, t_e2e, c3_ms, c3_gather_ms, c4_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, t_e2e = float(t[0]), float(t[1])
+    ms, t_e2e, c3_ms, c3_gather_ms, c4_ms = (float(v) for v in t)
     if rank != 0:
+        if gather is not None:
+            gather.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -416,33 +566,53 @@ def main():
         r = roofline_of(k, v[0], v[1], a.steps, a.batch, pk)
         kernels[k] = {"launches_per_step": v[0] / a.steps, "ms_per_step": v[1] / a.steps, "share": v[1] / total_kernel_ms,
                       "bound": r["bound"], "achieved": r.get("achieved"), "unit": r.get("unit"), "frac": r.get("frac")}
-    top = max(prof.items(), key=lambda kv: kv[1][1])
+    top = max(((k, v) for k, v in prof.items() if k.startswith(("det_", "nms_"))), key=lambda kv: kv[1][1])
     roof = roofline_of(top[0], top[1][0], top[1][1], a.steps, a.batch, pk)
-    nms_name = "nms_windowed" if a.nms == "windowed" else "nms_greedy_rounds"
-    roof_nms = roofline_of(nms_name, prof[nms_name][0], prof[nms_name][1], a.steps, a.batch, pk) if nms_name in prof else None
+    # the NMS + top-k stage the metric names: both kernels of the windowed path against the stage's algorithmic bytes
+    nms_keys = [k for k in prof if k.startswith("nms_")]
+    roof_nms = None
+    if nms_keys:
+        stage_ms = sum(prof[k][1] for k in nms_keys) / a.steps
+        nbytes = a.batch * (4 * H * W + 16 * K_FEATURES)
+        roof_nms = {"kernels": {k: prof[k][1] / a.steps for k in nms_keys}, "bound": "hbm", "stage_ms": stage_ms,
+                    "algorithmic_bytes": nbytes, "achieved": nbytes / (stage_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": nbytes / (stage_ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"],
+                    "traffic": sum(filter(None, (ncu_traffic(k) for k in nms_keys))) or None}
     det_ms = sum(v[1] for k, v in prof.items() if k.startswith("det_")) / a.steps
+    det_tf = a.batch * 512 * 640 * FLOP_PER_PADDED_PIXEL / (det_ms * 1e-3) / 1e12 if det_ms else None
     line = {
         "metric": METRIC, "value": images * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": det.precision, "data": "synthetic",
-        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "nms": a.nms, "k": K_FEATURES,
-                   "padded": "512x640", "weights": "random-init torch.manual_seed(0)",
-                   "l2": "no explicit flush: each step streams >2 GB of activations per GPU, far above the 126 MB L2"},
+        "scaling": "weak", "vs_baseline": None, "dtype": det.resolve_precision(a.nms), "data": "synthetic",
+        "config": config_of(a),
         "clocks": clocks,
         "e2e": {"value": images * a.steps / (t_e2e * 1e-3), "unit": "images/s", "passes_ms": [round(x, 3) for x in e2e_passes],
-                "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": d2h},
+                "reported": "median of the passes", "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": roof,
         "roofline_nms": roof_nms,
-        "detector": {"ms_per_step": det_ms, "tflops": a.batch * 512 * 640 * FLOP_PER_PADDED_PIXEL / (det_ms * 1e-3) / 1e12
-                     if det_ms else None},
+        "detector": {"ms_per_step": det_ms, "tflops": det_tf,
+                     "frac_of_tf32_peak": det_tf / (pk["tensor"] / 2) if det_tf else None, "peak_source": pk["src"]},
         "kernels": kernels,
+        "cfg3": {"workload": "configs[3]: 1024 synthetic 1024x1024 images strong-scaled over %d rank(s), detector + windowed NMS + "
+                             "top-2048, records all-gathered per 64-image chunk (balf_gather_keypoints, NCCL)" % world,
+                 "images_per_s": 1024 / (c3_ms * 1e-3), "ms": c3_ms, "images_per_rank": c3_local,
+                 "gather_ms_total": c3_gather_ms if world > 1 else None},
+        "cfg4": {"workload": "configs[4]: 256 synthetic 1024x1024 images over %d rank(s), 3-level pyramid (0.7x), windowed NMS, "
+                             "top-8192 merged" % world, "images_per_s": 256 / (c4_ms * 1e-3), "ms": c4_ms, "images_per_rank": c4_local},
     }
     if world == 1:
-        line["extras"] = extras(dev, pk)
+        line["extras"] = extras(dev, pk, det)
+        line["greedy"] = extras_greedy(a, dev, pk, det, config.default_test_args(sub_pixel=False, num_features=K_FEATURES), u8)
+        line["pair_cfg2"] = extras_pair(dev, det)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a)
+        # the reference's shipped demo path (greedy nms_fast in Python loops) beside the greedy GPU number
+        line["greedy"]["cpu_baseline"] = cpu_baseline(a, nms="greedy", greedy_impl="python", budget_s=6.0, max_images=4)
+        line["greedy"]["cpu_baseline_c_loop"] = cpu_baseline(a, nms="greedy", greedy_impl="c", budget_s=4.0, max_images=8)
     print(json.dumps(line))
+    if gather is not None:
+        gather.close()
     if world > 1:
         dist.destroy_process_group()
 

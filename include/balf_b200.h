@@ -246,6 +246,22 @@ BALF_API int balf_resize_repeatability(const double* kp, int n1, const double* w
                                        int src_w, int dst_h, int dst_w, int keep_k, double dist_thresh, double* out6,
                                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * the one collective of the sharded path.  No reference counterpart (the reference is single-device,
+ * demo/demo_match.py:29): image batches are partitioned over the ranks, every rank runs the whole pipeline on its shard, and
+ * the fixed-size keypoint records are all-gathered over NCCL (NVLink 5 / NVSwitch).
+ * `comm` is an ncclComm_t; NCCL is bound at run time from the libnccl.so.2 the process already uses.  The helpers create
+ * one from a 128-byte ncclUniqueId (host) that rank 0 obtains and the caller distributes by any means.
+ * balf_gather_keypoints: xy int32 [B_local,K,2], score fp32 [B_local,K], count int32 [B_local] of this rank ->
+ *     xy_all [world*B_local,K,2], score_all [world*B_local,K], count_all [world*B_local] in rank order, on every rank. */
+BALF_API int balf_nccl_unique_id(void* id_host_128);
+BALF_API int balf_nccl_comm_create(const void* id_host_128, int world, int rank, void** comm_out);
+BALF_API int balf_nccl_comm_destroy(void* comm);
+BALF_API size_t balf_gather_workspace_bytes(int world, int B_local, int K);
+BALF_API int balf_gather_keypoints(void* comm, int world, const int32_t* xy, const float* score, const int32_t* count, int B_local,
+                                   int K, int32_t* xy_all, float* score_all, int32_t* count_all, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,8 +16,11 @@ pytestmark = pytest.mark.gpu
 
 PATCH_ATOL = 1e-4        # sample coordinates are fp32 at magnitudes up to ~600 px (ulp 6e-5 px) and noise images have
                          # unit gradients between neighbouring pixels; typical error is < 1e-6 (checked via the mean)
-DESC_ATOL = 2e-5         # fp32 conv summation order over K <= 8192, unit-norm 128-d outputs
-DESC_ATOL_TC = 2e-3      # tensor-core (tf32 operand) HardNet path
+# Descriptor tolerances = 2x the error measured against the REFERENCE's own output on 2048 seeded patches
+# (tests/golden/r2_hardnet2048.npz; scripts/measure_parity.py on B200): fp32 FFMA path max |err| 1.0e-6 (mean 1.0e-7); tensor-core
+# path (tf32 operands, fp32 accumulate) max |err| 3.1e-4 (mean 5.2e-5) on unit-norm 128-d vectors (typical component 0.09).
+DESC_ATOL = 5e-6         # fp32 path: the patch-sampled inputs of the demo chain have a wider dynamic range than rand() patches
+DESC_ATOL_TC = 6e-4      # tensor-core (tf32 operand) HardNet path
 
 
 def dev():
@@ -87,6 +90,21 @@ def test_hardnet_golden(hardnet):
     tol = DESC_ATOL if getattr(hn, "precision", "fp32") == "fp32" else DESC_ATOL_TC
     np.testing.assert_allclose(got, g["out"], atol=tol, rtol=0)                     # the reference's own output
     np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+
+
+def test_hardnet_reference_golden_2048(hardnet):
+    """the reference's own HardNet output on 2048 seeded patches (two internal passes of the chunked reference loop)"""
+    want = load_golden("r2_hardnet2048.npz")["out"]
+    x = torch.rand(2048, 1, 32, 32, generator=torch.Generator().manual_seed(4321))
+    hn = hardnet.to(dev())
+    with torch.inference_mode():
+        got = hn(x.to(dev())).cpu().numpy()
+    tc = getattr(hn, "precision", "fp32") != "fp32"
+    err = np.abs(got - want)
+    assert err.max() <= (DESC_ATOL_TC if tc else 2.5e-6), err.max()
+    assert err.mean() <= (1.1e-4 if tc else 2.5e-7), err.mean()
+    cos = (got * want).sum(1)
+    assert cos.min() > 1 - 2e-6
 
 
 @pytest.mark.parametrize("n", [1, 7, 1000, 1337])
@@ -182,4 +200,5 @@ def test_extract_features_and_matches(detector, detector_sd, hardnet):
     got = set(map(tuple, np.round(np.concatenate([p1, p2], 1), 2)))
     want = set(map(tuple, np.round(np.concatenate([w1, w2], 1), 2)))
     assert len(want) > 20
-    assert len(got & want) / len(want) >= 0.9
+    # measured 1.000 / 1.000 (scripts/measure_parity.py): the demo path runs the detector in its fp32-class default
+    assert len(got & want) / len(want) >= 0.99 and len(got & want) / len(got) >= 0.99

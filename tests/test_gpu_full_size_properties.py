@@ -147,3 +147,39 @@ def test_config3_pair_properties(detector):
     p1, p2 = demo_match.extract_matches(args, rgb1, g1, rgb2, g2, det, hn, DEV)
     assert p1.shape == p2.shape == (len(ids), 2)
     assert np.median(np.abs(p1 - p2).max(1)) < 1.0                              # matched keypoints coincide (same scene)
+
+
+def test_config3_pair_vs_reference_and_oracle(detector):
+    """BASELINE.json configs[2] against the reference and the CPU oracle at full size (900x1200, seeds 1234 / 1235):
+    (i) demo_match.detect against the REFERENCE's own detect() output (tests/golden/r2_detector_large.npz, 2048 of ~2900
+    greedy survivors: the top-k cut binds), (ii) the whole pair pipeline -- detector, greedy NMS + sub-pixel, level-1
+    patches, HardNet, SMNN -- against oracle.pipeline.extract_matches on the same images (measured recall = precision =
+    1.000 with the default precisions, scripts/measure_parity.py)."""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
+    from conftest import load_golden
+    from oracle import pipeline, weights
+    det = copy.deepcopy(detector).to(DEV).eval()
+    torch.manual_seed(0)
+    hn = HardNet().eval().to(DEV)
+    g = load_golden("r2_detector_large.npz")
+    args0 = config.default_test_args(sub_pixel=False)
+    for seed in (1234, 1235):
+        im = synth_u8(900, 1200, seed)
+        got = demo_match.detect(args0, im, det, DEV)
+        ref = g["detect_900x1200_s%d" % seed]
+        assert got.shape == ref.shape == (2048, 3)
+        inter = set(map(tuple, got[:, :2])) & set(map(tuple, ref[:, :2]))
+        assert len(inter) >= 0.99 * len(ref), (seed, len(inter))
+    args = config.default_test_args()
+    rgb1 = synth_u8(900, 1200, 1234)
+    noise = np.random.default_rng(5).integers(-2, 3, rgb1.shape[:2])[..., None]
+    rgb2 = np.clip(rgb1.astype(np.int64) + noise, 0, 255).astype(np.uint8)
+    g1, g2 = rgb1[..., 0].copy(), rgb2[..., 0].copy()
+    p1, p2 = demo_match.extract_matches(args, rgb1, g1, rgb2, g2, det, hn, DEV)
+    w1, w2 = pipeline.extract_matches(args, weights.detector_state_dict(0), weights.hardnet_state_dict(0), rgb1, g1, rgb2, g2)
+    got = set(map(tuple, np.round(np.concatenate([p1, p2], 1), 2)))
+    want = set(map(tuple, np.round(np.concatenate([w1, w2], 1), 2)))
+    assert len(want) > 1500
+    assert len(got & want) >= 0.99 * len(want) and len(got & want) >= 0.99 * len(got), (len(got), len(want), len(got & want))
