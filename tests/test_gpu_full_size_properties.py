@@ -21,11 +21,11 @@ def batch():
     return torch.from_numpy(np.stack([synth_u8(H, W, 1000 + i)[:, :, :1] for i in range(B)]))
 
 
-def _score_maps(det, u8):
+def _score_maps(det, u8, nms="windowed"):
     import balf_b200._capi as capi
     x, (top, left) = capi.preprocess_u8(u8)
     with torch.inference_mode():
-        prob = det(x)["prob"]
+        prob = det(x, precision=det.resolve_precision(nms))["prob"]      # the arithmetic detect_batch_device(nms) runs in
     return prob[:, top:top + H, left:left + W].contiguous()
 
 
@@ -68,7 +68,7 @@ def test_greedy_full_batch_properties(detector, batch):
     args = config.default_test_args(sub_pixel=False, num_features=K)
     u8 = batch[:16].to(DEV)
     xy, sc, _, cnt = demo_match.detect_batch_device(args, u8, det, "greedy")
-    prob = _score_maps(det, u8)
+    prob = _score_maps(det, u8, "greedy")
     b, r, thr = args.border_size, args.nms_size, np.float32(args.heatmap_confidence_threshold)
     for i in range(16):
         n = int(cnt[i])
