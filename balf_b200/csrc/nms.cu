@@ -529,8 +529,10 @@ __global__ void __launch_bounds__(256) greedy_nms_kernel(NmsWs ws, int H, int W,
 struct CellWs {
     uint32_t* alive;    // [B][cells][8]   bit ly * 16 + lx of cell pixel (ly, lx)
     u64* cmax;          // [B][cells]      maximum alive key, 0 = none
+    u64* kept;          // [B][cells]      the cell's kept key (at most one per cell), 0 = none; compacted into the key list at the end
     int* dirty;         // [B][cells]
     int cx, cy;         // cells per row / column
+    int vec_ok;         // S = 16 and 16-byte aligned rows: interior cells of the first pass use 128-bit loads
 };
 __device__ __forceinline__ u64 warp_max_u64(u64 v) {
 #pragma unroll
@@ -538,16 +540,12 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     return v;
 }
 // this lane's 8 pixels of a cell: row ly = lane >> 1, columns (lane & 1) * 8 .. + 7
-// (re)compute the maximum alive key of cell c; init: alive = masked score >= thr
+// (re)compute the maximum alive key of cell c (one warp); init: alive = masked score >= thr
 __device__ __forceinline__ void cell_refresh(const MapView& mv, const CellWs& cw, const Footprint& f, int b, int c, bool init,
                                              float thr) {
     const int lane = threadIdx.x & 31;
     const size_t cell = (size_t)b * cw.cx * cw.cy + c;
-    if (!init) {
-        if (!cw.dirty[cell]) return;                 // warp-uniform
-        __syncwarp();
-        if (lane == 0) cw.dirty[cell] = 0;
-    }
+    if (!init && lane == 0) cw.dirty[cell] = 0;
     const int cyi = c / cw.cx, cxi = c - cyi * cw.cx;
     const int ly = lane >> 1, lx0 = (lane & 1) * 8;
     const int y = cyi * f.S + ly;
@@ -556,7 +554,23 @@ __device__ __forceinline__ void cell_refresh(const MapView& mv, const CellWs& cw
     uint32_t bits = init ? 0xFFu : (__shfl_sync(0xffffffffu, word, ly >> 1) >> ((ly & 1) * 16 + lx0)) & 0xFFu;
     u64 best = 0;
     uint32_t mine = 0;
-    if (ly < f.S && y < mv.H && bits) {
+    // first pass, cells that lie inside the border-masked interior: two 128-bit loads per lane, no per-pixel tests
+    const bool interior = init && cw.vec_ok && cyi * 16 >= mv.border && cyi * 16 + 16 <= mv.H - mv.border &&
+                          cxi * 16 >= mv.border && cxi * 16 + 16 <= mv.W - mv.border;
+    if (interior) {
+        const float4* src = reinterpret_cast<const float4*>(mv.score + ((size_t)b * mv.Hs + mv.top + y) * mv.Ws + mv.left + cxi * 16 + lx0);
+        const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+        const float sc8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const uint32_t r0 = (uint32_t)(y * mv.W + cxi * 16 + lx0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (sc8[j] >= thr) {
+                mine |= 1u << j;
+                const u64 k = make_key(sc8[j], r0 + j);
+                best = k > best ? k : best;
+            }
+        }
+    } else if (ly < f.S && y < mv.H && bits) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int lx = lx0 + j, x = cxi * f.S + lx;
@@ -579,35 +593,46 @@ __device__ __forceinline__ void cell_refresh(const MapView& mv, const CellWs& cw
     }
     if (lane == 0) cw.cmax[cell] = best;
 }
-// decide the maximum of cell c; returns true when it was kept
-__device__ __forceinline__ bool cell_decide(const MapView& mv, const CellWs& cw, const Footprint& f, const NmsWs& ws, int b, int c) {
+// one THREAD: can the maximum of cell c be kept?  0 = no (empty cell, or a larger neighbour maximum lies inside its footprint);
+// otherwise 1 | (mask of the neighbours whose larger maximum lies outside the footprint: their alive pixels must be scanned) << 1
+__device__ __forceinline__ uint32_t cell_classify(const CellWs& cw, const Footprint& f, int W, int b, int c) {
+    const size_t cell0 = (size_t)b * cw.cx * cw.cy;
+    const u64 p = cw.cmax[cell0 + c];
+    if (p == 0ull) return 0u;
+    const int cyi = c / cw.cx, cxi = c - cyi * cw.cx;
+    const int pr = (int)key_raster(p), py = pr / W, px = pr - py * W;
+    u64 m[9];
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {
+        const int ny = cyi + n / 3 - 1, nx = cxi + n % 3 - 1;
+        m[n] = (n != 4 && ny >= 0 && ny < cw.cy && nx >= 0 && nx < cw.cx) ? cw.cmax[cell0 + ny * cw.cx + nx] : 0ull;
+    }
+    uint32_t slow = 0;
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {
+        if (m[n] > p) {
+            const int qr = (int)key_raster(m[n]), qy = qr / W, qx = qr - qy * W;
+            if (fp_inside(f, qy - py, qx - px)) return 0u;
+            slow |= 1u << n;
+        }
+    }
+    return 1u | (slow << 1);
+}
+// one WARP: scan the flagged neighbours for an alive pixel with a larger key inside the footprint; none -> keep the cell maximum
+// and clear its footprint
+__device__ __forceinline__ void cell_keep(const MapView& mv, const CellWs& cw, const Footprint& f, const NmsWs& ws, int b, int c,
+                                          uint32_t slow) {
     const int lane = threadIdx.x & 31;
     const size_t cell0 = (size_t)b * cw.cx * cw.cy;
     const u64 p = cw.cmax[cell0 + c];
-    if (p == 0ull) return false;
     const int cyi = c / cw.cx, cxi = c - cyi * cw.cx;
     const int pr = (int)key_raster(p), py = pr / mv.W, px = pr - py * mv.W;
-    bool fast = false, slow = false;
-    int ncell = -1;
-    if (lane < 9 && lane != 4) {
-        const int ny = cyi + lane / 3 - 1, nx = cxi + lane % 3 - 1;
-        if (ny >= 0 && ny < cw.cy && nx >= 0 && nx < cw.cx) {
-            ncell = ny * cw.cx + nx;
-            const u64 m = cw.cmax[cell0 + ncell];
-            if (m > p) {
-                const int qr = (int)key_raster(m), qy = qr / mv.W, qx = qr - qy * mv.W;
-                if (fp_inside(f, qy - py, qx - px)) fast = true; else slow = true;
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, fast)) return false;
-    unsigned todo = __ballot_sync(0xffffffffu, slow);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int nc = __shfl_sync(0xffffffffu, ncell, src);
-        const int ny = nc / cw.cx, nx = nc - ny * cw.cx;
-        uint32_t word = lane < 8 ? cw.alive[(cell0 + nc) * 8 + lane] : 0u;
+    while (slow) {
+        const int n = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const int ny = cyi + n / 3 - 1, nx = cxi + n % 3 - 1;
+        const size_t nc = cell0 + (size_t)ny * cw.cx + nx;
+        uint32_t word = lane < 8 ? cw.alive[nc * 8 + lane] : 0u;
         const int ly = lane >> 1, lx0 = (lane & 1) * 8, y = ny * f.S + ly;
         const uint32_t bits = (__shfl_sync(0xffffffffu, word, ly >> 1) >> ((ly & 1) * 16 + lx0)) & 0xFFu;
         bool hit = false;
@@ -622,13 +647,10 @@ __device__ __forceinline__ bool cell_decide(const MapView& mv, const CellWs& cw,
                 }
             }
         }
-        if (__any_sync(0xffffffffu, hit)) return false;
+        if (__any_sync(0xffffffffu, hit)) return;
     }
-    // kept
-    if (lane == 0) {
-        const unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
-        if (slot < ws.cap) ws.keys[(size_t)b * ws.cap + slot] = p; else atomicOr(ws.flags + b, 1);
-    }
+    if (lane == 0) cw.kept[cell0 + c] = p;             // no atomics: the slot is the cell (same-address atomics on the image's
+                                                       // counter serialised the ~350 keeps of a first round)
     for (int t = lane; t < 72; t += 32) {
         const int n = t >> 3, j = t & 7;
         const int ny = cyi + n / 3 - 1, nx = cxi + n % 3 - 1;
@@ -649,24 +671,63 @@ __device__ __forceinline__ bool cell_decide(const MapView& mv, const CellWs& cw,
             cw.dirty[nc] = 1;
         }
     }
-    return true;
+}
+// a warp takes kCpw consecutive cells [base, base + kCpw) of the flattened (image, cell) range: the cheap per-cell tests run
+// one thread per cell (independent load chains in flight), the heavy steps (about one cell in five in the first round) run one
+// warp per cell; kCpw = 8 spreads those over every warp of the grid (32 measured 1.5x slower: ten serial keeps per warp)
+constexpr int kCpw = 8;
+__device__ __forceinline__ void cells_refresh32(const MapView& mv, const CellWs& cw, const Footprint& f, int base, int total, int nc) {
+    const int lane = threadIdx.x & 31, i = base + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, lane < kCpw && i < total && cw.dirty[i] != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int ci = base + src, b = ci / nc;
+        cell_refresh(mv, cw, f, b, ci - b * nc, false, 0.f);
+    }
+}
+__device__ __forceinline__ void cells_decide32(const MapView& mv, const CellWs& cw, const Footprint& f, const NmsWs& ws, int base,
+                                               int total, int nc) {
+    const int lane = threadIdx.x & 31, i = base + lane;
+    uint32_t cls = 0;
+    if (lane < kCpw && i < total) { const int b = i / nc; cls = cell_classify(cw, f, mv.W, b, i - b * nc); }
+    unsigned todo = __ballot_sync(0xffffffffu, cls != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t slow = __shfl_sync(0xffffffffu, cls, src) >> 1;
+        const int ci = base + src, b = ci / nc;
+        cell_keep(mv, cw, f, ws, b, ci - b * nc, slow);
+    }
 }
 
-__global__ void __launch_bounds__(256) greedy_cells_refresh_kernel(MapView mv, CellWs cw, Footprint f, int init, float thr) {
+// persistent grids: a few CTAs per SM walk all cells of the batch (launching one CTA per eight cells cost ~25 us per pass in
+// CTA scheduling alone, ten times the work of a late round)
+__global__ void __launch_bounds__(256) greedy_cells_init_kernel(MapView mv, CellWs cw, Footprint f, float thr, int B) {
     __shared__ Footprint fs;
     if (threadIdx.x == 0) fs = f;
     __syncthreads();
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
-    if (c >= cw.cx * cw.cy) return;
-    cell_refresh(mv, cw, fs, b, c, init != 0, thr);
+    const int nc = cw.cx * cw.cy, total = nc * B;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += gridDim.x * 8) {
+        const int b = i / nc;
+        cell_refresh(mv, cw, fs, b, i - b * nc, true, thr);
+    }
 }
-__global__ void __launch_bounds__(256) greedy_cells_decide_kernel(MapView mv, CellWs cw, Footprint f, NmsWs ws) {
+__global__ void __launch_bounds__(256) greedy_cells_refresh_kernel(MapView mv, CellWs cw, Footprint f, int B) {
     __shared__ Footprint fs;
     if (threadIdx.x == 0) fs = f;
     __syncthreads();
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
-    if (c >= cw.cx * cw.cy) return;
-    cell_decide(mv, cw, fs, ws, b, c);
+    const int nc = cw.cx * cw.cy, total = nc * B;
+    for (int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kCpw; base < total; base += gridDim.x * 8 * kCpw)
+        cells_refresh32(mv, cw, fs, base, total, nc);
+}
+__global__ void __launch_bounds__(256) greedy_cells_decide_kernel(MapView mv, CellWs cw, Footprint f, NmsWs ws, int B) {
+    __shared__ Footprint fs;
+    if (threadIdx.x == 0) fs = f;
+    __syncthreads();
+    const int nc = cw.cx * cw.cy, total = nc * B;
+    for (int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kCpw; base < total; base += gridDim.x * 8 * kCpw)
+        cells_decide32(mv, cw, fs, ws, base, total, nc);
 }
 // one CTA per image: runs rounds until no cell has an alive pixel (returns at once when the multi-CTA rounds finished the job)
 __global__ void __launch_bounds__(1024) greedy_cells_finish_kernel(MapView mv, CellWs cw, Footprint f, NmsWs ws) {
@@ -674,28 +735,35 @@ __global__ void __launch_bounds__(1024) greedy_cells_finish_kernel(MapView mv, C
     __shared__ int alive_cells;
     if (threadIdx.x == 0) fs = f;
     const int b = blockIdx.x, nc = cw.cx * cw.cy, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const size_t cell0 = (size_t)b * nc;
+    const int first = b * nc, last = first + nc;              // this image's slice of the flattened cell range
     for (int round = 0; round < (1 << 24); ++round) {          // every round keeps at least the largest alive key
         __syncthreads();
         if (threadIdx.x == 0) alive_cells = 0;
         __syncthreads();
-        for (int c = warp; c < nc; c += nw) cell_refresh(mv, cw, fs, b, c, false, 0.f);
+        for (int base = first + warp * kCpw; base < last; base += nw * kCpw) cells_refresh32(mv, cw, fs, base, last, nc);
         __syncthreads();
         int loc = 0;
-        for (int c = threadIdx.x; c < nc; c += blockDim.x) loc += cw.cmax[cell0 + c] != 0ull ? 1 : 0;
+        for (int c = first + threadIdx.x; c < last; c += blockDim.x) loc += cw.cmax[c] != 0ull ? 1 : 0;
         if (loc) atomicAdd(&alive_cells, loc);
         __syncthreads();
         if (alive_cells == 0) break;
-        for (int c = warp; c < nc; c += nw) cell_decide(mv, cw, fs, ws, b, c);
+        for (int base = first + warp * kCpw; base < last; base += nw * kCpw) cells_decide32(mv, cw, fs, ws, base, last, nc);
         __threadfence_block();
     }
-    if (threadIdx.x == 0) {
-        const int n = ws.count[b];
-        if (n > (int)ws.cap) { ws.count[b] = (int)ws.cap; ws.flags[b] |= 1; }
+    // kept keys of the cells -> the image's key list (order is irrelevant: the select / sort kernel orders by key)
+    __shared__ int n_keys;
+    __syncthreads();
+    if (threadIdx.x == 0) n_keys = 0;
+    __syncthreads();
+    for (int c = first + threadIdx.x; c < last; c += blockDim.x) {
+        const u64 k = cw.kept[c];
+        if (k != 0ull) ws.keys[(size_t)b * ws.cap + atomicAdd(&n_keys, 1)] = k;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) ws.count[b] = n_keys;
 }
 
-constexpr int kGreedyCellRounds = 8;        // multi-CTA rounds before the per-image finisher (typical maps need 5-7)
+int g_greedy_rounds = 3;                    // multi-CTA rounds before the per-image finisher (development: balf_debug_set key 6)
 
 static void square_footprint(int r, Footprint* f) {
     f->S = r + 1;
@@ -703,12 +771,13 @@ static void square_footprint(int r, Footprint* f) {
     for (int i = 0; i <= kFpMax; ++i) f->hw[i] = i <= r ? r : -1;
 }
 // The kept list needs one slot per cell, so in cell mode the key area is re-cut: [B][cells] keys, then the cell structures
-// (52 bytes per cell against the 12 bytes per pixel of the key + alive areas: any S >= 3 fits).
+// (60 bytes per cell against the 12 bytes per pixel of the key + alive areas: any S >= 3 fits).
 static bool cells_layout(const NmsWs& ws, int B, int H, int W, int S, NmsWs* ws2, CellWs* cw) {
     const int cx = cdiv(W, S), cy = cdiv(H, S);
     const size_t cells = (size_t)B * cx * cy;
     const size_t o_alive = align_up(cells * 8, 256), o_cmax = o_alive + align_up(cells * 32, 256);
-    const size_t o_dirty = o_cmax + align_up(cells * 8, 256), need = o_dirty + align_up(cells * 4, 256);
+    const size_t o_kept = o_cmax + align_up(cells * 8, 256);
+    const size_t o_dirty = o_kept + align_up(cells * 8, 256), need = o_dirty + align_up(cells * 4, 256);
     const size_t have = align_up(sizeof(u64) * (size_t)H * W * B, 256) + sizeof(float) * (size_t)H * W * B;
     if (S < 3 || S > 16 || need > have) return false;
     char* p = reinterpret_cast<char*>(ws.keys);
@@ -716,7 +785,9 @@ static bool cells_layout(const NmsWs& ws, int B, int H, int W, int S, NmsWs* ws2
     ws2->cap = (size_t)cx * cy;
     cw->alive = reinterpret_cast<uint32_t*>(p + o_alive);
     cw->cmax = reinterpret_cast<u64*>(p + o_cmax);
+    cw->kept = reinterpret_cast<u64*>(p + o_kept);
     cw->dirty = reinterpret_cast<int*>(p + o_dirty);
+    cw->vec_ok = 0;
     cw->cx = cx;
     cw->cy = cy;
     return true;
@@ -724,21 +795,31 @@ static bool cells_layout(const NmsWs& ws, int B, int H, int W, int S, NmsWs* ws2
 static int run_greedy_cells(const MapView& mv, const NmsWs& ws, const CellWs& cw, const Footprint& f, int B, float thr,
                             cudaStream_t st) {
     const int nc = cw.cx * cw.cy;
-    dim3 grid(cdiv(nc, 8), B);
-    BALF_CUDA_OK(cudaMemsetAsync(cw.dirty, 0, sizeof(int) * (size_t)nc * B, st));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = cdiv(nc * B, 8);
+    const int grid = want < sms * 8 ? want : sms * 8;                 // 8 CTAs x 8 warps = a full SM of warps
+    CellWs cwv = cw;
+    cwv.vec_ok = f.S == 16 && mv.left % 4 == 0 && mv.Ws % 4 == 0 && reinterpret_cast<uintptr_t>(mv.score) % 16 == 0;
+    BALF_CUDA_OK(cudaMemsetAsync(cw.kept, 0, align_up(sizeof(u64) * (size_t)nc * B, 256) + sizeof(int) * (size_t)nc * B, st));   // kept + dirty
     {
         ProfScope p("nms_greedy_init", st);
-        greedy_cells_refresh_kernel<<<grid, 256, 0, st>>>(mv, cw, f, 1, thr);
+        greedy_cells_init_kernel<<<grid, 256, 0, st>>>(mv, cwv, f, thr, B);
+    }
+    for (int r = 0; r < g_greedy_rounds; ++r) {
+        if (r) {
+            ProfScope p("nms_greedy_refresh", st);
+            greedy_cells_refresh_kernel<<<grid, 256, 0, st>>>(mv, cw, f, B);
+        }
+        ProfScope p("nms_greedy_decide", st);
+        greedy_cells_decide_kernel<<<grid, 256, 0, st>>>(mv, cw, f, ws, B);
     }
     {
-        ProfScope p("nms_greedy_rounds", st);
-        for (int r = 0; r < kGreedyCellRounds; ++r) {
-            if (r) greedy_cells_refresh_kernel<<<grid, 256, 0, st>>>(mv, cw, f, 0, thr);
-            greedy_cells_decide_kernel<<<grid, 256, 0, st>>>(mv, cw, f, ws);
-        }
+        ProfScope p("nms_greedy_finish", st);
         greedy_cells_finish_kernel<<<B, 1024, 0, st>>>(mv, cw, f, ws);
     }
-    BALF_COUNT_LAUNCH(2 * kGreedyCellRounds + 1);
+    BALF_COUNT_LAUNCH(2 * g_greedy_rounds + 1);
     BALF_LAUNCH_OK();
     return 0;
 }
