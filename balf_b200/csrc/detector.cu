@@ -543,6 +543,7 @@ extern int g_match_impl;          // match.cu
 extern int g_tc_variant;          // detector_tc.cu
 extern int g_greedy_impl;         // nms.cu
 extern int g_greedy_rounds;       // nms.cu
+extern int g_nms_tma;             // nms.cu
 int g_tc_mask = 0x1F;              // debug hook (balf_debug_set key 0): bit l = stage l on the tensor-core path, bit 4 = head
 
 int g_chunk_images = 0;            // images per internal pass; 0 = automatic (debug hook key 1 pins it)
@@ -626,7 +627,8 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
 using namespace balf;
 
 extern "C" int balf_debug_set(int key, int value) {
-    BALF_REQUIRE(key >= 0 && key <= 6, "unknown debug key %d", key);
+    BALF_REQUIRE(key >= 0 && key <= 7, "unknown debug key %d", key);
+    if (key == 7) { g_nms_tma = value ? 1 : 0; return 0; }
     if (key == 6) { g_greedy_rounds = value < 0 ? 0 : value > 64 ? 64 : value; return 0; }
     if (key == 5) { g_greedy_impl = value ? 1 : 0; return 0; }
     if (key == 3) { g_match_impl = value ? 1 : 0; return 0; }

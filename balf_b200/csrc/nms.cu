@@ -15,6 +15,7 @@
 // pass with lanes on columns, log-step doubling networks in registers), survivors are compacted
 // as 64-bit (score, ~raster) keys, and one CTA per image does radix-select + bitonic sort.
 #include <algorithm>
+#include <cuda.h>            // CUtensorMap (type only; the encode entry point is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 #include "../../include/balf_b200.h"
 
@@ -201,8 +202,16 @@ __device__ __forceinline__ Interior interior_of(const MapView& mv) {
     return Interior{mv.border, (unsigned)max(mv.H - 2 * mv.border, 0), (unsigned)max(mv.W - 2 * mv.border, 0)};
 }
 
-__global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int vec_ok) {
-    __shared__ __align__(16) int px[kNmsIn][kNmsIn];
+// Tiles whose 80 x 80 input window lies inside the border-masked interior (80 % of them at 480 x 640) are loaded by the TMA:
+// one cp.async.bulk.tensor of the [80 x 80] box of a 3-D tensor map over the score maps [B, Hs, Ws] -- no thread instruction, no
+// index arithmetic, completion on an mbarrier.  (Phase 1 was two thirds of this issue-bound kernel's instructions.)  The raw
+// fp32 bits are used as they are: scores are >= 0 (softmax probabilities), and a negative value orders below zero as an
+// integer, i.e. it can never survive -- the same outcome as the max(bits, 0) of the manual path.
+__device__ __forceinline__ uint32_t nms_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int vec_ok, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    __shared__ __align__(128) int px[kNmsIn][kNmsIn];
+    __shared__ __align__(8) unsigned long long tma_bar;
     __shared__ int cmax[kNmsNB][kNmsNB + 1];
     __shared__ uint32_t cand[kNmsInner * kNmsInner];       // lby | lbx << 8 | sure << 16
     __shared__ u64 surv[kNmsListCap];
@@ -220,7 +229,23 @@ __global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int ve
     // per-pixel bounds / border test: phase 1 is two thirds of this kernel's instructions, and the kernel is issue-bound.
     const bool inner = vec_ok && in.yok(ty0 - kNmsHalo) && in.yok(ty0 - kNmsHalo + kNmsIn - 1) &&
                        in.xok(tx0 - kNmsHalo) && in.xok(tx0 - kNmsHalo + kNmsIn - 1);
-    if (inner) {
+    if (inner && use_tma) {
+        const uint32_t bar = nms_smem_u32(&tma_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)(kNmsIn * kNmsIn * 4)) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(nms_smem_u32(&px[0][0])), "l"(&tmap), "r"(mv.left + tx0 - kNmsHalo), "r"(mv.top + ty0 - kNmsHalo), "r"(b), "r"(bar)
+                         : "memory");
+        }
+        __syncthreads();                                   // the barrier is initialised before anybody polls it
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+    } else if (inner) {
         const int* base = img + (size_t)(ty0 - kNmsHalo) * mv.Ws + (tx0 - kNmsHalo);
 #pragma unroll
         for (int k = 0; k < kIter; ++k) {
@@ -842,15 +867,28 @@ __device__ u64 radix_select(const u64* keys, int n, int kth, int nbytes, Pred pr
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int cum = 0, bin = 255;
-            for (; bin > 0; --bin) {
-                int h = (int)hist[bin];
-                if (cum + h >= remaining) break;
-                cum += h;
+        if (threadIdx.x < 32) {
+            // bins from the top: lane l owns bins 255 - 8 l .. 248 - 8 l; warp prefix sums find the bin that holds the k-th
+            // key (a single thread walking 256 bins was ~2500 cycles of dependent shared-memory loads per digit)
+            const int lane = threadIdx.x, hi = 255 - 8 * lane;
+            int own = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) own += (int)hist[hi - j];
+            int incl = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const unsigned cross = __ballot_sync(0xffffffffu, incl >= remaining);
+            const int src = cross ? __ffs(cross) - 1 : 31;
+            if (lane == src) {
+                int cum = incl - own, bin = hi;
+                for (int j = 0; j < 8; ++j, --bin) {
+                    const int h = (int)hist[bin];
+                    if (cum + h >= remaining || bin == 0) break;
+                    cum += h;
+                }
+                xch[0] = (unsigned)bin;
+                xch[1] = (unsigned)(remaining - cum);
             }
-            xch[0] = (unsigned)bin;
-            xch[1] = (unsigned)(remaining - cum);
         }
         __syncthreads();
         prefix |= (u64)xch[0] << shift;
@@ -923,15 +961,21 @@ __global__ void nms_map_generic_kernel(MapView mv, float* __restrict__ out, int 
 
 // mode 0: windowed (find_index_higher_scores semantics), mode 1: greedy (plain top-k by key)
 __global__ void __launch_bounds__(1024) select_sort_kernel(NmsWs ws, int mode, int k, int npow2, int H, int W,
-                                                           int32_t* xy, float* out_score, int32_t* out_count) {
+                                                           int32_t* xy, float* out_score, int32_t* out_count, int stage_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* sel = reinterpret_cast<u64*>(smem_raw);          // [npow2]
+    u64* stage = sel + npow2;                             // [stage_cap] the image's keys, staged once when they fit: the
+                                                          // digit passes of the radix select then run from shared memory
     __shared__ unsigned hist[256];
     __shared__ unsigned xch[2];
     __shared__ int n_sel, c_gt, c_eq;
     const int b = blockIdx.x;
     const u64* keys = ws.keys + (size_t)b * ws.cap;
     const int n = min(ws.count[b], (int)ws.cap);
+    if (n > k && n <= stage_cap) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = keys[i];
+        keys = stage;                                      // (visible after the barrier below)
+    }
     int32_t* oxy = xy + (size_t)b * k * 2;
     float* osc = out_score + (size_t)b * k;
 
@@ -1037,12 +1081,43 @@ static int launch_windowed(const MapView& mv, const NmsWs& ws, int B, cudaStream
 }
 
 // nms_size 15: the fused two-level kernel
+int g_nms_tma = 1;          // development switch (balf_debug_set key 7): 0 = per-thread 128-bit loads for every tile
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
 static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStream_t st) {
     const int vec_ok = (mv.left % 4 == 0) && (mv.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(mv.score) % 16 == 0);
     dim3 grid(cdiv(mv.W, kNmsTile), cdiv(mv.H, kNmsTile), B);
+    // 3-D tensor map over the score maps [B, Hs, Ws] fp32, box = one 80 x 80 input window (row pitch a multiple of 16 bytes)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tma = 0;
+    if (vec_ok && g_nms_tma && mv.Ws >= kNmsIn && mv.Hs >= kNmsIn) {
+        if (EncodeTiledFn enc = encode_tiled_fn()) {
+            const cuuint64_t dims[3] = {(cuuint64_t)mv.Ws, (cuuint64_t)mv.Hs, (cuuint64_t)B};
+            const cuuint64_t strides[2] = {(cuuint64_t)mv.Ws * 4, (cuuint64_t)mv.Ws * mv.Hs * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)kNmsIn, (cuuint32_t)kNmsIn, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(mv.score), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+    }
     {
         ProfScope p("nms_windowed", st);
-        nms15_kernel<<<grid, 256, 0, st>>>(mv, ws, vec_ok);
+        nms15_kernel<<<grid, 256, 0, st>>>(mv, ws, vec_ok, tmap, use_tma);
     }
     BALF_COUNT_LAUNCH(1);
     return 0;
@@ -1078,12 +1153,14 @@ static int check_common(const float* score, int B, int Hs, int Ws, int top, int 
 static int run_select(const NmsWs& ws, int mode, int B, int H, int W, int k, int32_t* xy, float* sc, int32_t* cnt,
                       cudaStream_t st) {
     int np2 = next_pow2(k < 2 ? 2 : k);
-    size_t smem = sizeof(u64) * (size_t)np2;
+    const size_t room = (size_t)200 * 1024 - sizeof(u64) * (size_t)np2;
+    const int stage_cap = (int)std::min<size_t>(8192, room / sizeof(u64));
+    size_t smem = sizeof(u64) * ((size_t)np2 + stage_cap);
     if (smem > 48 * 1024)
         BALF_CUDA_OK(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope p("nms_select_sort", st);
-        select_sort_kernel<<<B, 1024, smem, st>>>(ws, mode, k, np2, H, W, xy, sc, cnt);
+        select_sort_kernel<<<B, 1024, smem, st>>>(ws, mode, k, np2, H, W, xy, sc, cnt, stage_cap);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();

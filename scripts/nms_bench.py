@@ -27,3 +27,15 @@ c.profile_enable(False)
 alg = B * (480 * 640 * 4)
 for k, (cnt, ms) in rep.items():
     print("%-22s %8.1f us/launch  %8.1f GB/s (score-map bytes / time)" % (k, ms / cnt * 1e3, alg / (ms / cnt * 1e-3) / 1e9))
+if mode == "windowed":        # A/B of the TMA tile load (balf_debug_set key 7)
+    for tma in (0, 1):
+        c.debug_set(7, tma)
+        c.profile_enable(True); c.profile_report(reset=True)
+        for _ in range(n):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        rep = c.profile_report(reset=True)
+        c.profile_enable(False)
+        print("tma=%d " % tma + "  ".join("%s %.1f us" % (k, ms / cnt * 1e3) for k, (cnt, ms) in rep.items()))
+    c.debug_set(7, 1)
