@@ -32,3 +32,20 @@ def parse_test_config(argv=None):
     p.add_argument("--patch_size", type=int, default=4)
     args = p.parse_args(argv)
     return args, test_utils.get_cfg_from_yaml_file(args.cfg_file)
+
+
+# multi-scale extraction: the defaults of the reference's parser (balf/configs/config_hpatches.py:50-82, parse_multiscale_config;
+# the script that would consume them is not shipped)
+MULTISCALE_DEFAULTS = dict(nms_size=15, num_points=1500, border_size=15, scale_factor_levels=2 ** 0.5, pyramid_levels=5,
+                           upsampled_levels=1)
+
+
+def default_multiscale_args(**overrides):
+    return types.SimpleNamespace(**{**MULTISCALE_DEFAULTS, **overrides})
+
+
+def multiscale_pyramid(margs):
+    """parser arguments -> keyword arguments of demo_match.detect_multiscale_batch_device: the original image, `pyramid_levels`
+    levels each 1 / scale_factor_levels of the previous one, and `upsampled_levels` levels each scale_factor_levels larger."""
+    return dict(scale=1.0 / float(margs.scale_factor_levels), levels=int(margs.pyramid_levels) + 1,
+                upsampled_levels=int(margs.upsampled_levels))

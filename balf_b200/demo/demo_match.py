@@ -50,16 +50,20 @@ def detect_batch_device(args, u8, detector, nms="greedy"):
         radius=args.nms_size, subpixel_ps=args.patch_size if args.sub_pixel else 0, crop=(top, left, h, w))
 
 
-def detect_multiscale_batch_device(args, u8, detector, scale=0.7, levels=3, nms="windowed"):
+def detect_multiscale_batch_device(args, u8, detector, scale=0.7, levels=3, nms="windowed", upsampled_levels=0):
     """Multi-scale pyramid extraction (the mode the reference advertises in balf/configs/config_hpatches.py:50-82 but
     does not implement; semantics defined in include/balf_b200.h and restated in oracle/multiscale.py).
-    u8 [B,H,W,C] uint8 CUDA.  Level l is the bilinear resize of the image to round(H s^l) x round(W s^l); every level
-    runs the detector and the per-level extraction with capacity args.num_features, and the lists are merged by score
-    into the best args.num_features keypoints in level-0 coordinates.
-    -> (xy fp32 [B,K,2], score fp32 [B,K], level int32 [B,K], count int32 [B]) on the device."""
+    u8 [B,H,W,C] uint8 CUDA.  Level l (l = -upsampled_levels .. levels - 1, finest first) is the bilinear resize of the
+    image to round(H s^l) x round(W s^l) -- l < 0 are the up-sampled levels of the parser's ``--upsampled_levels``; every
+    level runs the detector and the per-level extraction with capacity args.num_features, and the lists are merged by score
+    into the best args.num_features keypoints in level-0 coordinates.  The parser's defaults (scale_factor_levels sqrt(2),
+    pyramid_levels 5, upsampled_levels 1) are ``scale=2 ** -0.5, levels=6, upsampled_levels=1``:
+    ``config.multiscale_pyramid(config.default_multiscale_args())``.
+    -> (xy fp32 [B,K,2], score fp32 [B,K], level int32 [B,K] (index into the finest-first level list), count int32 [B])
+    on the device."""
     B, h, w, _ = u8.shape
     lists, scales = [], []
-    for l in range(levels):
+    for l in range(-int(upsampled_levels), levels):
         hs, ws = _capi.level_size(h, scale, l), _capi.level_size(w, scale, l)
         if l == 0:
             x, (top, left) = _capi.preprocess_u8(u8)
@@ -102,17 +106,15 @@ class DetectPipeline:
         self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.compute_stream = torch.cuda.Stream(self.dev)
-        self.depth, self._n, self._slots, self._in_flight = depth, 0, {}, 0
+        self.depth, self._free, self._in_flight = depth, {}, 0
 
     def _staging(self, outs):
-        """pinned host buffers, a ring of ``depth`` sets per output shape (no allocation in the steady state);
-        a set is reused ``depth`` submissions later, i.e. after its ticket has normally been collected."""
+        """a set of pinned host buffers for these output shapes from the free list of that shape (allocated on first use:
+        no allocation in the steady state).  A set belongs to its ticket until ``result`` has copied it out and returned
+        it -- tickets may be collected in any order and batches of different shapes may interleave."""
         key = tuple((tuple(o.shape), o.dtype) for o in outs)
-        ring = self._slots.setdefault(key, [])
-        if len(ring) < self.depth:
-            ring.append([torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs])
-            return ring[-1]
-        return ring[self._n % self.depth]
+        free = self._free.setdefault(key, [])
+        return key, (free.pop() if free else [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs])
 
     def submit(self, images):
         if self._in_flight >= self.depth:
@@ -127,19 +129,23 @@ class DetectPipeline:
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(arrived)
             xy, sc, _, cnt = detect_batch_device(self.args, u8, self.detector, self.nms)
-            host = self._staging((xy, sc, cnt))
+            key, host = self._staging((xy, sc, cnt))
             for h, o in zip(host, (xy, sc, cnt)):
                 h.copy_(o, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.compute_stream)
-        self._n += 1
-        return host, done, (xy, sc, cnt)              # device tensors kept alive until the copies have run
+        return [key, host, done, (xy, sc, cnt)]       # device tensors kept alive until the copies have run
 
     def result(self, ticket):
-        host, done, _ = ticket
+        key, host, done, _ = ticket
+        if host is None:
+            raise RuntimeError("DetectPipeline: this ticket has already been collected")
         done.synchronize()
         self._in_flight -= 1
-        return tuple(h.numpy().copy() for h in host)     # the staging set is recycled `depth` submissions later
+        out = tuple(h.numpy().copy() for h in host)
+        self._free[key].append(host)                  # only now may another submission reuse the staging set
+        ticket[1] = ticket[3] = None
+        return out
 
 
 def detect(args, im, detector, device):

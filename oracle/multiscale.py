@@ -2,7 +2,8 @@
 
 * ``rgb_to_gray``: PIL ``Image.convert('L')`` as used by the reference's ``load_im`` (demo/demo_match.py:13-19):
   ITU-R 601-2 luma in 16.16 fixed point, L = (19595 R + 38470 G + 7471 B + 32768) >> 16 (Pillow ``Convert.c``;
-  Pillow is not importable here, so this row is anchored on the published formula: PARITY UNPINNED).
+  PINNED: tests/test_media_fixtures.py checks it against PIL's own output on media/im1.jpg, im2.jpg,
+  tests/golden/r2_media.npz).
 * ``resize_preprocess`` / ``merge_levels`` / ``detect_multiscale``: the multi-scale pyramid extraction.  The reference
   ships only its argument parser (balf/configs/config_hpatches.py:50-82), no implementation: the semantics are the
   ones documented in include/balf_b200.h, restated here operation by operation in float32.  PARITY UNPINNED.
@@ -70,15 +71,15 @@ def level_score_map(sd, level_f32):
     return prob[t0:t0 + hs, l0:l0 + ws]
 
 
-def detect_multiscale(sd, im_u8, scale, levels, k, nms_size=15, border=15, score_maps=None):
+def detect_multiscale(sd, im_u8, scale, levels, k, nms_size=15, border=15, score_maps=None, upsampled_levels=0):
     """full CPU pipeline for one uint8 image [H,W,C]: per level resize -> pad -> detector -> windowed NMS top-k -> merge.
     ``score_maps`` (optional, one per level) replaces the detector forward (same-input parity of the extraction)."""
     H, W = im_u8.shape[:2]
     lists, scales = [], []
-    for l in range(levels):
+    for i, l in enumerate(range(-int(upsampled_levels), levels)):     # finest (most up-sampled) level first
         hs, ws = level_size(H, scale, l), level_size(W, scale, l)
         if score_maps is not None:
-            crop = score_maps[l]
+            crop = score_maps[i]
         else:
             lvl = (im_u8.astype(F) / F(255)) if l == 0 else resize_level(im_u8, hs, ws)
             if lvl.shape[2] == 1:

@@ -154,6 +154,41 @@ def test_multiscale_detect_end_to_end(detector, detector_sd):
     assert len(got & want) >= 0.99 * len(want), (len(got & want), len(want))
 
 
+def test_multiscale_parser_defaults_with_upsampled_level(detector):
+    """the pyramid of the reference's own parser (config_hpatches.py:71-76: scale sqrt(2), 5 down-sampled levels and ONE
+    up-sampled level = 7 levels, finest first): same-input parity of extraction + merge with the oracle restatement"""
+    from balf_b200.configs import config
+    from balf_b200.demo import demo_match
+    import balf_b200._capi as capi
+    det = copy.deepcopy(detector).to(DEV).eval()
+    det.precision = "fp32"
+    margs = config.default_multiscale_args()
+    pyr = config.multiscale_pyramid(margs)
+    assert pyr["levels"] == 6 and pyr["upsampled_levels"] == 1 and abs(pyr["scale"] - 2 ** -0.5) < 1e-12
+    args = config.default_test_args(sub_pixel=False, num_features=margs.num_points, nms_size=margs.nms_size, border_size=margs.border_size)
+    im = synth_u8(384, 448, 13)[:, :, :1].copy()
+    u8 = torch.from_numpy(im[None]).to(DEV)
+    xy, sc, lv, cnt = demo_match.detect_multiscale_batch_device(args, u8, det, **pyr)
+    n = int(cnt[0])
+    assert n == margs.num_points and set(np.unique(lv[0, :n].cpu().numpy())) <= set(range(7)) and 0 in lv[0, :n].cpu().numpy()
+    maps = []
+    for l in range(-1, 6):
+        hs, ws = capi.level_size(384, pyr["scale"], l), capi.level_size(448, pyr["scale"], l)
+        x, (top, left) = capi.preprocess_u8(u8) if l == 0 else capi.resize_preprocess_u8(u8, hs, ws)
+        if l == -1:
+            assert (hs, ws) == (543, 634)
+        with torch.inference_mode():
+            maps.append(det(x)["prob"][0, top:top + hs, left:left + ws].cpu().numpy())
+    wxy, wsc, wlv = oms.detect_multiscale(None, im, pyr["scale"], 6, margs.num_points, score_maps=maps, upsampled_levels=1)
+    np.testing.assert_array_equal(sc[0, :n].cpu().numpy(), wsc)
+    np.testing.assert_array_equal(lv[0, :n].cpu().numpy(), wlv)
+    np.testing.assert_array_equal(xy[0, :n].cpu().numpy(), wxy)
+    # the up-sampled level's input itself: bit-exact against the restated resize
+    x, (top, left) = capi.resize_preprocess_u8(u8, 543, 634)
+    want = oms.resize_level(im, 543, 634)
+    np.testing.assert_array_equal(x[0, 0, top:top + 543, left:left + 634].cpu().numpy(), want[:, :, 0])
+
+
 def test_detect_pipeline_equals_detect_batch(detector):
     """the streaming host-buffer API returns exactly what detect_batch returns, in submission order"""
     from balf_b200.configs import config
@@ -171,3 +206,25 @@ def test_detect_pipeline_equals_detect_batch(detector):
             want = demo_match.detect_batch(args, b, det, DEV, nms)
             for g, w in zip(got, want):
                 np.testing.assert_array_equal(g, w)
+
+
+def test_nccl_gather_c_abi_single_rank():
+    """balf_gather_keypoints on an ncclComm_t created through the C-ABI (world size 1 here; bench.py --gpus N runs it over
+    NVLink): the records come back unchanged, rank-ordered; pack / unpack kernels agree with balf_b200.sharding."""
+    import balf_b200._capi as capi
+    from balf_b200 import sharding
+    uid = capi.nccl_unique_id()
+    assert len(uid) == 128
+    comm = capi.nccl_comm_create(uid, 1, 0, DEV)
+    try:
+        g = torch.Generator().manual_seed(3)
+        xy = torch.randint(0, 640, (5, 77, 2), generator=g, dtype=torch.int32).to(DEV)
+        sc = torch.rand(5, 77, generator=g).to(DEV)
+        cnt = torch.randint(0, 78, (5,), generator=g, dtype=torch.int32).to(DEV)
+        xa, sa, ca = capi.gather_keypoints(comm, 1, xy, sc, cnt)
+        torch.cuda.synchronize()
+        assert torch.equal(xa, xy) and torch.equal(sa, sc) and torch.equal(ca, cnt)
+        x2, s2, c2 = sharding.unpack_records(sharding.pack_records(xy, sc, cnt))
+        assert torch.equal(x2, xy) and torch.equal(s2, sc) and torch.equal(c2, cnt)
+    finally:
+        capi.nccl_comm_destroy(comm)

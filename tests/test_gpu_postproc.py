@@ -142,6 +142,21 @@ def test_dense_apply_nms_and_helpers():
     assert tu.mod_padding_symmetric(np.zeros((480, 640, 3))).shape == (512, 640, 3)
     assert tu.mod_padding_symmetric(np.zeros((900, 1200, 3))).shape == (960, 1216, 3)
     assert tu.mod_padding_symmetric(np.zeros((128, 192, 3))).shape == (128, 192, 3)
+    # the stand-alone helper follows the reference arithmetic for odd sizes too (121 -> 127 rows with 3 + 3), golden pad arrays
+    odd = np.arange(121 * 187 * 3, dtype=np.float64).reshape(121, 187, 3)
+    p = tu.mod_padding_symmetric(odd)
+    assert p.shape == (127, 191, 3) and np.array_equal(p[3:124, 2:189], odd) and p[:3].sum() == 0
+    # nms_fast returns the caller's own (unrounded) columns, like the reference (test_utils.py:161)
+    sub = np.stack([np.array([10.2, 30.7, 11.4, 80.0]), np.array([5.1, 5.4, 6.2, 40.0]), np.array([0.5, 0.9, 0.7, 0.1])])
+    out, inds = tu.nms_fast(sub, 64, 96, 4)
+    np.testing.assert_array_equal(inds, [1, 2, 3])
+    np.testing.assert_array_equal(out, sub[:, [1, 2, 3]])
+    # float64 maps keep their own values (the device only decides the mask)
+    m64 = g["map_rand"].astype(np.float64) + 1e-12
+    np.testing.assert_array_equal(tu.apply_nms(m64, 15), m64 * (postproc.apply_nms(g["map_rand"], 15) != 0))
+    # no silent truncation: a radius-2 NMS on a large map can keep more than the 16384 points of one call
+    with pytest.raises(ValueError):
+        tu.get_points_direct_from_score_map(np.random.default_rng(0).random((600, 800), dtype=np.float32), 0.015, 2, False, 4)
 
 
 def test_errors():
