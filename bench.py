@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--nms", default="windowed", choices=["windowed", "greedy"])
     p.add_argument("--precision", default=None, help="detector precision (default: the module's)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="development / profiling: only the configs[1] workload")
     p.add_argument("--chunk", type=int, default=0, help="development: images per internal detector pass (library default if 0)")
     return p.parse_args()
 
@@ -545,8 +546,12 @@ def main():
     d2h = sum(int(r.nbytes) for r in res)
 
     # the other BASELINE.json configs (every rank takes part: cfg3 / cfg4 are sharded over the ranks)
-    c3_ms, c3_gather_ms, c3_local = extras_cfg3(dev, det, world, rank, gather)
-    c4_ms, c4_local = extras_cfg4(dev, det, world, rank)
+    if a.no_extras:
+        c3_ms = c3_gather_ms = c4_ms = float("nan")
+        c3_local = c4_local = 0
+    else:
+        c3_ms, c3_gather_ms, c3_local = extras_cfg3(dev, det, world, rank, gather)
+        c4_ms, c4_local = extras_cfg4(dev, det, world, rank)
 
     t = torch.tensor([ms, t_e2e, c3_ms, c3_gather_ms, c4_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -601,11 +606,13 @@ def main():
         "cfg4": {"workload": "configs[4]: 256 synthetic 1024x1024 images over %d rank(s), 3-level pyramid (0.7x), windowed NMS, "
                              "top-8192 merged" % world, "images_per_s": 256 / (c4_ms * 1e-3), "ms": c4_ms, "images_per_rank": c4_local},
     }
-    if world == 1:
+    if a.no_extras:
+        line.pop("cfg3"), line.pop("cfg4")
+    if world == 1 and not a.no_extras:
         line["extras"] = extras(dev, pk, det)
         line["greedy"] = extras_greedy(a, dev, pk, det, config.default_test_args(sub_pixel=False, num_features=K_FEATURES), u8)
         line["pair_cfg2"] = extras_pair(dev, det)
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and not a.no_extras:
         line["cpu_baseline"] = cpu_baseline(a)
         # the reference's shipped demo path (greedy nms_fast in Python loops) beside the greedy GPU number
         line["greedy"]["cpu_baseline"] = cpu_baseline(a, nms="greedy", greedy_impl="python", budget_s=6.0, max_images=4)

@@ -104,7 +104,7 @@ def traffic():
             d = dict(zip(head, r))
             kn = d.get("Kernel Name", "")
             name = None
-            m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
+            m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)?>", kn)
             if m:
                 name = "det_branch_%s_c%s" % ("grid" if m.group(3) == "0" else "block", m.group(2))
             m = re.search(r"tc_merge(?:_bulk)?_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
@@ -151,5 +151,7 @@ if __name__ == "__main__":
     full(tag)
     full(tag, "prof_nms.ncu-rep", "_ncu_nms.md", "the windowed NMS + select/sort kernels (scripts/nms_bench.py, 64 maps)")
     full(tag, "prof_hn.ncu-rep", "_ncu_hardnet.md", "the HardNet tensor-core kernels (scripts/hn_bench.py, 4096 patches)")
+    full(tag, "prof_greedy.ncu-rep", "_ncu_greedy.md", "the cell-based greedy NMS kernels (bench.py --nms greedy, 64 maps)")
+    full(tag, "prof_smnn.ncu-rep", "_ncu_smnn.md", "the SMNN kernels (scripts/smnn_bench.py, 2048 x 2048)")
     traffic()
     bench(tag)
