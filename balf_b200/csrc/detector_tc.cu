@@ -29,6 +29,7 @@
 // Weights are pre-packed into the exact shared-memory image of the B operands and brought in by TMA
 // bulk copies (cp.async.bulk + mbarrier) -- once per CTA when the whole set fits next to the operand
 // region (level 1), otherwise through a 2-slot ring that runs ahead of the MMAs.
+#include <cuda_fp16.h>
 #include "detector.cuh"
 #include "umma.cuh"
 
@@ -52,6 +53,7 @@ struct TcGemm {
     uint16_t rows;        // rows of the packed operand (N of a Linear layer, 64 for a mixing matrix)
     uint16_t kb;          // K columns per block
     uint16_t bias;        // 1: the last block carries 8 extra K columns (bias hi, bias lo, 0 ...)
+    uint16_t h16;         // 1: the K columns are fp16 (kind::f16 MMAs, 8 per 16-byte chunk); the bias columns stay tf32
 };
 struct TcPlan {
     const float* base;
@@ -92,9 +94,11 @@ __host__ __device__ constexpr int tc_kb(int rows, int K, int cap = 32768) {
 }
 __host__ __device__ constexpr int tc_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
 __host__ __device__ inline uint32_t gemm_block_bytes(const TcGemm& g, uint32_t b) {
-    return (uint32_t)g.rows * (g.kb + ((g.bias && b + 1 == g.nblk) ? 8u : 0u)) * 4u;
+    return (uint32_t)g.rows * (g.kb * (g.h16 ? 2u : 4u) + ((g.bias && b + 1 == g.nblk) ? 32u : 0u));
 }
-__host__ __device__ inline uint32_t gemm_bytes(const TcGemm& g) { return (uint32_t)g.rows * ((uint32_t)g.kb * g.nblk + (g.bias ? 8u : 0u)) * 4u; }
+__host__ __device__ inline uint32_t gemm_bytes(const TcGemm& g) {
+    return (uint32_t)g.rows * ((uint32_t)g.kb * g.nblk * (g.h16 ? 2u : 4u) + (g.bias ? 32u : 0u));
+}
 
 // ------------------------------------------------------------------------------------------ weight ring (thread 0)
 struct Ring {
@@ -120,7 +124,8 @@ __device__ __forceinline__ void ring_build_schedule(uint2* sched, const TcPlan& 
     uint32_t n = 0;
     for (int gi = 0; gi < p.ngemm; ++gi) {
         const TcGemm g = p.g[gi];
-        for (uint32_t b = 0; b < g.nblk; ++b) sched[n++] = make_uint2(g.goff + b * (uint32_t)g.rows * g.kb, gemm_block_bytes(g, b));
+        for (uint32_t b = 0; b < g.nblk; ++b)
+            sched[n++] = make_uint2(g.goff + b * (uint32_t)g.rows * g.kb / (g.h16 ? 2u : 1u), gemm_block_bytes(g, b));
     }
     *count = n;
 }
@@ -168,6 +173,7 @@ template <int CIN, int C> struct BranchG {
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
+    __host__ __device__ static constexpr bool h16(int) { return false; }
 };
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
@@ -177,6 +183,9 @@ template <int CIN, int C> struct MergeG {
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
+    // stages 1-2: u' / v' cross HBM as fp16 tiles (same 11-bit significand as the tf32 operands they replace, half the
+    // bytes of the HBM-bound merge kernels), so dense2 runs as kind::f16 on fp16 weights
+    __host__ __device__ static constexpr bool h16(int gi) { return C <= 64 && (gi == MG_PD2A || gi == MG_PD2B); }
 };
 template <int C> struct HeadG {
     static constexpr int count = HG_COUNT;
@@ -186,8 +195,11 @@ template <int C> struct HeadG {
     __host__ __device__ static constexpr int rows(int gi) { return gi == HG_DENSE ? kHeadN : C; }
     __host__ __device__ static constexpr int K(int) { return C; }
     __host__ __device__ static constexpr bool bias(int) { return true; }
+    __host__ __device__ static constexpr bool h16(int) { return false; }
 };
-template <typename G> __host__ __device__ constexpr uint32_t g_bytes(int gi) { return (uint32_t)G::rows(gi) * (G::K(gi) + (G::bias(gi) ? 8 : 0)) * 4u; }
+template <typename G> __host__ __device__ constexpr uint32_t g_bytes(int gi) {
+    return (uint32_t)G::rows(gi) * (G::K(gi) * (G::h16(gi) ? 2u : 4u) + (G::bias(gi) ? 32u : 0u));
+}
 template <typename G> __host__ __device__ constexpr uint32_t g_off(int gi) { uint32_t o = 0; for (int i = 0; i < gi; ++i) o += g_bytes<G>(i); return o; }
 
 // high word of a SWIZZLE_NONE descriptor (SBO = 128, version 1) -- the low word is (LBO >> 4) << 16 | addr >> 4
@@ -196,6 +208,14 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t addr, uint32_t lbo) {
     return ((uint64_t)kDescHi << 32) | (uint64_t)(((lbo >> 4) << 16) | ((addr >> 4) & 0x3FFFu));
 }
 
+// kind::f16 with fp16 operands (A, B format 0 = F16, D = F32), K = 16 per instruction; probed: scripts/umma_probe_f16.cu
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
 // Thread 0: D[128 x N] (+)= A[128 x K] * W^T (+ bias) for GEMM GI of plan G (see issue_linear).
 // high word of a K-major SWIZZLE_128B descriptor (SBO = 1024: 8 rows x 128 B, version 1, layout type 2); LBO is ignored
 // by the hardware for swizzled K-major operands (encoded 1).  Probed: profiles/r01_umma_probe.txt "Kmaj SW128".
@@ -207,16 +227,18 @@ __device__ __forceinline__ uint64_t desc_sw_of(uint32_t addr) {
 template <typename G, int GI, bool ASW = false>
 __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_t a_addr, uint32_t ones_addr, uint32_t d_tmem, bool first) {
     constexpr int ROWS = G::rows(GI), K = G::K(GI);
-    constexpr bool BIAS = G::bias(GI);
+    constexpr bool BIAS = G::bias(GI), H16 = G::h16(GI);        // H16: A and B are fp16 chunk-major (8 halves per 16-byte chunk)
+    static_assert(!(H16 && ASW), "fp16 operands use the chunk-major layout");
     constexpr int KB = tc_kb(ROWS, K, G::cap), NBLK = K / KB;
-    constexpr uint32_t idesc = make_idesc_tf32(128, ROWS);
+    constexpr uint32_t idesc = H16 ? make_idesc_f16(128, ROWS) : make_idesc_tf32(128, ROWS);
     constexpr uint32_t a_lbo = TM * 16u, b_lbo = (uint32_t)ROWS * 16u;
+    constexpr int KSTEP = H16 ? 16 : 8, EPC = H16 ? 8 : 4;      // K per MMA, elements per 16-byte chunk
     const uint64_t a_desc = ASW ? desc_sw_of(a_addr) : desc_of(a_addr, a_lbo);
 #pragma unroll
     for (int b = 0; b < NBLK; ++b) {
         uint32_t w_addr, slot = 0;
         if (G::resident) {
-            w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * 4u;
+            w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * (H16 ? 2u : 4u);
         } else {
             ring_top_up<G::nslot>(r, p);
             slot = r.cslot;
@@ -226,15 +248,15 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
         const uint64_t b_desc = desc_of(w_addr, b_lbo);
         fence_after_sync();
 #pragma unroll
-        for (int k8 = 0; k8 < KB / 8; ++k8) {
-            const uint32_t kchunk = (uint32_t)(b * KB) / 4u + (uint32_t)k8 * 2u;
+        for (int ks = 0; ks < KB / KSTEP; ++ks) {
+            const uint32_t kchunk = (uint32_t)(b * KB) / EPC + (uint32_t)ks * 2u;
             // swizzled panels: 32 K columns (128 B) per panel of TM rows, 32 B per MMA inside a panel
             const uint32_t a_off = ASW ? (kchunk / 8u) * (TM * 128u) + (kchunk % 8u) * 16u : kchunk * a_lbo;
-            mma_tf32(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)k8 * 2u * b_lbo) >> 4), idesc,
-                     !(first && b == 0 && k8 == 0));
+            if (H16) mma_f16(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)ks * 2u * b_lbo) >> 4), idesc, !(first && b == 0 && ks == 0));
+            else mma_tf32(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)ks * 2u * b_lbo) >> 4), idesc, !(first && b == 0 && ks == 0));
         }
-        if (BIAS && b + 1 == NBLK)
-            mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / 4u) * b_lbo) >> 4), idesc, true);
+        if (BIAS && b + 1 == NBLK)      // the bias columns (tf32: bias hi, bias lo, 0 ...) follow the block's KB / EPC chunks
+            mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / EPC) * b_lbo) >> 4), make_idesc_tf32(128, ROWS), true);
         if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
     }
 }
@@ -749,7 +771,9 @@ template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
-    static constexpr bool swz_out = C <= 128;                      // u' / v' leave in the swizzled panel layout (bulk-copied by the merge kernels)
+    static constexpr bool swz_out = C == 128;                      // u' / v' leave in the swizzled panel layout (bulk-copied by the merge kernel)
+    static constexpr bool h16_out = C <= 64;                       // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
+                                                                   // layout of the merge kernel's kind::f16 dense2, half the HBM bytes
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
     static constexpr int ncols = NG_ * tc_cols(col_y + 2 * C) > 512 ? col_y + 2 * C : tc_cols(col_y + 2 * C);   // TMEM columns per group
@@ -945,7 +969,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             // images).  Lanes 2i / 2i+1 therefore swap every other chunk: both lanes write the two halves of one 32-byte
             // sector of row 2i, then of row 2i+1 -- 16 full sectors per instruction.
             const bool odd = (threadIdx.x & 1) != 0;
-            const size_t own_base = Cfg::swz_out ? ((size_t)img * npix + (pix & ~(TM - 1))) * C : ((size_t)img * npix + pix) * C;
+            const size_t own_base = (Cfg::swz_out || Cfg::h16_out) ? ((size_t)img * npix + (pix & ~(TM - 1))) * C : ((size_t)img * npix + pix) * C;
             const int own_sw = pix & (TM - 1);
             const size_t oth_base = __shfl_xor_sync(0xffffffffu, (unsigned long long)own_base, 1);
             const int oth_sw = __shfl_xor_sync(0xffffffffu, own_sw, 1);
@@ -956,6 +980,25 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 float a[SC], r[SC];
                 ld_row<SC>(lane_base + Cfg::col_y + col0 + c, a);
                 if (Cfg::park_u) ld_row<SC>(lane_base + Cfg::col_u + col0 + c, r);
+                if constexpr (Cfg::h16_out) {
+                    // fp16 tile of the merge kernel: chunk j (8 channels) of pixel row p sits at halves j * 1024 + p * 8 of the
+                    // tile; a lane stores 16 bytes per chunk -- neighbouring pixels (the other unit of the tile in the grid
+                    // branch, the same block row in the block branch) complete the 32-byte sectors.  fp16 has the 11-bit
+                    // significand of the tf32 operand this value would otherwise be rounded to; satfinite guards the range.
+                    __half* tile = reinterpret_cast<__half*>(out) + own_base + (size_t)own_sw * 8;
+#pragma unroll
+                    for (int j = 0; j < SC / 8; ++j) {
+                        uint32_t h[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float lo = a[8 * j + 2 * e] + r[8 * j + 2 * e], hi = a[8 * j + 2 * e + 1] + r[8 * j + 2 * e + 1];
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(hi), "f"(lo));
+                        }
+                        if (valid && (!(BALF_EXP & 8) || h[0] == 0x12345678u))
+                            *reinterpret_cast<uint4*>(tile + (size_t)((col0 + c) / 8 + j) * (TM * 8)) = make_uint4(h[0], h[1], h[2], h[3]);
+                    }
+                    continue;
+                }
                 float4 o[SC / 4];
                 if constexpr (!Cfg::park_u) {                // the residual u comes back from `out` (full-sector pair loads)
                     float4* rq = reinterpret_cast<float4*>(r);
@@ -1263,9 +1306,10 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
 template <int CIN, int C> struct MergeBulkCfg {
     static constexpr int CH = C / 2;
     static constexpr bool cc0 = CIN < 8;
-    static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;
+    static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;      // W / Q staging tiles (fp32)
+    static constexpr uint32_t uv_bytes = (uint32_t)TM * C * 2;        // u' / v' tiles (fp16, chunk-major)
     static constexpr uint32_t xbytes = cc0 ? 0u : (uint32_t)TM * tc_kin(CIN) * 4;
-    static constexpr uint32_t region = 4 * tile_bytes + xbytes;
+    static constexpr uint32_t region = 2 * uv_bytes + 2 * tile_bytes + xbytes;
     static constexpr int col_acc = 0, col_x0 = C;
     static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
     static constexpr int min_ctas = C <= 32 ? 2 : 1;
@@ -1280,9 +1324,9 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     constexpr int CH = Cfg::CH;
     using G = MergeG<CIN, C>;
     const TcShared s = carve(smem, Cfg::region, plan);
-    float* const regU = s.region;
-    float* const regV = regU + (size_t)TM * C;
-    float* const regW = regV + (size_t)TM * C;
+    float* const regU = s.region;                                    // fp16 tile: TM * C / 2 floats
+    float* const regV = regU + (size_t)TM * C / 2;
+    float* const regW = regV + (size_t)TM * C / 2;
     float* const regQ = regW + (size_t)TM * C;
     float* const regX = regQ + (size_t)TM * C;
     uint64_t* const ld_bar = s.aux;
@@ -1306,10 +1350,10 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         im = fast_div(un, geo.upi, geo.inv_upi);
         px = (un - im * geo.upi) * 64 + (row & 63);
     };
-    auto load_tile = [&](int tt) {                          // elected lane: next tile's u' and v' -> U, V
-        mbar_expect_tx(ld_bar, 2 * Cfg::tile_bytes);
-        bulk_load(u_addr, uin + (size_t)tt * tile_floats, Cfg::tile_bytes, ld_bar);
-        bulk_load(v_addr, vin + (size_t)tt * tile_floats, Cfg::tile_bytes, ld_bar);
+    auto load_tile = [&](int tt) {                          // elected lane: next tile's u' and v' (fp16 tiles) -> U, V
+        mbar_expect_tx(ld_bar, 2 * Cfg::uv_bytes);
+        bulk_load(u_addr, uin + (size_t)tt * (tile_floats / 2), Cfg::uv_bytes, ld_bar);
+        bulk_load(v_addr, vin + (size_t)tt * (tile_floats / 2), Cfg::uv_bytes, ld_bar);
     };
     InputPf<CIN> pfx;
     if ((int)blockIdx.x < ntiles) {
@@ -1330,8 +1374,8 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             if constexpr (!Cfg::cc0) issue_linear_t<G, MG_CONV0>(ring, plan, x_addr, ones_addr, tm + Cfg::col_x0, true);
             mbar_wait(ld_bar, ld_phase & 1);
             fence_after_sync();
-            issue_linear_t<G, MG_PD2A, true>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true);
-            issue_linear_t<G, MG_PD2B, true>(ring, plan, v_addr, ones_addr, tm + Cfg::col_acc, false);
+            issue_linear_t<G, MG_PD2A>(ring, plan, u_addr, ones_addr, tm + Cfg::col_acc, true);      // kind::f16 on the fp16 tiles
+            issue_linear_t<G, MG_PD2B>(ring, plan, v_addr, ones_addr, tm + Cfg::col_acc, false);
             commit(s.done);
             bulk_wait_read();                               // the previous tile's q / r stores have left W and Q
         }
@@ -1531,6 +1575,16 @@ __global__ void tc_pack_kernel(const float* __restrict__ wT, int ld, int n0, int
     }
     dst[(size_t)b * rows * kb + (size_t)(kk >> 2) * rows * 4 + n * 4 + (kk & 3)] = to_tf32_exact(v);
 }
+// the same for fp16 GEMMs (TcGemm::h16): blocks of [rows x kb] halves, chunk-major with 8 halves per 16-byte chunk
+__global__ void tc_pack_h16_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real, int k_pad, int kb,
+                                   __half* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * k_pad) return;
+    const int k = i / rows, n = i - k * rows;
+    const int b = k / kb, kk = k - b * kb;
+    const float v = k < k_real ? wT[(size_t)k * ld + n0 + n] : 0.f;
+    dst[(size_t)b * rows * kb + (size_t)(kk >> 3) * rows * 8 + n * 8 + (kk & 7)] = __float2half_rn(v);
+}
 // bias columns of the last block: b' = (bias[n] + sum_k W[n][k] beta[k]) * alpha[n] + add[n], split into tf32 hi + lo
 __global__ void tc_pack_bias_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real,
                                     const float* __restrict__ bias, const float* __restrict__ beta,
@@ -1560,7 +1614,7 @@ struct TcPlans {
     size_t floats;
 };
 
-static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768) {
+static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768, bool h16 = false) {
     const int kb = tc_kb(rows, K, cap);
     TcGemm& g = p.g[gi];
     g.goff = (uint32_t)off;
@@ -1568,6 +1622,7 @@ static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, i
     g.rows = (uint16_t)rows;
     g.kb = (uint16_t)kb;
     g.bias = bias ? 1 : 0;
+    g.h16 = h16 ? 1 : 0;
     off += gemm_bytes(g) / 4;
     p.bytes += gemm_bytes(g);
     const uint32_t big = (gemm_block_bytes(g, g.nblk - 1) + 127u) / 128u * 128u;
@@ -1582,7 +1637,8 @@ static bool plan_matches(const TcPlan& p) {
     for (int gi = 0; gi < G::count; ++gi) {
         const TcGemm& g = p.g[gi];
         ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap) && g.nblk * g.kb == G::K(gi) &&
-             (g.bias != 0) == G::bias(gi) && gemm_bytes(g) == g_bytes<G>(gi) && (g.goff - p.g[0].goff) * 4u == off;
+             (g.bias != 0) == G::bias(gi) && (g.h16 != 0) == G::h16(gi) && gemm_bytes(g) == g_bytes<G>(gi) &&
+             (g.goff - p.g[0].goff) * 4u == off;
         off += gemm_bytes(g);
     }
     return ok;
@@ -1612,8 +1668,8 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         m.nslot = c == 64 ? 3 : 2;                                     // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
         tc_add(m, MG_CONV0, off, c, cin, true, mcap);
-        tc_add(m, MG_PD2A, off, c, c, false, mcap);
-        tc_add(m, MG_PD2B, off, c, c, true, mcap);
+        tc_add(m, MG_PD2A, off, c, c, false, mcap, c <= 64);          // mirrors MergeG::h16
+        tc_add(m, MG_PD2B, off, c, c, true, mcap, c <= 64);
         tc_add(m, MG_RC1, off, c, c, true, mcap);
         tc_add(m, MG_RC2, off, c, c, true, mcap);
     }
@@ -1643,10 +1699,14 @@ static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0
                         float* blob, cudaStream_t st) {
     const TcGemm& g = p.g[gi];
     const int k_pad = g.nblk * g.kb;
-    tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha, blob + g.goff);
+    if (g.h16)      // (no folds on the fp16 GEMMs: dense2 of the multi-axis gMLP has neither a LayerNorm in front nor a scale)
+        tc_pack_h16_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb,
+                                                                      reinterpret_cast<__half*>(blob + g.goff));
+    else
+        tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha, blob + g.goff);
     if (g.bias)   // two chunk planes after the last block's kb columns; the second stays zero (blob is memset)
         tc_pack_bias_kernel<<<cdiv(g.rows, 128), 128, 0, st>>>(wT, ld, n0, g.rows, k_real, bias, f.beta, f.alpha, f.add,
-                                                               blob + g.goff + (size_t)g.rows * k_pad);
+                                                               blob + g.goff + (size_t)g.rows * k_pad / (g.h16 ? 2 : 1));
 }
 
 // fp32-path packed weights (DetW) -> tc blob
