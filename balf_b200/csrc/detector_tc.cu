@@ -1312,7 +1312,7 @@ template <int CIN, int C> struct MergeBulkCfg {
     static constexpr uint32_t region = 2 * uv_bytes + 2 * tile_bytes + xbytes;
     static constexpr int col_acc = 0, col_x0 = C;
     static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
-    static constexpr int min_ctas = C <= 32 ? 2 : 1;
+    static constexpr int min_ctas = C <= 32 ? 3 : 1;
 };
 
 template <int CIN, int C>

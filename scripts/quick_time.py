@@ -13,6 +13,7 @@ dev = torch.device("cuda:0")
 cfg = test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)
 torch.manual_seed(0)
 det = get_model.load_model(cfg["model"]).eval().to(dev)
+det.precision = "tf32"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 
 

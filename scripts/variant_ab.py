@@ -15,6 +15,7 @@ dev = torch.device("cuda:0")
 cfg = test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)
 torch.manual_seed(0)
 det = get_model.load_model(cfg["model"]).eval().to(dev)
+det.precision = "tf32"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 masks = [int(a, 0) for a in sys.argv[2:]] or [0, 0x01, 0x02, 0x40, 0x41]
 g = torch.Generator().manual_seed(1234)
