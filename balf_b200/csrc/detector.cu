@@ -18,6 +18,7 @@
 //   se            mean -> excite.0 -> ReLU -> excite.2 -> sigmoid = s
 //   pool          max-pool2x2(r * s + q)            (stages 1-3)
 //   head          conv2(r * s + q) -> ReLU -> dense -> BN -> softmax -> depth-to-space (stage 4)
+#include <cuda_fp16.h>
 #include "detector.cuh"
 
 namespace balf {
@@ -397,7 +398,16 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             const size_t rowi = p & 127;
             const size_t cs = swz ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
                                   : ((p * C) >> 2) + c4;
-            float4 rv = __ldg(reinterpret_cast<const float4*>(r) + cs);
+            float4 rv;
+            if (swz) {
+                // r of those stages is an fp16 tile [C / 8 chunks][128 pixels][8 halves] (tc_merge_bulk_kernel)
+                const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r) + (p - rowi) * C +
+                                                                     (size_t)(c4 >> 1) * (128 * 8) + rowi * 8 + (c4 & 1) * 4));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                rv = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                rv = __ldg(reinterpret_cast<const float4*>(r) + cs);
+            }
             float4 qv = __ldg(reinterpret_cast<const float4*>(q) + cs);
             best.x = fmaxf(best.x, rv.x * s.x + qv.x); best.y = fmaxf(best.y, rv.y * s.y + qv.y);
             best.z = fmaxf(best.z, rv.z * s.z + qv.z); best.w = fmaxf(best.w, rv.w * s.w + qv.w);
