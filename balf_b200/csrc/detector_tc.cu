@@ -177,7 +177,7 @@ template <int CIN, int C> struct BranchG {
 };
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
-    static constexpr bool resident = C <= 32;
+    static constexpr bool resident = C <= 64;       // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions
     static constexpr int cap = 32768;
     static constexpr int nslot = C == 64 ? 3 : 2;           // C = 128: two operand regions leave room for two slots
     __host__ __device__ static constexpr int rows(int) { return C; }
@@ -1664,7 +1664,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
     TcPlans P;
     for (int l = 0; l < 4; ++l) {
         const int cin = tc_kin(a.dims[l]), c = a.dims[l + 1];
-        const bool resident = c <= 32;
+        const bool resident = c <= 64;                                 // mirrors MergeG::resident
         for (int b = 0; b < 2; ++b) {
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
