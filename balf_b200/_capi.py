@@ -323,7 +323,7 @@ def hardnet_pack_weights(raw):
     return packed
 
 
-HARDNET_PRECISIONS = {"fp32": 0, "tf32": 1}
+HARDNET_PRECISIONS = {"fp32": 0, "tf32": 1, "fp16": 2}
 
 
 def hardnet_forward(patches, packed, precision="tf32"):

@@ -217,19 +217,19 @@ extern "C" int balf_hardnet_pack_weights(const float* raw, float* packed, void* 
 static size_t hn_fp32_workspace_bytes(int n_patches) { return 2 * align_up((size_t)n_patches * 32 * 1024 * sizeof(float), 256); }
 extern "C" size_t balf_hardnet_workspace_bytes(int n_patches, int precision) {
     if (n_patches <= 0) return 0;
-    return precision == 1 ? hn_tc_workspace_bytes(n_patches) : hn_fp32_workspace_bytes(n_patches);
+    return precision >= 1 ? hn_tc_workspace_bytes(n_patches) : hn_fp32_workspace_bytes(n_patches);
 }
 
 extern "C" int balf_hardnet_forward(const float* packed, const float* patches, int n_patches, float* desc, void* workspace,
                                     size_t workspace_bytes, int precision, void* stream) {
     BALF_REQUIRE(packed && patches && desc && workspace, "null pointer argument");
     BALF_REQUIRE(n_patches > 0, "n_patches must be positive");
-    BALF_REQUIRE(precision == 0 || precision == 1, "precision %d is not built in this library (0 = fp32, 1 = tf32)", precision);
+    BALF_REQUIRE(precision >= 0 && precision <= 2, "precision %d is not built in this library (0 = fp32, 1 = tf32, 2 = fp16 operands)", precision);
     BALF_REQUIRE(workspace_bytes >= balf_hardnet_workspace_bytes(n_patches, precision), "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     HnW w;
     const size_t fp32_floats = hn_walk(packed, &w);
-    if (precision == 1) return hn_tc_forward(w, packed + fp32_floats, patches, n_patches, desc, workspace, st);
+    if (precision >= 1) return hn_tc_forward(w, packed + fp32_floats, patches, n_patches, desc, workspace, st, precision == 2);
     float* a = static_cast<float*>(workspace);
     float* b = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)n_patches * 32 * 1024 * sizeof(float), 256));
     const int n = n_patches;

@@ -34,7 +34,7 @@ size_t hn_tc_blob_floats();
 int hn_tc_pack_weights(const HnW& w, float* blob, cudaStream_t st);
 size_t hn_tc_workspace_bytes(int n_patches);
 int hn_tc_forward(const HnW& w, const float* blob, const float* patches, int n_patches, float* desc, void* workspace,
-                  cudaStream_t st);
+                  cudaStream_t st, int fp16_operands);
 // final 8x8 "valid" layer + BatchNorm + L2 norm on a flat [n][8192] input (hardnet.cu)
 int hn_run_final(const float* in, int n, const HnW& w, float* desc, cudaStream_t st);
 

@@ -166,7 +166,9 @@ BALF_API int balf_extract_patches_u8(const uint8_t* gray, int B, int H, int W, c
  * patches fp32 [N,1,32,32] -> desc fp32 [N,128].
  * precision: 0 = fp32 FFMA kernels (hardnet.cu),
  *            1 = the six 3x3 layers after the first as implicit-GEMM tcgen05 tiles, TF32 operands, fp32 accumulate
- *                in TMEM (hardnet_tc.cu); the workspace size depends on it. */
+ *                in TMEM (hardnet_tc.cu),
+ *            2 = the same kernels with fp16 operands (same 11-bit significand as TF32, half the bytes and half the MMAs;
+ *                activations are post-ReLU and saturate at 65504); the workspace size depends on the precision. */
 BALF_API int64_t balf_hardnet_raw_weight_count(void);
 BALF_API int64_t balf_hardnet_packed_weight_count(void);
 BALF_API int balf_hardnet_pack_weights(const float* raw, float* packed, void* stream);

@@ -24,7 +24,7 @@ sd = weights.detector_state_dict(0)
 hn_sd = weights.hardnet_state_dict(0)
 g = load_golden("r2_hardnet2048.npz")["out"]
 x = torch.rand(2048, 1, 32, 32, generator=torch.Generator().manual_seed(4321)).to(dev)
-for prec in ("tf32", "fp32"):
+for prec in ("fp16", "tf32", "fp32"):
     torch.manual_seed(0)
     hn = HardNet().eval().to(dev); hn.precision = prec
     with torch.inference_mode():

@@ -61,7 +61,7 @@ def detector_sd(detector):
     return {k: v.detach().clone() for k, v in detector.state_dict().items()}
 
 
-@pytest.fixture(scope="session", params=["tf32", "fp32"])
+@pytest.fixture(scope="session", params=["fp16", "tf32", "fp32"])
 def hardnet(request):
     """HardNet with the reference's random init (seed 0), once per precision of balf_hardnet_forward."""
     from balf_b200.third_party.hardnet.hardnet_pytorch import HardNet
