@@ -87,9 +87,9 @@ constexpr int kHeadN = 80;              // 65 logits padded to a legal UMMA N (m
 
 __host__ __device__ constexpr int tc_kin(int cin) { return cin < 8 ? 8 : cin; }
 // K columns per streamed block: the largest power-of-two divisor of K (>= 8) whose block is <= cap bytes
-__host__ __device__ constexpr int tc_kb(int rows, int K, int cap = 32768) {
+__host__ __device__ constexpr int tc_kb(int rows, int K, int cap = 32768, int eb = 4) {
     int kb = K;
-    while (kb > 8 && (kb * rows * 4 > cap || K % kb != 0)) kb /= 2;
+    while (kb > 32 / eb && (kb * rows * eb > cap || K % kb != 0)) kb /= 2;
     return kb;
 }
 __host__ __device__ constexpr int tc_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
@@ -173,7 +173,10 @@ template <int CIN, int C> struct BranchG {
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
-    __host__ __device__ static constexpr bool h16(int) { return false; }
+    // the GEMMs whose A operand is written by an epilogue run on fp16 operands (kind::f16): the same 11-bit significand as
+    // tf32, half the weight bytes to stream / keep resident, half the operand stores and MMAs.  conv.0 (A = the level input as
+    // loaded) and the token mixing (B = the [channel][token] activations) stay tf32.
+    __host__ __device__ static constexpr bool h16(int gi) { return gi == BG_PD1 || gi == BG_D1A || gi == BG_D1B || gi == BG_D2; }
 };
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
@@ -229,7 +232,7 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
     constexpr int ROWS = G::rows(GI), K = G::K(GI);
     constexpr bool BIAS = G::bias(GI), H16 = G::h16(GI);        // H16: A and B are fp16 chunk-major (8 halves per 16-byte chunk)
     static_assert(!(H16 && ASW), "fp16 operands use the chunk-major layout");
-    constexpr int KB = tc_kb(ROWS, K, G::cap), NBLK = K / KB;
+    constexpr int KB = tc_kb(ROWS, K, G::cap, H16 ? 2 : 4), NBLK = K / KB;
     constexpr uint32_t idesc = H16 ? make_idesc_f16(128, ROWS) : make_idesc_tf32(128, ROWS);
     constexpr uint32_t a_lbo = TM * 16u, b_lbo = (uint32_t)ROWS * 16u;
     constexpr int KSTEP = H16 ? 16 : 8, EPC = H16 ? 8 : 4;      // K per MMA, elements per 16-byte chunk
@@ -399,6 +402,19 @@ __device__ __forceinline__ void row_to_a(const float (&v)[CH], float* region, in
     for (int j = 0; j < CH / 4; ++j)
         *reinterpret_cast<float4*>(region + ((size_t)(col0 / 4 + j) * TM + row) * 4) =
             to_tf32(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+}
+
+// the same as fp16 (kind::f16 operand): 8 channels per 16-byte chunk, round to nearest, saturating at the fp16 range
+template <int CH>
+__device__ __forceinline__ void row_to_a16(const float (&v)[CH], float* region, int row, int col0) {
+    if (BALF_EXP & 2) { if (v[0] == 12345.678f) region[row] = v[1]; return; }
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(v[8 * j + 2 * e + 1]), "f"(v[8 * j + 2 * e]));
+        *reinterpret_cast<uint4*>(region + ((size_t)(col0 / 8 + j) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
 }
 
 // ---- "swizzled panel" layout of a [128 rows x C] tile (the K-major SWIZZLE_128B operand layout of tcgen05): panels of 32
@@ -886,7 +902,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             stats_of(v, sum, sq);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
-            row_to_a<CH>(v, s.region, row, col0);
+            row_to_a16<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma<NG, NTG>(grp);
@@ -903,7 +919,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
-            row_to_a<CH>(v, s.region, row, col0);
+            row_to_a16<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 7);
         sync_for_mma<NG, NTG>(grp);
@@ -953,7 +969,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 const unsigned long long b2 = pk2(mix_b1, mix_b1);
 #pragma unroll
                 for (int i = 0; i < SC; i += 2) upk2(mul2(pk2(y1[i], y1[i + 1]), add2(pk2(y2[i], y2[i + 1]), b2)), y2[i], y2[i + 1]);
-                row_to_a<SC>(y2, s.region, row, col0 + c);
+                row_to_a16<SC>(y2, s.region, row, col0 + c);
             }
         }
         TC_TRACE(plan, it, 13);
@@ -1592,12 +1608,17 @@ __global__ void tc_pack_kernel(const float* __restrict__ wT, int ld, int n0, int
 }
 // the same for fp16 GEMMs (TcGemm::h16): blocks of [rows x kb] halves, chunk-major with 8 halves per 16-byte chunk
 __global__ void tc_pack_h16_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real, int k_pad, int kb,
-                                   __half* __restrict__ dst) {
+                                   const float* __restrict__ gamma, const float* __restrict__ alpha, __half* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * k_pad) return;
     const int k = i / rows, n = i - k * rows;
     const int b = k / kb, kk = k - b * kb;
-    const float v = k < k_real ? wT[(size_t)k * ld + n0 + n] : 0.f;
+    float v = 0.f;
+    if (k < k_real) {
+        v = wT[(size_t)k * ld + n0 + n];
+        if (gamma) v *= gamma[k];
+        if (alpha) v *= alpha[n0 + n];
+    }
     dst[(size_t)b * rows * kb + (size_t)(kk >> 3) * rows * 8 + n * 8 + (kk & 7)] = __float2half_rn(v);
 }
 // bias columns of the last block: b' = (bias[n] + sum_k W[n][k] beta[k]) * alpha[n] + add[n], split into tf32 hi + lo
@@ -1630,7 +1651,7 @@ struct TcPlans {
 };
 
 static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768, bool h16 = false) {
-    const int kb = tc_kb(rows, K, cap);
+    const int kb = tc_kb(rows, K, cap, h16 ? 2 : 4);
     TcGemm& g = p.g[gi];
     g.goff = (uint32_t)off;
     g.nblk = (uint16_t)(K / kb);
@@ -1651,7 +1672,7 @@ static bool plan_matches(const TcPlan& p) {
     bool ok = true;
     for (int gi = 0; gi < G::count; ++gi) {
         const TcGemm& g = p.g[gi];
-        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap) && g.nblk * g.kb == G::K(gi) &&
+        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap, G::h16(gi) ? 2 : 4) && g.nblk * g.kb == G::K(gi) &&
              (g.bias != 0) == G::bias(gi) && (g.h16 != 0) == G::h16(gi) && gemm_bytes(g) == g_bytes<G>(gi) &&
              (g.goff - p.g[0].goff) * 4u == off;
         off += gemm_bytes(g);
@@ -1671,11 +1692,11 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
             p.base = base; p.ngemm = BG_COUNT; p.resident = c <= 64;       // mirrors BranchG::resident
             p.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                  // mirrors BranchG::nslot (checked by plan_matches)
             tc_add(p, BG_CONV0, off, c, cin, true);
-            tc_add(p, BG_PD1, off, c, c, true);
-            tc_add(p, BG_D1A, off, c, c, true);
-            tc_add(p, BG_D1B, off, c, c, true);
+            tc_add(p, BG_PD1, off, c, c, true, 32768, true);           // mirrors BranchG::h16
+            tc_add(p, BG_D1A, off, c, c, true, 32768, true);
+            tc_add(p, BG_D1B, off, c, c, true, 32768, true);
             tc_add(p, BG_WM, off, 64, 64, false);
-            tc_add(p, BG_D2, off, c, c, true);
+            tc_add(p, BG_D2, off, c, c, true, 32768, true);
         }
         TcPlan& m = P.merge[l];
         m = TcPlan{};
@@ -1714,8 +1735,8 @@ static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0
                         float* blob, cudaStream_t st) {
     const TcGemm& g = p.g[gi];
     const int k_pad = g.nblk * g.kb;
-    if (g.h16)      // (no folds on the fp16 GEMMs: dense2 of the multi-axis gMLP has neither a LayerNorm in front nor a scale)
-        tc_pack_h16_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb,
+    if (g.h16)
+        tc_pack_h16_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha,
                                                                       reinterpret_cast<__half*>(blob + g.goff));
     else
         tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha, blob + g.goff);
