@@ -188,7 +188,9 @@ template <int CIN, int C> struct MergeG {
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
     // stages 1-2: u' / v' cross HBM as fp16 tiles (same 11-bit significand as the tf32 operands they replace, half the
     // bytes of the HBM-bound merge kernels), so dense2 runs as kind::f16 on fp16 weights
-    __host__ __device__ static constexpr bool h16(int gi) { return C <= 64 && (gi == MG_PD2A || gi == MG_PD2B); }
+    // conv1 / conv2 (A operands written by the epilogues) run on fp16 operands at every stage
+    // and dense2 as well: u' / v' arrive as fp16 tiles (C <= 128) or are converted by the loader (C = 256)
+    __host__ __device__ static constexpr bool h16(int gi) { return gi != MG_CONV0; }
 };
 template <int C> struct HeadG {
     static constexpr int count = HG_COUNT;
@@ -198,7 +200,7 @@ template <int C> struct HeadG {
     __host__ __device__ static constexpr int rows(int gi) { return gi == HG_DENSE ? kHeadN : C; }
     __host__ __device__ static constexpr int K(int) { return C; }
     __host__ __device__ static constexpr bool bias(int) { return true; }
-    __host__ __device__ static constexpr bool h16(int) { return false; }
+    __host__ __device__ static constexpr bool h16(int) { return true; }
 };
 template <typename G> __host__ __device__ constexpr uint32_t g_bytes(int gi) {
     return (uint32_t)G::rows(gi) * (G::K(gi) * (G::h16(gi) ? 2u : 4u) + (G::bias(gi) ? 32u : 0u));
@@ -667,7 +669,7 @@ __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
 }
 
 // this thread's part (1 / TPR) of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
-template <int CIN, int TPR = 2>
+template <int CIN, int TPR = 2, bool H16 = false>       // H16: the operand is fp16 (two 4-channel chunks -> one 16-byte chunk of 8 halves)
 __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
                                                float* dst, int row, int half) {
     if constexpr (CIN < 8) {                       // NCHW network input: part 0 gathers the planes, part 1 zero-fills
@@ -689,8 +691,16 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
 #pragma unroll
             for (int j = 0; j < NB; j += 2) {
                 pair_unswap(v[j], v[j + 1]);
-                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j) * TM + row) * 4) = to_tf32(v[j]);
-                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j + 1) * TM + row) * 4) = to_tf32(v[j + 1]);
+                if constexpr (H16) {
+                    const float e[8] = {v[j].x, v[j].y, v[j].z, v[j].w, v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
+                    uint32_t h[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                    *reinterpret_cast<uint4*>(dst + ((size_t)((half * N + j0 + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+                } else {
+                    *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j) * TM + row) * 4) = to_tf32(v[j]);
+                    *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j + 1) * TM + row) * 4) = to_tf32(v[j + 1]);
+                }
             }
         }
     }
@@ -787,8 +797,8 @@ template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
     static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
-    static constexpr bool swz_out = C == 128;                      // u' / v' leave in the swizzled panel layout (bulk-copied by the merge kernel)
-    static constexpr bool h16_out = C <= 64;                       // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
+    static constexpr bool swz_out = false;                         // (round-1 layout: fp32 tiles in the swizzled panel layout)
+    static constexpr bool h16_out = C <= 128;                      // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
                                                                    // layout of the merge kernel's kind::f16 dense2, half the HBM bytes
     static constexpr int col_u = 0;
     static constexpr int col_y = park_u ? C : 0;
@@ -1138,8 +1148,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const uint32_t r2_addr = region_addr + (uint32_t)TM * C * 4;            // bulk_uv: u' tiles land here
     uint64_t* const ld_u = s.aux;
     uint64_t* const ld_v = &s.gdone[1];
-    constexpr uint32_t kTileBytes = (uint32_t)TM * C * 4;
-    const size_t tile_floats = (size_t)TM * C;
+    constexpr uint32_t kTileBytes = (uint32_t)TM * C * 2;                  // u' / v' tiles are fp16 (chunk-major)
+    const size_t tile_floats = (size_t)TM * C / 2;                         // ... i.e. TM * C / 2 floats apart
     uint32_t ld_phase = 0;
     const int ug = row >> 6, tok = row & 63;
     const int col0 = half * CH;
@@ -1189,7 +1199,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                 issue_linear_t<G, MG_CONV0>(ring, plan, region_addr, ones_addr, tm + Cfg::col_x0, true);
                 mbar_wait(ld_u, ld_phase & 1);
                 fence_after_sync();
-                issue_linear_t<G, MG_PD2A, true>(ring, plan, r2_addr, ones_addr, tm + Cfg::col_acc, true);
+                issue_linear_t<G, MG_PD2A>(ring, plan, r2_addr, ones_addr, tm + Cfg::col_acc, true);
                 commit(s.done);
             }
             wait_done_ring<G>(s.done, phase, ring, plan, w0);
@@ -1209,7 +1219,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             if (w0 && elect_one()) {
                 mbar_wait(ld_v, ld_phase & 1);
                 fence_after_sync();
-                issue_linear_t<G, MG_PD2B, true>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false);
+                issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false);
                 commit(s.done);
             }
             ++ld_phase;
@@ -1228,7 +1238,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             store_input_row<C>(pfu, s.region, row, half);
             fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
         } else {
-            load_input_row<C>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<C, 2, true>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
@@ -1237,7 +1247,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         if (InputPf<C>::enabled) store_input_row<C>(pfu, s.region, row, half);
-        else load_input_row<C>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        else load_input_row<C, 2, true>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
@@ -1270,7 +1280,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
-            row_to_a<CH>(v, s.region, row, col0);
+            row_to_a16<CH>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 10);
         sync_for_mma();
@@ -1286,7 +1296,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
         }
-        row_to_a<CH>(v, s.region, row, col0);
+        row_to_a16<CH>(v, s.region, row, col0);
         TC_TRACE(plan, it, 13);
         sync_for_mma();
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
@@ -1428,12 +1438,12 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
-            row_to_sw<CH, true>(v, regW, row, col0);
+            row_to_a16<CH>(v, regW, row, col0);
         }
         sync_for_mma();
         // ---- phase 2: conv1 -> LeakyReLU(0.2); q leaves, the next tile's u' / v' arrive (phase 1 released U and V)
         if (w0 && elect_one()) {
-            issue_linear_t<G, MG_RC1, true>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
+            issue_linear_t<G, MG_RC1>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
             commit(s.done);
             bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
             bulk_commit();
@@ -1447,10 +1457,10 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
         }
-        row_to_sw<CH, true>(v, regW, row, col0);
+        row_to_a16<CH>(v, regW, row, col0);
         sync_for_mma();
         // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, true>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
         row_to_sw<CH, false>(v, regW, row, col0);              // exact fp32: the squeeze sums below
@@ -1540,10 +1550,18 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
 #pragma unroll
             for (int j = 0; j < 8; j += 2) { pair_unswap(rv[j], rv[j + 1]); pair_unswap(qv[j], qv[j + 1]); }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + col0) + j0 + j);
-                const float4 o = make_float4(rv[j].x * sv.x + qv[j].x, rv[j].y * sv.y + qv[j].y, rv[j].z * sv.z + qv[j].z, rv[j].w * sv.w + qv[j].w);
-                *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j0 + j) * TM + row) * 4) = to_tf32(o);
+            for (int j = 0; j < 8; j += 2) {                  // two 4-channel chunks -> one fp16 chunk of 8 channels
+                float e[8];
+#pragma unroll
+                for (int u2 = 0; u2 < 2; ++u2) {
+                    const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + col0) + j0 + j + u2);
+                    e[4 * u2] = rv[j + u2].x * sv.x + qv[j + u2].x; e[4 * u2 + 1] = rv[j + u2].y * sv.y + qv[j + u2].y;
+                    e[4 * u2 + 2] = rv[j + u2].z * sv.z + qv[j + u2].z; e[4 * u2 + 3] = rv[j + u2].w * sv.w + qv[j + u2].w;
+                }
+                uint32_t h[4];
+#pragma unroll
+                for (int w2 = 0; w2 < 4; ++w2) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[w2]) : "f"(e[2 * w2 + 1]), "f"(e[2 * w2]));
+                *reinterpret_cast<uint4*>(s.region + ((size_t)((col0 / 4 + j0 + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
             }
         }
         sync_for_mma();
@@ -1554,7 +1572,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
             ld_row<CH>(lane_base + col0, v);
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
-            row_to_a<CH>(v, s.region, row, col0);
+            row_to_a16<CH>(v, s.region, row, col0);
         }
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
@@ -1704,16 +1722,16 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         m.nslot = c == 64 ? 3 : 2;                                     // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
         tc_add(m, MG_CONV0, off, c, cin, true, mcap);
-        tc_add(m, MG_PD2A, off, c, c, false, mcap, c <= 64);          // mirrors MergeG::h16
-        tc_add(m, MG_PD2B, off, c, c, true, mcap, c <= 64);
-        tc_add(m, MG_RC1, off, c, c, true, mcap);
-        tc_add(m, MG_RC2, off, c, c, true, mcap);
+        tc_add(m, MG_PD2A, off, c, c, false, mcap, true);             // mirrors MergeG::h16
+        tc_add(m, MG_PD2B, off, c, c, true, mcap, true);
+        tc_add(m, MG_RC1, off, c, c, true, mcap, true);
+        tc_add(m, MG_RC2, off, c, c, true, mcap, true);
     }
     TcPlan& h = P.head;
     h = TcPlan{};
     h.base = base; h.ngemm = HG_COUNT; h.resident = 0; h.nslot = 2;
-    tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true);
-    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true);
+    tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true, 32768, true);          // mirrors HeadG::h16
+    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true, 32768, true);
     P.floats = off;
     for (int l = 0; l < 4; ++l) {
         P.branch[l][0].trace = P.branch[l][1].trace = g_tc_trace_sel == 0 ? g_tc_trace : nullptr;
