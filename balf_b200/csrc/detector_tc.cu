@@ -42,6 +42,12 @@ using namespace umma;
 #ifndef BALF_EXP
 #define BALF_EXP 0
 #endif
+#ifndef BALF_MERGE32_CTAS
+#define BALF_MERGE32_CTAS 3
+#endif
+#ifndef BALF_RC16_MINC
+#define BALF_RC16_MINC 32     // conv1 / conv2 of the merge kernels run on fp16 operands for C > this
+#endif
 constexpr int TM = 128;                 // pixel rows per tile
 constexpr int NT2 = 256;                // threads per CTA (two per row)
 constexpr int kMaxSlot = 4;              // ring slots: per kernel family (G::nslot), sized from the shared-memory budget
@@ -190,7 +196,7 @@ template <int CIN, int C> struct MergeG {
     // bytes of the HBM-bound merge kernels), so dense2 runs as kind::f16 on fp16 weights
     // conv1 / conv2 (A operands written by the epilogues) run on fp16 operands at every stage
     // and dense2 as well: u' / v' arrive as fp16 tiles (C <= 128) or are converted by the loader (C = 256)
-    __host__ __device__ static constexpr bool h16(int gi) { return gi != MG_CONV0; }
+    __host__ __device__ static constexpr bool h16(int gi) { return gi == MG_PD2A || gi == MG_PD2B || ((gi == MG_RC1 || gi == MG_RC2) && C > BALF_RC16_MINC); }
 };
 template <int C> struct HeadG {
     static constexpr int count = HG_COUNT;
@@ -1338,7 +1344,7 @@ template <int CIN, int C> struct MergeBulkCfg {
     static constexpr uint32_t region = 3 * uv_bytes + 2 * tile_bytes + xbytes;   // U, V, R16 (fp16) | W, Q (fp32) | X
     static constexpr int col_acc = 0, col_x0 = C;
     static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
-    static constexpr int min_ctas = C <= 32 ? 3 : 1;
+    static constexpr int min_ctas = C <= 32 ? BALF_MERGE32_CTAS : 1;
 };
 
 template <int CIN, int C>
@@ -1438,12 +1444,12 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
-            row_to_a16<CH>(v, regW, row, col0);
+            if constexpr (G::h16(MG_RC1)) row_to_a16<CH>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         }
         sync_for_mma();
         // ---- phase 2: conv1 -> LeakyReLU(0.2); q leaves, the next tile's u' / v' arrive (phase 1 released U and V)
         if (w0 && elect_one()) {
-            issue_linear_t<G, MG_RC1>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
+            issue_linear_t<G, MG_RC1, !G::h16(MG_RC1)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
             commit(s.done);
             bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
             bulk_commit();
@@ -1457,10 +1463,10 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
         }
-        row_to_a16<CH>(v, regW, row, col0);
+        if constexpr (G::h16(MG_RC1)) row_to_a16<CH>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         sync_for_mma();
         // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, !G::h16(MG_RC2)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
         row_to_sw<CH, false>(v, regW, row, col0);              // exact fp32: the squeeze sums below
@@ -1724,8 +1730,8 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         tc_add(m, MG_CONV0, off, c, cin, true, mcap);
         tc_add(m, MG_PD2A, off, c, c, false, mcap, true);             // mirrors MergeG::h16
         tc_add(m, MG_PD2B, off, c, c, true, mcap, true);
-        tc_add(m, MG_RC1, off, c, c, true, mcap, true);
-        tc_add(m, MG_RC2, off, c, c, true, mcap, true);
+        tc_add(m, MG_RC1, off, c, c, true, mcap, c > BALF_RC16_MINC);
+        tc_add(m, MG_RC2, off, c, c, true, mcap, c > BALF_RC16_MINC);
     }
     TcPlan& h = P.head;
     h = TcPlan{};
