@@ -205,15 +205,17 @@ def kernel_work(name, images):
         if c in lv:
             cin, ch, px = level_dims()[lv[c]]
             n = images * px
+            uv = 2 if ch <= 128 else 4                   # bytes per element of u' / v' in HBM (fp16 tiles at stages 1-3)
+            rb = 2 if ch <= 64 else 4                    # ... of r (fp16 tiles at stages 1-2); q and the level input are fp32
             if "branch" in name:                       # half of dense1, branch dense1, token mix, dense2; x in, u' out
-                return n * (2 * cin * ch + 2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch), n * 4 * (cin + ch)
+                return n * (2 * cin * ch + 2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch), n * (4 * cin + uv * ch)
             if "merge" in name:                        # conv.0, dense2 (2C->C), conv1, conv2; x, u', v' in, r, q out
-                return n * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch), n * 4 * (cin + 4 * ch)
+                return n * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch), n * (4 * cin + 2 * uv * ch + rb * ch + 4 * ch)
         if name == "det_head":                         # r, q in; prob out (64 values per 8x8 cell)
             n = images * level_dims()[3][2]
             return n * (2 * 256 * 256 + 2 * 256 * 65), n * 4 * (2 * 256 + 64)
-        if name == "det_pool":                         # r, q in, pooled out, stages 1-3
-            return 0, sum(images * px * 4 * (2 * ch + ch // 4) for _, ch, px in level_dims()[:3])
+        if name == "det_pool":                         # r (fp16 at stages 1-2), q in, pooled out, stages 1-3
+            return 0, sum(images * px * ((2 if ch <= 64 else 4) * ch + 4 * ch + ch) for _, ch, px in level_dims()[:3])
         return 0, 0
     if name.startswith("nms_windowed"):
         return 0, images * (4 * H * W)
@@ -588,7 +590,9 @@ def main():
     line = {
         "metric": METRIC, "value": images * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": det.resolve_precision(a.nms), "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"tf32": "fp16/tf32 operands (11-bit significand), fp32 accumulate"}.get(det.resolve_precision(a.nms), det.resolve_precision(a.nms)),
+        "data": "synthetic",
         "config": config_of(a),
         "clocks": clocks,
         "e2e": {"value": images * a.steps / (t_e2e * 1e-3), "unit": "images/s", "passes_ms": [round(x, 3) for x in e2e_passes],
@@ -597,7 +601,10 @@ def main():
         "roofline": roof,
         "roofline_nms": roof_nms,
         "detector": {"ms_per_step": det_ms, "tflops": det_tf,
-                     "frac_of_tf32_peak": det_tf / (pk["tensor"] / 2) if det_tf else None, "peak_source": pk["src"]},
+                     "frac_of_tf32_peak": det_tf / (pk["tensor"] / 2) if det_tf else None,
+                     "frac_of_f16_peak": det_tf / pk["tensor"] if det_tf else None,
+                     "note": "most GEMMs run as kind::f16 (fp16 operands), conv.0 / token mixing / biases as kind::tf32",
+                     "peak_source": pk["src"]},
         "kernels": kernels,
         "cfg3": {"workload": "configs[3]: 1024 synthetic 1024x1024 images strong-scaled over %d rank(s), detector + windowed NMS + "
                              "top-2048, records all-gathered per 64-image chunk (balf_gather_keypoints, NCCL)" % world,
