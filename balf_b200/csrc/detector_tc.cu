@@ -173,16 +173,15 @@ __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
 // (the serial issue path sits on the critical path of every phase of every tile).  Must mirror tc_build_plans.
 template <int CIN, int C> struct BranchG {
     static constexpr int count = BG_COUNT;
-    static constexpr bool resident = C <= 64;       // C = 64: 100 KB of weights shared by the two tile groups of a CTA
+    static constexpr bool resident = C <= 128;      // fp16 weights: 60 KB at C = 64 (shared by two tile groups), 172 KB at C = 128
     static constexpr int cap = 32768;
-    static constexpr int nslot = C == 64 ? 3 : C == 128 ? 4 : 2;
+    static constexpr int nslot = C == 256 ? 3 : 2;
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
-    // the GEMMs whose A operand is written by an epilogue run on fp16 operands (kind::f16): the same 11-bit significand as
-    // tf32, half the weight bytes to stream / keep resident, half the operand stores and MMAs.  conv.0 (A = the level input as
-    // loaded) and the token mixing (B = the [channel][token] activations) stay tf32.
-    __host__ __device__ static constexpr bool h16(int gi) { return gi == BG_PD1 || gi == BG_D1A || gi == BG_D1B || gi == BG_D2; }
+    // every GEMM runs on fp16 operands (kind::f16): the same 11-bit significand as tf32, half the weight bytes to stream / keep
+    // resident, half the operand bytes and MMAs.  (The network-input stage computes conv.0, K = 3, on the CUDA cores.)
+    __host__ __device__ static constexpr bool h16(int gi) { return gi != BG_CONV0 || CIN >= 8; }
 };
 template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
@@ -196,7 +195,9 @@ template <int CIN, int C> struct MergeG {
     // bytes of the HBM-bound merge kernels), so dense2 runs as kind::f16 on fp16 weights
     // conv1 / conv2 (A operands written by the epilogues) run on fp16 operands at every stage
     // and dense2 as well: u' / v' arrive as fp16 tiles (C <= 128) or are converted by the loader (C = 256)
-    __host__ __device__ static constexpr bool h16(int gi) { return gi == MG_PD2A || gi == MG_PD2B || ((gi == MG_RC1 || gi == MG_RC2) && C > BALF_RC16_MINC); }
+    __host__ __device__ static constexpr bool h16(int gi) {
+        return gi == MG_PD2A || gi == MG_PD2B || (gi == MG_CONV0 && CIN >= 8) || ((gi == MG_RC1 || gi == MG_RC2) && C > BALF_RC16_MINC);
+    }
 };
 template <int C> struct HeadG {
     static constexpr int count = HG_COUNT;
@@ -285,15 +286,16 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
         w_addr = r.wsm + slot * p.slot_bytes;
     }
     fence_after_sync();
-    constexpr uint32_t idesc = make_idesc_tf32(64, C);
+    // fp16 operands: A = the 64 x 64 mixing matrix, B = the unit's activations [channel][token], 8 tokens per 16-byte chunk
+    constexpr uint32_t idesc = make_idesc_f16(64, C);
     constexpr uint32_t b_lbo = (uint32_t)CP * 16u;
     const uint64_t w_desc = desc_of(w_addr, 1024u);
 #pragma unroll
     for (uint32_t u = 0; u < 2; ++u) {
         const uint64_t y_desc = desc_of(y_addr + u * y_stride, b_lbo);
 #pragma unroll
-        for (uint32_t k8 = 0; k8 < 8; ++k8)
-            mma_tf32(d_tmem + ((u * 16u) << 16), w_desc + ((k8 * 2u * 1024u) >> 4), y_desc + ((k8 * 2u * b_lbo) >> 4), idesc, k8 > 0);
+        for (uint32_t ks = 0; ks < 4; ++ks)
+            mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((ks * 2u * b_lbo) >> 4), idesc, ks > 0);
     }
     if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
 }
@@ -741,7 +743,7 @@ __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, s
         }
     }
 }
-template <int CIN, bool PAIR = true, int TPR = 2>
+template <int CIN, bool PAIR = true, int TPR = 2, bool H16 = false>
 __device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, float* dst, int row, int half) {
     if constexpr (CIN < 8) {
         if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
@@ -751,8 +753,16 @@ __device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, flo
         for (int j = 0; j < N; j += 2) {
             float4 c0 = pf.v[j], c1 = pf.v[j + 1];
             if constexpr (PAIR) pair_unswap(c0, c1);
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j) * TM + row) * 4) = to_tf32(c0);
-            *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j + 1) * TM + row) * 4) = to_tf32(c1);
+            if constexpr (H16) {                 // two 4-channel chunks -> one 16-byte chunk of 8 halves
+                const float e[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                uint32_t h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                *reinterpret_cast<uint4*>(dst + ((size_t)((half * N + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+            } else {
+                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j) * TM + row) * 4) = to_tf32(c0);
+                *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j + 1) * TM + row) * 4) = to_tf32(c1);
+            }
         }
     }
 }
@@ -800,8 +810,8 @@ template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
     static constexpr int NTG = TM * TPR;                           // threads per tile group
     static constexpr int CH = C / TPR;
     static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
-    static constexpr uint32_t y_stride = (CP * 64 + 16) * 4;       // bytes between the two units' operands
-    static constexpr uint32_t region = (2 * y_stride > (uint32_t)TM * C * 4 ? 2 * y_stride : (uint32_t)TM * C * 4);
+    static constexpr uint32_t y_stride = (CP * 64 + 16) * 2;       // bytes between the two units' (fp16) mixing operands
+    static constexpr uint32_t region = ((2 * y_stride > (uint32_t)TM * C * 2 ? 2 * y_stride : (uint32_t)TM * C * 2) + 127u) / 128u * 128u;
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
     static constexpr bool swz_out = false;                         // (round-1 layout: fp32 tiles in the swizzled panel layout)
     static constexpr bool h16_out = C <= 128;                      // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
@@ -894,14 +904,14 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
             if (InputPf<CIN, TPR>::enabled) {
-                store_input_row<CIN, true, TPR>(pf, s.region, row, half);
+                store_input_row<CIN, true, TPR, true>(pf, s.region, row, half);
                 if (t + vgrid < ntiles) {
                     bool vld; int im, px;
                     coords(t + vgrid, vld, im, px);
                     fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
                 }
             } else {
-                load_input_row<CIN, TPR>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+                load_input_row<CIN, TPR, true>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
             }
             TC_TRACE(plan, it, 1);
             sync_for_mma<NG, NTG>(grp);
@@ -956,7 +966,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
-            float* yt = s.region + (size_t)ug * (Cfg::y_stride / 4) + (size_t)(tok >> 2) * (Cfg::CP * 4) + (tok & 3) + (size_t)col0 * 4;
+            __half* yt = reinterpret_cast<__half*>(s.region) + (size_t)ug * (Cfg::y_stride / 2) + (size_t)(tok >> 3) * (Cfg::CP * 8) + (tok & 7) + (size_t)col0 * 8;
             norm_row<CH>(v, rstd, shift);
 #pragma unroll
             for (int i = 0; i < CH; i += 2) {
@@ -964,8 +974,10 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 float o0, o1;
                 upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), o0, o1);
                 if (!(BALF_EXP & 2) || o0 == 12345.678f) {
-                    yt[(size_t)i * 4] = to_tf32(o0);
-                    yt[(size_t)(i + 1) * 4] = to_tf32(o1);
+                    uint32_t h;
+                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(o1), "f"(o0));
+                    reinterpret_cast<unsigned short*>(yt)[(size_t)i * 8] = (unsigned short)(h & 0xFFFFu);
+                    reinterpret_cast<unsigned short*>(yt)[(size_t)(i + 1) * 8] = (unsigned short)(h >> 16);
                 }
             }
         }
@@ -1187,14 +1199,14 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
         if (InputPf<CIN>::enabled) {
-            store_input_row<CIN>(pf, s.region, row, half);
+            store_input_row<CIN, true, 2, true>(pf, s.region, row, half);
             if (t + (int)gridDim.x < ntiles) {
                 bool vld; int im, px;
                 coords(t + gridDim.x, vld, im, px);
                 fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
             }
         } else {
-            load_input_row<CIN>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<CIN, 2, true>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
@@ -1400,7 +1412,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         float v[CH], x0[CH];
         // ---- phase 1: acc = dense2([u', v']) (+ conv.0(x) at CIN >= 8) on the tensor core | x0 on the CUDA cores at CIN < 8
         if constexpr (!Cfg::cc0) {
-            store_input_row<CIN, false>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
+            store_input_row<CIN, false, 2, true>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
             sync_for_mma();
         }
         if (w0 && elect_one()) {
@@ -1713,13 +1725,13 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         for (int b = 0; b < 2; ++b) {
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
-            p.base = base; p.ngemm = BG_COUNT; p.resident = c <= 64;       // mirrors BranchG::resident
-            p.nslot = c == 64 ? 3 : c == 128 ? 4 : 2;                  // mirrors BranchG::nslot (checked by plan_matches)
-            tc_add(p, BG_CONV0, off, c, cin, true);
+            p.base = base; p.ngemm = BG_COUNT; p.resident = c <= 128;      // mirrors BranchG::resident
+            p.nslot = c == 256 ? 3 : 2;                                // mirrors BranchG::nslot (checked by plan_matches)
+            tc_add(p, BG_CONV0, off, c, cin, true, 32768, a.dims[l] >= 8);
             tc_add(p, BG_PD1, off, c, c, true, 32768, true);           // mirrors BranchG::h16
             tc_add(p, BG_D1A, off, c, c, true, 32768, true);
             tc_add(p, BG_D1B, off, c, c, true, 32768, true);
-            tc_add(p, BG_WM, off, 64, 64, false);
+            tc_add(p, BG_WM, off, 64, 64, false, 32768, true);
             tc_add(p, BG_D2, off, c, c, true, 32768, true);
         }
         TcPlan& m = P.merge[l];
@@ -1727,7 +1739,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
         m.nslot = c == 64 ? 3 : 2;                                     // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
-        tc_add(m, MG_CONV0, off, c, cin, true, mcap);
+        tc_add(m, MG_CONV0, off, c, cin, true, mcap, a.dims[l] >= 8);
         tc_add(m, MG_PD2A, off, c, c, false, mcap, true);             // mirrors MergeG::h16
         tc_add(m, MG_PD2B, off, c, c, true, mcap, true);
         tc_add(m, MG_RC1, off, c, c, true, mcap, c > BALF_RC16_MINC);
