@@ -187,7 +187,7 @@ template <int CIN, int C> struct MergeG {
     static constexpr int count = MG_COUNT;
     static constexpr bool resident = C <= 64;       // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions
     static constexpr int cap = 32768;
-    static constexpr int nslot = C == 64 ? 3 : 2;           // C = 128: two operand regions leave room for two slots
+    static constexpr int nslot = C == 256 ? 2 : 3;          // C = 128: 96 KB of operand regions leave room for three 36 KB slots
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
@@ -821,7 +821,7 @@ template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
     static constexpr int ncols = NG_ * tc_cols(col_y + 2 * C) > 512 ? col_y + 2 * C : tc_cols(col_y + 2 * C);   // TMEM columns per group
     static constexpr int groups = NG_;                             // tile groups per CTA (shared resident weights)
     static constexpr uint32_t xch = TPR == 1 ? 0u : 2u * TPR * TM * 8u;   // LayerNorm exchange buffers per group
-    static constexpr int SC = TPR == 1 ? 16 : TPR == 4 ? 32 : (CH > 64 ? 64 : CH);   // sub-chunks bound the live registers
+    static constexpr int SC = TPR == 1 ? 16 : TPR == 4 ? (CH < 32 ? CH : 32) : (CH > 64 ? 64 : CH);   // sub-chunks bound the live registers
 };
 template <int C> struct BranchCfg : BranchCfgT<C, 2, (C <= 32 ? 4 : C <= 64 ? 2 : 1)> {};
 
@@ -1093,6 +1093,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
 template <int C, int V> struct BranchSel { using Cfg = BranchCfg<C>; };
 template <> struct BranchSel<32, 1> { using Cfg = BranchCfgT<32, 1, 5>; };
 template <> struct BranchSel<32, 2> { using Cfg = BranchCfgT<32, 1, 5, true>; };
+template <> struct BranchSel<64, 1> { using Cfg = BranchCfgT<64, 4, 2>; };
 template <> struct BranchSel<128, 1> { using Cfg = BranchCfgT<128, 4, 1>; };
 template <> struct BranchSel<256, 1> { using Cfg = BranchCfgT<256, 4, 1>; };
 
@@ -1138,7 +1139,7 @@ template <int C> struct MergeCfg {
     // C = 128: u' and v' (swizzled panel tiles, tf32-rounded by the branch kernels) arrive by bulk copy -- u' into a second
     // region a tile ahead, v' into the first as soon as conv.0 has released it -- and conv.0 shares its phase with dense2(u')
     static constexpr bool bulk_uv = C == 128;
-    static constexpr uint32_t region = (uint32_t)TM * C * 4 * (bulk_uv ? 2 : 1);
+    static constexpr uint32_t region = (uint32_t)TM * C * 4 + (bulk_uv ? (uint32_t)TM * C * 2 : 0u);   // + the fp16 u' tile
     static constexpr int col_x0 = 0, col_acc = C;
     static constexpr int ncols = tc_cols(2 * C);
     static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
@@ -1737,7 +1738,7 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        m.nslot = c == 64 ? 3 : 2;                                     // mirrors MergeG::nslot / MergeG::cap
+        m.nslot = c == 256 ? 2 : 3;                                    // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
         tc_add(m, MG_CONV0, off, c, cin, true, mcap, a.dims[l] >= 8);
         tc_add(m, MG_PD2A, off, c, c, false, mcap, true);             // mirrors MergeG::h16
@@ -1878,7 +1879,7 @@ static int tc_run_branches(const float* xin, const DownW& w, const TcPlans& P, i
         if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
         if (var == 2) return tc_launch_branches<CIN, C, 2>(xin, w, P, level, g, ntiles, u, v, st);
     }
-    if constexpr (C == 128 || C == 256) {
+    if constexpr (C == 64 || C == 128 || C == 256) {
         if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
     }
     return tc_launch_branches<CIN, C, 0>(xin, w, P, level, g, ntiles, u, v, st);
