@@ -150,7 +150,7 @@ def detector_pack_weights(raw, arch):
     return packed
 
 
-PRECISIONS = {"fp32": 0, "tf32": 1}
+PRECISIONS = {"fp32": 0, "tf32": 1, "f16x3": 2}     # f16x3: tensor cores on fp16 hi + lo operand pairs (three MMAs per product), fp32-class results
 
 
 def detector_forward(x, packed, arch, precision="fp32", want_logits=True):

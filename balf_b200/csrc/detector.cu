@@ -373,9 +373,10 @@ __global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------ pool (stages 1-3)
 // out[b, py, px, :] = max over the 2x2 window of (r * s + q)
+// swz: 0 = r, q channels-last; 1 = q in swizzled-panel tiles, r in fp16 tiles; 2 = r and q in swizzled-panel tiles (split precision)
 template <int C>
 __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict__ q, const float* __restrict__ scale,
-                            int h, int w, float* __restrict__ out, size_t total, bool swz) {
+                            int h, int w, float* __restrict__ out, size_t total, int swz) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     constexpr int Q = C / 4;
@@ -399,7 +400,7 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             const size_t cs = swz ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
                                   : ((p * C) >> 2) + c4;
             float4 rv;
-            if (swz) {
+            if (swz == 1) {
                 // r of those stages is an fp16 tile [C / 8 chunks][128 pixels][8 halves] (tc_merge_bulk_kernel)
                 const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r) + (p - rowi) * C +
                                                                      (size_t)(c4 >> 1) * (128 * 8) + rowi * 8 + (c4 & 1) * 4));
@@ -621,7 +622,7 @@ static int run_se(const Workspace& ws, const DownW& w, int Bc, int npix, int par
 }
 
 template <int C>
-static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st, bool swz = false) {
+static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st, int swz = 0) {
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
     {
         ProfScope p("det_pool", st);
@@ -724,7 +725,7 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
     BALF_REQUIRE(B > 0 && Hp > 0 && Wp > 0, "B, Hp, Wp must be positive");
     BALF_REQUIRE(Hp % 64 == 0 && Wp % 64 == 0, "input %dx%d: height and width must be multiples of 64 "
                  "(3 max-pools x 8x8 grid/block tokens; pad with mod_padding_symmetric)", Hp, Wp);
-    BALF_REQUIRE(precision == 0 || precision == 1, "precision %d is not built in this library (0 = fp32, 1 = tf32)", precision);
+    BALF_REQUIRE(precision >= 0 && precision <= 2, "precision %d is not built in this library (0 = fp32, 1 = tf32-class, 2 = f16x3)", precision);
     const balf_detector_arch& a = *arch;
     const int chunk = chunk_images(a, B, Hp, Wp);
     BALF_REQUIRE(workspace_bytes >= ws_layout(a, chunk, Hp, Wp, nullptr, nullptr), "workspace too small");
@@ -740,31 +741,32 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
         const float* xb = x + (size_t)b0 * 3 * Hp * Wp;
         // precision 1: tensor-core kernels (detector_tc.cu); g_tc_mask (debug hook) can send single
         // stages back to the fp32 kernels -- both paths share the workspace formats.
-        const int tcm = precision == 1 ? g_tc_mask : 0;
+        const int tcm = precision >= 1 ? g_tc_mask : 0;
+        const int px = precision == 2 ? 1 : 0;                 // split precision: fp16 hi + lo operands, three MMAs per product
         const DownW* d = w.down;
         int tiles = 0;
         if (tcm & 1) {
-            if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<32>(ws, d[0], Bc, Hp * Wp, Hp * Wp / 64, st)) return e;
         } else if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
-        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) != 0)) return e;
+        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) ? 1 + px : 0)) return e;
         if (tcm & 2) {
-            if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;
         } else if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
-        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) != 0)) return e;
+        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) ? 1 + px : 0)) return e;
         if (tcm & 4) {
-            if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<128>(ws, d[2], Bc, Hp * Wp / 16, Hp * Wp / 1024, st)) return e;
         } else if (int e = run_level<64, 128, 64, 64>(ws.pooled[1], false, w.down[2], Bc, Hp / 4, Wp / 4, ws, st, &tiles)) return e;
         if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st)) return e;
         if (tcm & 8) {
-            if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st)) return e;
+            if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<256>(ws, d[3], Bc, hc * wc, hc * wc / 64, st)) return e;
         } else if (int e = run_level<128, 256, 64, 32>(ws.pooled[2], false, w.down[3], Bc, hc, wc, ws, st, &tiles)) return e;
         if (tcm & 16) {
             if (int e = tc_run_head(ws.r, ws.q, ws.scale, d[3], w.head, a, tc_blob, Bc, hc, wc,
-                                    logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp, st)) return e;
+                                    logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp, st, px)) return e;
             continue;
         }
         dim3 gh(hc * wc / 32, Bc);

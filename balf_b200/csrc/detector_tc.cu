@@ -60,7 +60,10 @@ struct TcGemm {
     uint16_t kb;          // K columns per block
     uint16_t bias;        // 1: the last block carries 8 extra K columns (bias hi, bias lo, 0 ...)
     uint16_t h16;         // 1: the K columns are fp16 (kind::f16 MMAs, 8 per 16-byte chunk); the bias columns stay tf32
+                          // 2: split precision ("f16x3"): every block holds its kb columns twice, fp16 hi then fp16 lo = fp16(w - hi)
 };
+// bytes per K element of a packed operand
+__host__ __device__ constexpr uint32_t tc_eb(int h16) { return h16 == 1 ? 2u : 4u; }
 struct TcPlan {
     const float* base;
     TcGemm g[kMaxGemm];
@@ -100,10 +103,10 @@ __host__ __device__ constexpr int tc_kb(int rows, int K, int cap = 32768, int eb
 }
 __host__ __device__ constexpr int tc_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
 __host__ __device__ inline uint32_t gemm_block_bytes(const TcGemm& g, uint32_t b) {
-    return (uint32_t)g.rows * (g.kb * (g.h16 ? 2u : 4u) + ((g.bias && b + 1 == g.nblk) ? 32u : 0u));
+    return (uint32_t)g.rows * (g.kb * tc_eb(g.h16) + ((g.bias && b + 1 == g.nblk) ? 32u : 0u));
 }
 __host__ __device__ inline uint32_t gemm_bytes(const TcGemm& g) {
-    return (uint32_t)g.rows * ((uint32_t)g.kb * g.nblk * (g.h16 ? 2u : 4u) + (g.bias ? 32u : 0u));
+    return (uint32_t)g.rows * ((uint32_t)g.kb * g.nblk * tc_eb(g.h16) + (g.bias ? 32u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------ weight ring (thread 0)
@@ -131,7 +134,7 @@ __device__ __forceinline__ void ring_build_schedule(uint2* sched, const TcPlan& 
     for (int gi = 0; gi < p.ngemm; ++gi) {
         const TcGemm g = p.g[gi];
         for (uint32_t b = 0; b < g.nblk; ++b)
-            sched[n++] = make_uint2(g.goff + b * (uint32_t)g.rows * g.kb / (g.h16 ? 2u : 1u), gemm_block_bytes(g, b));
+            sched[n++] = make_uint2(g.goff + b * (uint32_t)g.rows * g.kb / (g.h16 == 1 ? 2u : 1u), gemm_block_bytes(g, b));
     }
     *count = n;
 }
@@ -171,11 +174,14 @@ __device__ __forceinline__ void ring_load_all(Ring& r, const TcPlan& p) {
 // ---- compile-time plans.  Every GEMM of a kernel is fixed by its template parameters, so thread 0's issue path is
 // straight-line code: descriptors are a per-kernel base plus immediates instead of per-MMA address arithmetic
 // (the serial issue path sits on the critical path of every phase of every tile).  Must mirror tc_build_plans.
-template <int CIN, int C> struct BranchG {
+// PX = 1: the split-precision plans ("f16x3"): every operand is an fp16 hi + fp16 lo pair and every product runs as
+// hi*hi + lo*hi + hi*lo on the tensor core (fp32-class results, 3x the MMAs, 2x the operand bytes); see issue_linear_t.
+template <int CIN, int C, int PX = 0> struct BranchG {
     static constexpr int count = BG_COUNT;
-    static constexpr bool resident = C <= 128;      // fp16 weights: 60 KB at C = 64 (shared by two tile groups), 172 KB at C = 128
+    static constexpr bool x3 = PX != 0;
+    static constexpr bool resident = PX ? C <= 64 : C <= 128;   // fp16 weights: 60 KB at C = 64 (shared by two tile groups), 172 KB at C = 128
     static constexpr int cap = 32768;
-    static constexpr int nslot = C == 256 ? 3 : 2;
+    static constexpr int nslot = PX ? (C == 256 ? 2 : 3) : (C == 256 ? 3 : 2);
     __host__ __device__ static constexpr int rows(int gi) { return gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == BG_CONV0 ? tc_kin(CIN) : gi == BG_WM ? 64 : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != BG_WM; }
@@ -183,11 +189,12 @@ template <int CIN, int C> struct BranchG {
     // resident, half the operand bytes and MMAs.  (The network-input stage computes conv.0, K = 3, on the CUDA cores.)
     __host__ __device__ static constexpr bool h16(int gi) { return gi != BG_CONV0 || CIN >= 8; }
 };
-template <int CIN, int C> struct MergeG {
+template <int CIN, int C, int PX = 0> struct MergeG {
     static constexpr int count = MG_COUNT;
-    static constexpr bool resident = C <= 64;       // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions
+    static constexpr bool x3 = PX != 0;
+    static constexpr bool resident = PX ? C <= 32 : C <= 64;   // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions
     static constexpr int cap = 32768;
-    static constexpr int nslot = C == 256 ? 2 : 3;          // C = 128: 96 KB of operand regions leave room for three 36 KB slots
+    static constexpr int nslot = PX ? (C == 64 ? 3 : 2) : (C == 256 ? 2 : 3);   // C = 128: 96 KB of operand regions leave room for three 36 KB slots
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
     __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
@@ -196,11 +203,12 @@ template <int CIN, int C> struct MergeG {
     // conv1 / conv2 (A operands written by the epilogues) run on fp16 operands at every stage
     // and dense2 as well: u' / v' arrive as fp16 tiles (C <= 128) or are converted by the loader (C = 256)
     __host__ __device__ static constexpr bool h16(int gi) {
-        return gi == MG_PD2A || gi == MG_PD2B || (gi == MG_CONV0 && CIN >= 8) || ((gi == MG_RC1 || gi == MG_RC2) && C > BALF_RC16_MINC);
+        return gi == MG_PD2A || gi == MG_PD2B || (gi == MG_CONV0 && CIN >= 8) || ((gi == MG_RC1 || gi == MG_RC2) && (PX || C > BALF_RC16_MINC));
     }
 };
-template <int C> struct HeadG {
+template <int C, int PX = 0> struct HeadG {
     static constexpr int count = HG_COUNT;
+    static constexpr bool x3 = PX != 0;
     static constexpr bool resident = false;
     static constexpr int cap = 32768;
     static constexpr int nslot = 2;
@@ -209,8 +217,10 @@ template <int C> struct HeadG {
     __host__ __device__ static constexpr bool bias(int) { return true; }
     __host__ __device__ static constexpr bool h16(int) { return true; }
 };
+// packing mode of GEMM gi (TcGemm::h16) and its bytes per K element
+template <typename G> __host__ __device__ constexpr int g_mode(int gi) { return G::h16(gi) ? (G::x3 ? 2 : 1) : 0; }
 template <typename G> __host__ __device__ constexpr uint32_t g_bytes(int gi) {
-    return (uint32_t)G::rows(gi) * (G::K(gi) * (G::h16(gi) ? 2u : 4u) + (G::bias(gi) ? 32u : 0u));
+    return (uint32_t)G::rows(gi) * (G::K(gi) * tc_eb(g_mode<G>(gi)) + (G::bias(gi) ? 32u : 0u));
 }
 template <typename G> __host__ __device__ constexpr uint32_t g_off(int gi) { uint32_t o = 0; for (int i = 0; i < gi; ++i) o += g_bytes<G>(i); return o; }
 
@@ -240,8 +250,11 @@ template <typename G, int GI, bool ASW = false>
 __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_t a_addr, uint32_t ones_addr, uint32_t d_tmem, bool first) {
     constexpr int ROWS = G::rows(GI), K = G::K(GI);
     constexpr bool BIAS = G::bias(GI), H16 = G::h16(GI);        // H16: A and B are fp16 chunk-major (8 halves per 16-byte chunk)
+    // X3 (split precision): the A region holds K / 8 hi chunks followed by K / 8 lo chunks, a weight block its KB / 8 hi chunks
+    // followed by KB / 8 lo chunks; D += A_hi W_hi + A_lo W_hi + A_hi W_lo (the lo * lo term is below fp32 resolution)
+    constexpr bool X3 = H16 && G::x3;
     static_assert(!(H16 && ASW), "fp16 operands use the chunk-major layout");
-    constexpr int KB = tc_kb(ROWS, K, G::cap, H16 ? 2 : 4), NBLK = K / KB;
+    constexpr int KB = tc_kb(ROWS, K, G::cap, (int)tc_eb(g_mode<G>(GI))), NBLK = K / KB;
     constexpr uint32_t idesc = H16 ? make_idesc_f16(128, ROWS) : make_idesc_tf32(128, ROWS);
     constexpr uint32_t a_lbo = TM * 16u, b_lbo = (uint32_t)ROWS * 16u;
     constexpr int KSTEP = H16 ? 16 : 8, EPC = H16 ? 8 : 4;      // K per MMA, elements per 16-byte chunk
@@ -250,7 +263,7 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
     for (int b = 0; b < NBLK; ++b) {
         uint32_t w_addr, slot = 0;
         if (G::resident) {
-            w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * (H16 ? 2u : 4u);
+            w_addr = r.wsm + g_off<G>(GI) + (uint32_t)b * ROWS * KB * tc_eb(g_mode<G>(GI));
         } else {
             ring_top_up<G::nslot>(r, p);
             slot = r.cslot;
@@ -266,9 +279,13 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
             const uint32_t a_off = ASW ? (kchunk / 8u) * (TM * 128u) + (kchunk % 8u) * 16u : kchunk * a_lbo;
             if (H16) mma_f16(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)ks * 2u * b_lbo) >> 4), idesc, !(first && b == 0 && ks == 0));
             else mma_tf32(d_tmem, a_desc + (a_off >> 4), b_desc + (((uint32_t)ks * 2u * b_lbo) >> 4), idesc, !(first && b == 0 && ks == 0));
+            if constexpr (X3) {
+                mma_f16(d_tmem, a_desc + ((a_off + (uint32_t)(K / 8) * a_lbo) >> 4), b_desc + (((uint32_t)ks * 2u * b_lbo) >> 4), idesc, true);
+                mma_f16(d_tmem, a_desc + (a_off >> 4), b_desc + ((((uint32_t)KB / 8u + (uint32_t)ks * 2u) * b_lbo) >> 4), idesc, true);
+            }
         }
-        if (BIAS && b + 1 == NBLK)      // the bias columns (tf32: bias hi, bias lo, 0 ...) follow the block's KB / EPC chunks
-            mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / EPC) * b_lbo) >> 4), make_idesc_tf32(128, ROWS), true);
+        if (BIAS && b + 1 == NBLK)      // the bias columns (tf32: bias hi, bias lo, 0 ...) follow the block's KB / EPC chunks (twice that: X3)
+            mma_tf32(d_tmem, desc_of(ones_addr, TM * 16u), b_desc + ((((uint32_t)KB / EPC) * (X3 ? 2u : 1u) * b_lbo) >> 4), make_idesc_tf32(128, ROWS), true);
         if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
     }
 }
@@ -294,8 +311,13 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
     for (uint32_t u = 0; u < 2; ++u) {
         const uint64_t y_desc = desc_of(y_addr + u * y_stride, b_lbo);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks)
+        for (uint32_t ks = 0; ks < 4; ++ks) {
             mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((ks * 2u * b_lbo) >> 4), idesc, ks > 0);
+            if constexpr (G::x3) {      // lo copies: the mixing matrix 8 KB (64 x 64 halves) further, the activations after both units' hi copies
+                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((2u * y_stride + ks * 2u * b_lbo) >> 4), idesc, true);
+                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((8192u + ks * 2u * 1024u) >> 4), y_desc + ((ks * 2u * b_lbo) >> 4), idesc, true);
+            }
+        }
     }
     if (!G::resident) { commit(&r.empty[slot]); ring_consumed<G::nslot>(r); }
 }
@@ -415,15 +437,27 @@ __device__ __forceinline__ void row_to_a(const float (&v)[CH], float* region, in
 }
 
 // the same as fp16 (kind::f16 operand): 8 channels per 16-byte chunk, round to nearest, saturating at the fp16 range
-template <int CH>
+// (a, b) -> packed fp16 pair hi = (fp16(a), fp16(b)) and the packed fp16 pair of the rounding residuals lo = (fp16(a - hi.a), ...):
+// hi + lo carries ~22 significant bits of the value (fp16 subnormals keep |lo| down to 6e-8 absolute)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - f.y), "f"(a - f.x));
+}
+// LOC > 0 (split precision): the lo chunks follow LOC chunks (= K / 8) after the hi chunks
+template <int CH, int LOC = 0>
 __device__ __forceinline__ void row_to_a16(const float (&v)[CH], float* region, int row, int col0) {
     if (BALF_EXP & 2) { if (v[0] == 12345.678f) region[row] = v[1]; return; }
 #pragma unroll
     for (int j = 0; j < CH / 8; ++j) {
-        uint32_t h[4];
+        uint32_t h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(v[8 * j + 2 * e + 1]), "f"(v[8 * j + 2 * e]));
+        for (int e = 0; e < 4; ++e) {
+            if constexpr (LOC > 0) split_h2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], h[e], l[e]);
+            else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(v[8 * j + 2 * e + 1]), "f"(v[8 * j + 2 * e]));
+        }
         *reinterpret_cast<uint4*>(region + ((size_t)(col0 / 8 + j) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+        if constexpr (LOC > 0) *reinterpret_cast<uint4*>(region + ((size_t)(LOC + col0 / 8 + j) * TM + row) * 4) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -677,7 +711,8 @@ __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
 }
 
 // this thread's part (1 / TPR) of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
-template <int CIN, int TPR = 2, bool H16 = false>       // H16: the operand is fp16 (two 4-channel chunks -> one 16-byte chunk of 8 halves)
+// H16: 1 = the operand is fp16 (two 4-channel chunks -> one 16-byte chunk of 8 halves), 2 = fp16 hi + lo (lo chunks CIN / 8 further)
+template <int CIN, int TPR = 2, int H16 = 0>
 __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
                                                float* dst, int row, int half) {
     if constexpr (CIN < 8) {                       // NCHW network input: part 0 gathers the planes, part 1 zero-fills
@@ -699,12 +734,17 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
 #pragma unroll
             for (int j = 0; j < NB; j += 2) {
                 pair_unswap(v[j], v[j + 1]);
-                if constexpr (H16) {
+                if constexpr (H16 != 0) {
                     const float e[8] = {v[j].x, v[j].y, v[j].z, v[j].w, v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
-                    uint32_t h[4];
+                    uint32_t h[4], l[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                    for (int q = 0; q < 4; ++q) {
+                        if constexpr (H16 == 2) split_h2(e[2 * q], e[2 * q + 1], h[q], l[q]);
+                        else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                    }
                     *reinterpret_cast<uint4*>(dst + ((size_t)((half * N + j0 + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+                    if constexpr (H16 == 2)
+                        *reinterpret_cast<uint4*>(dst + ((size_t)(CIN / 8 + (half * N + j0 + j) / 2) * TM + row) * 4) = make_uint4(l[0], l[1], l[2], l[3]);
                 } else {
                     *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j) * TM + row) * 4) = to_tf32(v[j]);
                     *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j0 + j + 1) * TM + row) * 4) = to_tf32(v[j + 1]);
@@ -743,7 +783,7 @@ __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, s
         }
     }
 }
-template <int CIN, bool PAIR = true, int TPR = 2, bool H16 = false>
+template <int CIN, bool PAIR = true, int TPR = 2, int H16 = 0>
 __device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, float* dst, int row, int half) {
     if constexpr (CIN < 8) {
         if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
@@ -753,12 +793,17 @@ __device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, flo
         for (int j = 0; j < N; j += 2) {
             float4 c0 = pf.v[j], c1 = pf.v[j + 1];
             if constexpr (PAIR) pair_unswap(c0, c1);
-            if constexpr (H16) {                 // two 4-channel chunks -> one 16-byte chunk of 8 halves
+            if constexpr (H16 != 0) {            // two 4-channel chunks -> one 16-byte chunk of 8 halves
                 const float e[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                uint32_t h[4];
+                uint32_t h[4], l[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (H16 == 2) split_h2(e[2 * q], e[2 * q + 1], h[q], l[q]);
+                    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[q]) : "f"(e[2 * q + 1]), "f"(e[2 * q]));
+                }
                 *reinterpret_cast<uint4*>(dst + ((size_t)((half * N + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+                if constexpr (H16 == 2)
+                    *reinterpret_cast<uint4*>(dst + ((size_t)(CIN / 8 + (half * N + j) / 2) * TM + row) * 4) = make_uint4(l[0], l[1], l[2], l[3]);
             } else {
                 *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j) * TM + row) * 4) = to_tf32(c0);
                 *reinterpret_cast<float4*>(dst + ((size_t)(half * N + j + 1) * TM + row) * 4) = to_tf32(c1);
@@ -804,14 +849,17 @@ __device__ __forceinline__ void conv0_row(const float4 x, const float* vec, int 
 // (two threads per row); variant 1 is one thread per row at C = 32 (half the per-row overhead instructions -- address
 // arithmetic, barriers, LayerNorm exchanges -- of a kernel that is bound by instruction issue) and four threads per row at
 // C >= 128 (16 epilogue warps instead of 8 on an SM whose epilogues are latency-bound).
-template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
+template <int C, int TPR_, int NG_, bool WW_ = false, int PX_ = 0> struct BranchCfgT {
     static constexpr bool WW = WW_;                                // warps wait on the MMA completion barrier directly
+    static constexpr int PX = PX_;                                 // 1: split precision (fp16 hi + lo operands, see BranchG)
     static constexpr int TPR = TPR_;
     static constexpr int NTG = TM * TPR;                           // threads per tile group
     static constexpr int CH = C / TPR;
     static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 2;       // bytes between the two units' (fp16) mixing operands
-    static constexpr uint32_t region = ((2 * y_stride > (uint32_t)TM * C * 2 ? 2 * y_stride : (uint32_t)TM * C * 2) + 127u) / 128u * 128u;
+    // operand region of a group: the [128 x C] A operand (hi chunks, then lo chunks: PX) or the two units' mixing operands (hi, hi, lo, lo)
+    static constexpr uint32_t yb = (PX ? 4u : 2u) * y_stride, ab = (uint32_t)TM * C * (PX ? 4u : 2u);
+    static constexpr uint32_t region = ((yb > ab ? yb : ab) + 127u) / 128u * 128u;
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
     static constexpr bool swz_out = false;                         // (round-1 layout: fp32 tiles in the swizzled panel layout)
     static constexpr bool h16_out = C <= 128;                      // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
@@ -823,13 +871,15 @@ template <int C, int TPR_, int NG_, bool WW_ = false> struct BranchCfgT {
     static constexpr uint32_t xch = TPR == 1 ? 0u : 2u * TPR * TM * 8u;   // LayerNorm exchange buffers per group
     static constexpr int SC = TPR == 1 ? 16 : TPR == 4 ? (CH < 32 ? CH : 32) : (CH > 64 ? 64 : CH);   // sub-chunks bound the live registers
 };
-template <int C> struct BranchCfg : BranchCfgT<C, 2, (C <= 32 ? 4 : C <= 64 ? 2 : 1)> {};
+template <int C, int PX = 0> struct BranchCfg : BranchCfgT<C, 2, (C <= 32 ? 4 : C <= 64 ? 2 : 1), false, PX> {};
 
 template <int CIN, int C, int BR, typename Cfg>
 __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, const DownW& w, const TcPlan& plan, const UnitGeom& geo,
                                                float* __restrict__ out, unsigned char* smem) {
-    using G = BranchG<CIN, C>;
+    using G = BranchG<CIN, C, Cfg::PX>;
     constexpr int CH = Cfg::CH, NG = Cfg::groups, TPR = Cfg::TPR, NTG = Cfg::NTG, SC = Cfg::SC;
+    constexpr bool X3 = Cfg::PX != 0;
+    constexpr int LOC = X3 ? C / 8 : 0;                                   // lo chunks of an A operand follow its C / 8 hi chunks
     static_assert(NG == 1 || G::resident, "tile groups share resident weights (no ring state per group)");
     static_assert(CH % SC == 0 && SC % 16 == 0, "sub-chunking");
     TcShared s = carve(smem, Cfg::region, plan, NG, Cfg::xch);
@@ -904,14 +954,14 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
             if (InputPf<CIN, TPR>::enabled) {
-                store_input_row<CIN, true, TPR, true>(pf, s.region, row, half);
+                store_input_row<CIN, true, TPR, X3 ? 2 : 1>(pf, s.region, row, half);
                 if (t + vgrid < ntiles) {
                     bool vld; int im, px;
                     coords(t + vgrid, vld, im, px);
                     fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
                 }
             } else {
-                load_input_row<CIN, TPR, true>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+                load_input_row<CIN, TPR, X3 ? 2 : 1>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
             }
             TC_TRACE(plan, it, 1);
             sync_for_mma<NG, NTG>(grp);
@@ -928,7 +978,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             stats_of(v, sum, sq);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
-            row_to_a16<CH>(v, s.region, row, col0);
+            row_to_a16<CH, LOC>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma<NG, NTG>(grp);
@@ -945,7 +995,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
-            row_to_a16<CH>(v, s.region, row, col0);
+            row_to_a16<CH, LOC>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 7);
         sync_for_mma<NG, NTG>(grp);
@@ -974,10 +1024,15 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 float o0, o1;
                 upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), o0, o1);
                 if (!(BALF_EXP & 2) || o0 == 12345.678f) {
-                    uint32_t h;
-                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(o1), "f"(o0));
+                    uint32_t h, l;
+                    if constexpr (X3) split_h2(o0, o1, h, l);
+                    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(o1), "f"(o0));
                     reinterpret_cast<unsigned short*>(yt)[(size_t)i * 8] = (unsigned short)(h & 0xFFFFu);
                     reinterpret_cast<unsigned short*>(yt)[(size_t)(i + 1) * 8] = (unsigned short)(h >> 16);
+                    if constexpr (X3) {                                  // lo copies of both units follow the two hi copies
+                        reinterpret_cast<unsigned short*>(yt)[(size_t)Cfg::y_stride + (size_t)i * 8] = (unsigned short)(l & 0xFFFFu);
+                        reinterpret_cast<unsigned short*>(yt)[(size_t)Cfg::y_stride + (size_t)(i + 1) * 8] = (unsigned short)(l >> 16);
+                    }
                 }
             }
         }
@@ -997,7 +1052,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 const unsigned long long b2 = pk2(mix_b1, mix_b1);
 #pragma unroll
                 for (int i = 0; i < SC; i += 2) upk2(mul2(pk2(y1[i], y1[i + 1]), add2(pk2(y2[i], y2[i + 1]), b2)), y2[i], y2[i + 1]);
-                row_to_a16<SC>(y2, s.region, row, col0 + c);
+                row_to_a16<SC, LOC>(y2, s.region, row, col0 + c);
             }
         }
         TC_TRACE(plan, it, 13);
@@ -1013,7 +1068,9 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             // images).  Lanes 2i / 2i+1 therefore swap every other chunk: both lanes write the two halves of one 32-byte
             // sector of row 2i, then of row 2i+1 -- 16 full sectors per instruction.
             const bool odd = (threadIdx.x & 1) != 0;
-            const size_t own_base = (Cfg::swz_out || Cfg::h16_out) ? ((size_t)img * npix + (pix & ~(TM - 1))) * C : ((size_t)img * npix + pix) * C;
+            // (own_base counts elements of the tile format: halves of an fp16 tile -- twice as many per tile in split precision)
+            const size_t own_base = (Cfg::swz_out || Cfg::h16_out) ? ((size_t)img * npix + (pix & ~(TM - 1))) * C * (Cfg::h16_out && X3 ? 2 : 1)
+                                                                   : ((size_t)img * npix + pix) * C;
             const int own_sw = pix & (TM - 1);
             const size_t oth_base = __shfl_xor_sync(0xffffffffu, (unsigned long long)own_base, 1);
             const int oth_sw = __shfl_xor_sync(0xffffffffu, own_sw, 1);
@@ -1032,14 +1089,18 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                     __half* tile = reinterpret_cast<__half*>(out) + own_base + (size_t)own_sw * 8;
 #pragma unroll
                     for (int j = 0; j < SC / 8; ++j) {
-                        uint32_t h[4];
+                        uint32_t h[4], l[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float lo = a[8 * j + 2 * e] + r[8 * j + 2 * e], hi = a[8 * j + 2 * e + 1] + r[8 * j + 2 * e + 1];
-                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(hi), "f"(lo));
+                            if constexpr (X3) split_h2(lo, hi, h[e], l[e]);
+                            else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(hi), "f"(lo));
                         }
-                        if (valid && (!(BALF_EXP & 8) || h[0] == 0x12345678u))
+                        if (valid && (!(BALF_EXP & 8) || h[0] == 0x12345678u)) {
                             *reinterpret_cast<uint4*>(tile + (size_t)((col0 + c) / 8 + j) * (TM * 8)) = make_uint4(h[0], h[1], h[2], h[3]);
+                            if constexpr (X3)      // split precision: the tile is the merge kernel's [hi chunks | lo chunks] A operand
+                                *reinterpret_cast<uint4*>(tile + (size_t)(C / 8 + (col0 + c) / 8 + j) * (TM * 8)) = make_uint4(l[0], l[1], l[2], l[3]);
+                        }
                     }
                     continue;
                 }
@@ -1062,7 +1123,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                     // u' / v' feed nothing but the merge GEMM: rounding them here (RN, as every operand) lets the merge
                     // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
                     // the C >= 128 merge kernels round again when they load, which must be a no-op
-                    if (BR == 1 || Cfg::swz_out) o[j] = to_tf32_clean(o[j]);
+                    if ((BR == 1 || Cfg::swz_out) && !X3) o[j] = to_tf32_clean(o[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < SC / 4; j += 2) {
@@ -1090,18 +1151,18 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
 }
 
 // V = 0: the round-1 layout; V = 1: see BranchCfgT
-template <int C, int V> struct BranchSel { using Cfg = BranchCfg<C>; };
-template <> struct BranchSel<32, 1> { using Cfg = BranchCfgT<32, 1, 5>; };
-template <> struct BranchSel<32, 2> { using Cfg = BranchCfgT<32, 1, 5, true>; };
-template <> struct BranchSel<64, 1> { using Cfg = BranchCfgT<64, 4, 2>; };
-template <> struct BranchSel<128, 1> { using Cfg = BranchCfgT<128, 4, 1>; };
-template <> struct BranchSel<256, 1> { using Cfg = BranchCfgT<256, 4, 1>; };
+template <int C, int V, int PX = 0> struct BranchSel { using Cfg = BranchCfg<C, PX>; };
+template <int PX> struct BranchSel<32, 1, PX> { using Cfg = BranchCfgT<32, 1, 5, false, PX>; };
+template <int PX> struct BranchSel<32, 2, PX> { using Cfg = BranchCfgT<32, 1, 5, true, PX>; };
+template <int PX> struct BranchSel<64, 1, PX> { using Cfg = BranchCfgT<64, 4, 2, false, PX>; };
+template <int PX> struct BranchSel<128, 1, PX> { using Cfg = BranchCfgT<128, 4, 1, false, PX>; };
+template <int PX> struct BranchSel<256, 1, PX> { using Cfg = BranchCfgT<256, 4, 1, false, PX>; };
 
-template <int CIN, int C, int BR, int V>
-__global__ void __launch_bounds__(BranchSel<C, V>::Cfg::NTG * BranchSel<C, V>::Cfg::groups, 1)
+template <int CIN, int C, int BR, int V, int PX = 0>
+__global__ void __launch_bounds__(BranchSel<C, V, PX>::Cfg::NTG * BranchSel<C, V, PX>::Cfg::groups, 1)
 tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    tc_branch_body<CIN, C, BR, typename BranchSel<C, V>::Cfg>(xin, w, plan, geo, out, smem);
+    tc_branch_body<CIN, C, BR, typename BranchSel<C, V, PX>::Cfg>(xin, w, plan, geo, out, smem);
 }
 
 
@@ -1134,25 +1195,27 @@ __device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int t
 }
 
 // ------------------------------------------------------------------------------------------ merge kernel
-template <int C> struct MergeCfg {
+template <int C, int PX = 0> struct MergeCfg {
     static constexpr int CH = C / 2;
     // C = 128: u' and v' (swizzled panel tiles, tf32-rounded by the branch kernels) arrive by bulk copy -- u' into a second
     // region a tile ahead, v' into the first as soon as conv.0 has released it -- and conv.0 shares its phase with dense2(u')
     static constexpr bool bulk_uv = C == 128;
-    static constexpr uint32_t region = (uint32_t)TM * C * 4 + (bulk_uv ? (uint32_t)TM * C * 2 : 0u);   // + the fp16 u' tile
+    static constexpr uint32_t uv_bytes = (uint32_t)TM * C * (PX ? 4u : 2u);                 // an fp16 u' / v' tile (hi + lo: PX)
+    static constexpr uint32_t region = (uint32_t)TM * C * 4 + (bulk_uv ? uv_bytes : 0u);   // + the u' tile
     static constexpr int col_x0 = 0, col_acc = C;
     static constexpr int ncols = tc_cols(2 * C);
     static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
 };
 
-template <int CIN, int C>
-__global__ void __launch_bounds__(NT2, MergeCfg<C>::min_ctas)
+template <int CIN, int C, int PX = 0>
+__global__ void __launch_bounds__(NT2, MergeCfg<C, PX>::min_ctas)
 tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
                 const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = MergeCfg<C>;
-    using G = MergeG<CIN, C>;
+    using Cfg = MergeCfg<C, PX>;
+    using G = MergeG<CIN, C, PX>;
     constexpr int CH = Cfg::CH;
+    constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;      // operand mode of the loaders, lo-chunk offset of a K = C operand
     (void)w;
     const TcShared s = carve(smem, Cfg::region, plan);
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
@@ -1167,8 +1230,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const uint32_t r2_addr = region_addr + (uint32_t)TM * C * 4;            // bulk_uv: u' tiles land here
     uint64_t* const ld_u = s.aux;
     uint64_t* const ld_v = &s.gdone[1];
-    constexpr uint32_t kTileBytes = (uint32_t)TM * C * 2;                  // u' / v' tiles are fp16 (chunk-major)
-    const size_t tile_floats = (size_t)TM * C / 2;                         // ... i.e. TM * C / 2 floats apart
+    constexpr uint32_t kTileBytes = Cfg::uv_bytes;                         // u' / v' tiles are fp16 (chunk-major; hi then lo chunks: PX)
+    const size_t tile_floats = (size_t)kTileBytes / 4;                     // ... i.e. that many floats apart
     uint32_t ld_phase = 0;
     const int ug = row >> 6, tok = row & 63;
     const int col0 = half * CH;
@@ -1200,14 +1263,14 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
         if (InputPf<CIN>::enabled) {
-            store_input_row<CIN, true, 2, true>(pf, s.region, row, half);
+            store_input_row<CIN, true, 2, HM>(pf, s.region, row, half);
             if (t + (int)gridDim.x < ntiles) {
                 bool vld; int im, px;
                 coords(t + gridDim.x, vld, im, px);
                 fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
             }
         } else {
-            load_input_row<CIN, 2, true>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<CIN, 2, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
@@ -1254,10 +1317,10 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
         // ---- dense2([u', v']) accumulated over the two K halves (the region is reloaded in between)
         if (InputPf<C>::enabled) {
-            store_input_row<C>(pfu, s.region, row, half);
+            store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
             fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
         } else {
-            load_input_row<C, 2, true>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<C, 2, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
@@ -1265,8 +1328,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         TC_TRACE(plan, it, 5);
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
-        if (InputPf<C>::enabled) store_input_row<C>(pfu, s.region, row, half);
-        else load_input_row<C, 2, true>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        if (InputPf<C>::enabled) store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
+        else load_input_row<C, 2, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
@@ -1299,7 +1362,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
-            row_to_a16<CH>(v, s.region, row, col0);
+            row_to_a16<CH, LOC>(v, s.region, row, col0);
         }
         TC_TRACE(plan, it, 10);
         sync_for_mma();
@@ -1315,7 +1378,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
         }
-        row_to_a16<CH>(v, s.region, row, col0);
+        row_to_a16<CH, LOC>(v, s.region, row, col0);
         TC_TRACE(plan, it, 13);
         sync_for_mma();
         // ---- conv2 = r -> global, and staged (exact fp32) in the region for the per-unit channel sums (squeeze)
@@ -1348,31 +1411,33 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
 // following phases.  At C = 32 (CIN = 3) x0 = ReLU(conv.0(x)) runs on the CUDA cores while the dense2 MMAs execute; at
 // C = 64 conv.0 is a third MMA of phase 1 on a register-prefetched x tile.  Consumers of r / q (pool_kernel) un-permute.
 // Regions: U | V (operands of dense2) | W (conv1 / conv2 input, then r staging) | Q (q staging) | X (conv.0 operand).
-template <int CIN, int C> struct MergeBulkCfg {
+template <int CIN, int C, int PX = 0> struct MergeBulkCfg {
     static constexpr int CH = C / 2;
     static constexpr bool cc0 = CIN < 8;
     static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;      // W / Q staging tiles (fp32)
-    static constexpr uint32_t uv_bytes = (uint32_t)TM * C * 2;        // u' / v' tiles (fp16, chunk-major)
+    static constexpr uint32_t uv_bytes = (uint32_t)TM * C * (PX ? 4u : 2u);   // u' / v' tiles (fp16, chunk-major; hi then lo chunks: PX)
+    static constexpr uint32_t r16_bytes = PX ? 0u : (uint32_t)TM * C * 2;     // r as an fp16 tile (split precision stores the fp32 staging tile W)
     static constexpr uint32_t xbytes = cc0 ? 0u : (uint32_t)TM * tc_kin(CIN) * 4;
-    static constexpr uint32_t region = 3 * uv_bytes + 2 * tile_bytes + xbytes;   // U, V, R16 (fp16) | W, Q (fp32) | X
+    static constexpr uint32_t region = 2 * uv_bytes + r16_bytes + 2 * tile_bytes + xbytes;   // U, V, R16 (fp16) | W, Q (fp32) | X
     static constexpr int col_acc = 0, col_x0 = C;
     static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
-    static constexpr int min_ctas = C <= 32 ? BALF_MERGE32_CTAS : 1;
+    static constexpr int min_ctas = C <= 32 ? (PX ? 2 : BALF_MERGE32_CTAS) : 1;
 };
 
-template <int CIN, int C>
-__global__ void __launch_bounds__(NT2, MergeBulkCfg<CIN, C>::min_ctas)
+template <int CIN, int C, int PX = 0>
+__global__ void __launch_bounds__(NT2, MergeBulkCfg<CIN, C, PX>::min_ctas)
 tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
                      const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = MergeBulkCfg<CIN, C>;
+    using Cfg = MergeBulkCfg<CIN, C, PX>;
     constexpr int CH = Cfg::CH;
-    using G = MergeG<CIN, C>;
+    using G = MergeG<CIN, C, PX>;
+    constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;
     const TcShared s = carve(smem, Cfg::region, plan);
     float* const regU = s.region;                                    // fp16 tile: TM * C / 2 floats
-    float* const regV = regU + (size_t)TM * C / 2;
-    float* const regR = regV + (size_t)TM * C / 2;                   // r as an fp16 tile (chunk-major) for its bulk store
-    float* const regW = regR + (size_t)TM * C / 2;
+    float* const regV = regU + Cfg::uv_bytes / 4;
+    float* const regR = regV + Cfg::uv_bytes / 4;                    // r as an fp16 tile (chunk-major) for its bulk store (not PX)
+    float* const regW = regR + Cfg::r16_bytes / 4;
     float* const regQ = regW + (size_t)TM * C;
     float* const regX = regQ + (size_t)TM * C;
     uint64_t* const ld_bar = s.aux;
@@ -1398,8 +1463,8 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     };
     auto load_tile = [&](int tt) {                          // elected lane: next tile's u' and v' (fp16 tiles) -> U, V
         mbar_expect_tx(ld_bar, 2 * Cfg::uv_bytes);
-        bulk_load(u_addr, uin + (size_t)tt * (tile_floats / 2), Cfg::uv_bytes, ld_bar);
-        bulk_load(v_addr, vin + (size_t)tt * (tile_floats / 2), Cfg::uv_bytes, ld_bar);
+        bulk_load(u_addr, uin + (size_t)tt * (Cfg::uv_bytes / 4), Cfg::uv_bytes, ld_bar);
+        bulk_load(v_addr, vin + (size_t)tt * (Cfg::uv_bytes / 4), Cfg::uv_bytes, ld_bar);
     };
     InputPf<CIN> pfx;
     if ((int)blockIdx.x < ntiles) {
@@ -1413,7 +1478,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         float v[CH], x0[CH];
         // ---- phase 1: acc = dense2([u', v']) (+ conv.0(x) at CIN >= 8) on the tensor core | x0 on the CUDA cores at CIN < 8
         if constexpr (!Cfg::cc0) {
-            store_input_row<CIN, false, 2, true>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
+            store_input_row<CIN, false, 2, HM>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
             sync_for_mma();
         }
         if (w0 && elect_one()) {
@@ -1457,7 +1522,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
-            if constexpr (G::h16(MG_RC1)) row_to_a16<CH>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
+            if constexpr (G::h16(MG_RC1)) row_to_a16<CH, LOC>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         }
         sync_for_mma();
         // ---- phase 2: conv1 -> LeakyReLU(0.2); q leaves, the next tile's u' / v' arrive (phase 1 released U and V)
@@ -1476,14 +1541,14 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
         }
-        if constexpr (G::h16(MG_RC1)) row_to_a16<CH>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
+        if constexpr (G::h16(MG_RC1)) row_to_a16<CH, LOC>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         sync_for_mma();
         // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
         if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, !G::h16(MG_RC2)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
         row_to_sw<CH, false>(v, regW, row, col0);              // exact fp32: the squeeze sums below
-        {
+        if constexpr (!PX) {
             // r crosses HBM as an fp16 tile [C / 8 chunks][128 pixels][8 halves] (pool_kernel reads it back): r only enters
             // r * s + q with s in (0, 1) next to the fp32 q, and the sum is rounded to an 11-bit significand by its consumer --
             // measured effect on the score map: mean relative error 1.017e-4 -> 1.022e-4 (emulation)
@@ -1499,7 +1564,9 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         }
         sync_for_mma();
         if (w0 && elect_one()) {
-            bulk_store(rout + (size_t)t * (tile_floats / 2), smem_u32(regR), Cfg::uv_bytes);
+            // split precision: r leaves as the exact fp32 staging tile (swizzled panel layout, like q)
+            if constexpr (PX) bulk_store(rout + (size_t)t * tile_floats, w_addr, Cfg::tile_bytes);
+            else bulk_store(rout + (size_t)t * (tile_floats / 2), smem_u32(regR), Cfg::uv_bytes);
             bulk_commit();
         }
         {   // channel sums of each unit from the swizzled staging tile (see unit_channel_sums; same fixed order)
@@ -1531,12 +1598,13 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
 // ------------------------------------------------------------------------------------------ head kernel (last stage)
 // t = r * s + q -> conv2 (C -> C) -> ReLU -> dense (C -> 65, BatchNorm folded into weights and bias) = logits ->
 // softmax -> drop the dustbin -> depth-to-space.  The half-0 thread of a row finishes its 8x8 cell.
-template <int C>
+template <int C, int PX = 0>
 __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict__ r, const float* __restrict__ q,
                                                          const float* __restrict__ scale, TcPlan plan, UnitGeom geo, int cell,
                                                          float* __restrict__ logits, float* __restrict__ prob) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    using G = HeadG<C>;
+    using G = HeadG<C, PX>;
+    constexpr int LOC = PX ? C / 8 : 0;
     constexpr uint32_t region_bytes = (uint32_t)TM * C * 4;
     constexpr int ncols = tc_cols(C + 96);
     constexpr int CH = C / 2;
@@ -1546,7 +1614,7 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     Ring ring;
     const bool w0 = warp0_uniform();
-    tc_prologue<HeadG<C>::nslot>(s, ncols, ring, plan, my_tiles, w0);
+    tc_prologue<G::nslot>(s, ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
@@ -1577,24 +1645,29 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
                     e[4 * u2] = rv[j + u2].x * sv.x + qv[j + u2].x; e[4 * u2 + 1] = rv[j + u2].y * sv.y + qv[j + u2].y;
                     e[4 * u2 + 2] = rv[j + u2].z * sv.z + qv[j + u2].z; e[4 * u2 + 3] = rv[j + u2].w * sv.w + qv[j + u2].w;
                 }
-                uint32_t h[4];
+                uint32_t h[4], l[4];
 #pragma unroll
-                for (int w2 = 0; w2 < 4; ++w2) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[w2]) : "f"(e[2 * w2 + 1]), "f"(e[2 * w2]));
+                for (int w2 = 0; w2 < 4; ++w2) {
+                    if constexpr (PX) split_h2(e[2 * w2], e[2 * w2 + 1], h[w2], l[w2]);
+                    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[w2]) : "f"(e[2 * w2 + 1]), "f"(e[2 * w2]));
+                }
                 *reinterpret_cast<uint4*>(s.region + ((size_t)((col0 / 4 + j0 + j) / 2) * TM + row) * 4) = make_uint4(h[0], h[1], h[2], h[3]);
+                if constexpr (PX)
+                    *reinterpret_cast<uint4*>(s.region + ((size_t)(LOC + (col0 / 4 + j0 + j) / 2) * TM + row) * 4) = make_uint4(l[0], l[1], l[2], l[3]);
             }
         }
         sync_for_mma();
-        if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, HG_C2>(ring, plan, region_addr, ones_addr, tm, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         {
             float v[CH];
             ld_row<CH>(lane_base + col0, v);
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
-            row_to_a16<CH>(v, s.region, row, col0);
+            row_to_a16<CH, LOC>(v, s.region, row, col0);
         }
         sync_for_mma();
-        if (w0 && elect_one()) { issue_linear_t<HeadG<C>, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
+        if (w0 && elect_one()) { issue_linear_t<G, HG_DENSE>(ring, plan, region_addr, ones_addr, tm + C, true); commit(s.done); }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         // logits = columns C .. C+64 of the row.  tcgen05.ld is warp-collective and `half` is warp-uniform, so the
         // branch below is convergent per warp.
@@ -1658,6 +1731,24 @@ __global__ void tc_pack_h16_kernel(const float* __restrict__ wT, int ld, int n0,
     }
     dst[(size_t)b * rows * kb + (size_t)(kk >> 3) * rows * 8 + n * 8 + (kk & 7)] = __float2half_rn(v);
 }
+// split precision (TcGemm::h16 == 2): every block holds its kb columns as fp16 hi chunks followed by the fp16 lo chunks
+__global__ void tc_pack_x3_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real, int k_pad, int kb,
+                                  const float* __restrict__ gamma, const float* __restrict__ alpha, __half* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * k_pad) return;
+    const int k = i / rows, n = i - k * rows;
+    const int b = k / kb, kk = k - b * kb;
+    float v = 0.f;
+    if (k < k_real) {
+        v = wT[(size_t)k * ld + n0 + n];
+        if (gamma) v *= gamma[k];
+        if (alpha) v *= alpha[n0 + n];
+    }
+    const __half hi = __float2half_rn(v);
+    const size_t at = (size_t)b * rows * kb * 2 + (size_t)(kk >> 3) * rows * 8 + n * 8 + (kk & 7);
+    dst[at] = hi;
+    dst[at + (size_t)rows * kb] = __float2half_rn(v - __half2float(hi));
+}
 // bias columns of the last block: b' = (bias[n] + sum_k W[n][k] beta[k]) * alpha[n] + add[n], split into tf32 hi + lo
 __global__ void tc_pack_bias_kernel(const float* __restrict__ wT, int ld, int n0, int rows, int k_real,
                                     const float* __restrict__ bias, const float* __restrict__ beta,
@@ -1687,15 +1778,15 @@ struct TcPlans {
     size_t floats;
 };
 
-static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768, bool h16 = false) {
-    const int kb = tc_kb(rows, K, cap, h16 ? 2 : 4);
+static void tc_add(TcPlan& p, int gi, size_t& off, int rows, int K, bool bias, int cap = 32768, int h16 = 0) {
+    const int kb = tc_kb(rows, K, cap, (int)tc_eb(h16));
     TcGemm& g = p.g[gi];
     g.goff = (uint32_t)off;
     g.nblk = (uint16_t)(K / kb);
     g.rows = (uint16_t)rows;
     g.kb = (uint16_t)kb;
     g.bias = bias ? 1 : 0;
-    g.h16 = h16 ? 1 : 0;
+    g.h16 = (uint16_t)h16;
     off += gemm_bytes(g) / 4;
     p.bytes += gemm_bytes(g);
     const uint32_t big = (gemm_block_bytes(g, g.nblk - 1) + 127u) / 128u * 128u;
@@ -1709,48 +1800,50 @@ static bool plan_matches(const TcPlan& p) {
     bool ok = true;
     for (int gi = 0; gi < G::count; ++gi) {
         const TcGemm& g = p.g[gi];
-        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap, G::h16(gi) ? 2 : 4) && g.nblk * g.kb == G::K(gi) &&
-             (g.bias != 0) == G::bias(gi) && (g.h16 != 0) == G::h16(gi) && gemm_bytes(g) == g_bytes<G>(gi) &&
+        ok = ok && g.rows == G::rows(gi) && g.kb == tc_kb(G::rows(gi), G::K(gi), G::cap, (int)tc_eb(g_mode<G>(gi))) && g.nblk * g.kb == G::K(gi) &&
+             (g.bias != 0) == G::bias(gi) && (int)g.h16 == g_mode<G>(gi) && gemm_bytes(g) == g_bytes<G>(gi) &&
              (g.goff - p.g[0].goff) * 4u == off;
         off += gemm_bytes(g);
     }
     return ok;
 }
 
-static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPlans* out) {
-    size_t off = 0;
+// px = 1: the split-precision plans (they follow the px = 0 plans in the blob); `off` runs over both
+static void tc_build_plans_px(const balf_detector_arch& a, const float* base, TcPlans* out, int px, size_t& off) {
     TcPlans P;
+    const int hm = px ? 2 : 1;
     for (int l = 0; l < 4; ++l) {
         const int cin = tc_kin(a.dims[l]), c = a.dims[l + 1];
-        const bool resident = c <= 64;                                 // mirrors MergeG::resident
         for (int b = 0; b < 2; ++b) {
             TcPlan& p = P.branch[l][b];
             p = TcPlan{};
-            p.base = base; p.ngemm = BG_COUNT; p.resident = c <= 128;      // mirrors BranchG::resident
-            p.nslot = c == 256 ? 3 : 2;                                // mirrors BranchG::nslot (checked by plan_matches)
-            tc_add(p, BG_CONV0, off, c, cin, true, 32768, a.dims[l] >= 8);
-            tc_add(p, BG_PD1, off, c, c, true, 32768, true);           // mirrors BranchG::h16
-            tc_add(p, BG_D1A, off, c, c, true, 32768, true);
-            tc_add(p, BG_D1B, off, c, c, true, 32768, true);
-            tc_add(p, BG_WM, off, 64, 64, false, 32768, true);
-            tc_add(p, BG_D2, off, c, c, true, 32768, true);
+            p.base = base; p.ngemm = BG_COUNT;
+            p.resident = px ? c <= 64 : c <= 128;                      // mirrors BranchG::resident
+            p.nslot = px ? (c == 256 ? 2 : 3) : (c == 256 ? 3 : 2);    // mirrors BranchG::nslot (checked by plan_matches)
+            tc_add(p, BG_CONV0, off, c, cin, true, 32768, a.dims[l] >= 8 ? hm : 0);
+            tc_add(p, BG_PD1, off, c, c, true, 32768, hm);             // mirrors BranchG::h16
+            tc_add(p, BG_D1A, off, c, c, true, 32768, hm);
+            tc_add(p, BG_D1B, off, c, c, true, 32768, hm);
+            tc_add(p, BG_WM, off, 64, 64, false, 32768, hm);
+            tc_add(p, BG_D2, off, c, c, true, 32768, hm);
         }
         TcPlan& m = P.merge[l];
         m = TcPlan{};
-        m.base = base; m.ngemm = MG_COUNT; m.resident = resident;
-        m.nslot = c == 256 ? 2 : 3;                                    // mirrors MergeG::nslot / MergeG::cap
+        m.base = base; m.ngemm = MG_COUNT;
+        m.resident = px ? c <= 32 : c <= 64;                           // mirrors MergeG::resident
+        m.nslot = px ? (c == 64 ? 3 : 2) : (c == 256 ? 2 : 3);         // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
-        tc_add(m, MG_CONV0, off, c, cin, true, mcap, a.dims[l] >= 8);
-        tc_add(m, MG_PD2A, off, c, c, false, mcap, true);             // mirrors MergeG::h16
-        tc_add(m, MG_PD2B, off, c, c, true, mcap, true);
-        tc_add(m, MG_RC1, off, c, c, true, mcap, c > BALF_RC16_MINC);
-        tc_add(m, MG_RC2, off, c, c, true, mcap, c > BALF_RC16_MINC);
+        tc_add(m, MG_CONV0, off, c, cin, true, mcap, a.dims[l] >= 8 ? hm : 0);
+        tc_add(m, MG_PD2A, off, c, c, false, mcap, hm);               // mirrors MergeG::h16
+        tc_add(m, MG_PD2B, off, c, c, true, mcap, hm);
+        tc_add(m, MG_RC1, off, c, c, true, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
+        tc_add(m, MG_RC2, off, c, c, true, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
     }
     TcPlan& h = P.head;
     h = TcPlan{};
     h.base = base; h.ngemm = HG_COUNT; h.resident = 0; h.nslot = 2;
-    tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true, 32768, true);          // mirrors HeadG::h16
-    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true, 32768, true);
+    tc_add(h, HG_C2, off, a.dims[4], a.dims[4], true, 32768, hm);          // mirrors HeadG::h16
+    tc_add(h, HG_DENSE, off, kHeadN, a.dims[4], true, 32768, hm);
     P.floats = off;
     for (int l = 0; l < 4; ++l) {
         P.branch[l][0].trace = P.branch[l][1].trace = g_tc_trace_sel == 0 ? g_tc_trace : nullptr;
@@ -1759,10 +1852,17 @@ static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPla
     P.head.trace = nullptr;
     if (out) *out = P;
 }
+static void tc_build_plans(const balf_detector_arch& a, const float* base, TcPlans* out, int px = 0) {
+    size_t off = 0;
+    TcPlans P0;
+    tc_build_plans_px(a, base, &P0, 0, off);
+    if (px) tc_build_plans_px(a, base, out, 1, off);
+    else if (out) *out = P0;
+}
 
 size_t tc_blob_floats(const balf_detector_arch& a) {
     TcPlans P;
-    tc_build_plans(a, nullptr, &P);
+    tc_build_plans(a, nullptr, &P, 1);
     return P.floats;
 }
 
@@ -1772,22 +1872,26 @@ static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0
                         float* blob, cudaStream_t st) {
     const TcGemm& g = p.g[gi];
     const int k_pad = g.nblk * g.kb;
-    if (g.h16)
+    if (g.h16 == 2)
+        tc_pack_x3_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha,
+                                                                     reinterpret_cast<__half*>(blob + g.goff));
+    else if (g.h16)
         tc_pack_h16_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha,
                                                                       reinterpret_cast<__half*>(blob + g.goff));
     else
         tc_pack_kernel<<<cdiv(g.rows * k_pad, 256), 256, 0, st>>>(wT, ld, n0, g.rows, k_real, k_pad, g.kb, f.gamma, f.alpha, blob + g.goff);
     if (g.bias)   // two chunk planes after the last block's kb columns; the second stays zero (blob is memset)
         tc_pack_bias_kernel<<<cdiv(g.rows, 128), 128, 0, st>>>(wT, ld, n0, g.rows, k_real, bias, f.beta, f.alpha, f.add,
-                                                               blob + g.goff + (size_t)g.rows * k_pad / (g.h16 ? 2 : 1));
+                                                               blob + g.goff + (size_t)g.rows * k_pad / (g.h16 == 1 ? 2 : 1));
 }
 
 // fp32-path packed weights (DetW) -> tc blob
 int tc_pack_weights(const balf_detector_arch& a, const DetW& w, float* blob, cudaStream_t st) {
-    TcPlans P;
-    tc_build_plans(a, blob, &P);
-    BALF_CUDA_OK(cudaMemsetAsync(blob, 0, P.floats * sizeof(float), st));
+    BALF_CUDA_OK(cudaMemsetAsync(blob, 0, tc_blob_floats(a) * sizeof(float), st));
     const Fold none{nullptr, nullptr, nullptr, nullptr};
+    for (int px = 0; px < 2; ++px) {
+    TcPlans P;
+    tc_build_plans(a, blob, &P, px);
     for (int l = 0; l < 4; ++l) {
         const int ci = a.dims[l], c = a.dims[l + 1];
         const DownW& d = w.down[l];
@@ -1811,6 +1915,7 @@ int tc_pack_weights(const balf_detector_arch& a, const DetW& w, float* blob, cud
     tc_pack_one(P.head, HG_C2, w.down[3].c2_w, a.dims[4], 0, a.dims[4], w.down[3].c2_b, none, blob, st);
     // logits = (x W^T + b) * alpha + beta_bn  (eval BatchNorm folded, decoder.py:18-22)
     tc_pack_one(P.head, HG_DENSE, w.head.w, kHeadPad, 0, a.dims[4], w.head.b, Fold{nullptr, nullptr, w.head.alpha, w.head.beta}, blob, st);
+    }
     BALF_LAUNCH_OK();
     return 0;
 }
@@ -1850,65 +1955,65 @@ static int tc_launch_cfg(K kernel, size_t smem, int tmem_cols, int ntiles, int* 
 
 int g_tc_variant = 0x41;     // debug hook (balf_debug_set key 4): per-stage branch-kernel variant, 2 bits per stage (BranchSel)
 
-template <int CIN, int C, int V>
+template <int CIN, int C, int V, int PX>
 static int tc_launch_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
                               float* u, float* v, cudaStream_t st) {
-    using Cfg = typename BranchSel<C, V>::Cfg;
+    using Cfg = typename BranchSel<C, V, PX>::Cfg;
     constexpr int NG = Cfg::groups;
     int grid = 0;
     for (int b = 0; b < 2; ++b) {
         const TcPlan& p = P.branch[level][b];
         const size_t smem = tc_smem_bytes(Cfg::region, p, NG, Cfg::xch);
         if (b == 0) {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0, V>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0, V, PX>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
-            tc_branch_kernel<CIN, C, 0, V><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, u);
+            tc_branch_kernel<CIN, C, 0, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, u);
         } else {
-            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1, V>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
+            if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1, V, PX>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
-            tc_branch_kernel<CIN, C, 1, V><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, v);
+            tc_branch_kernel<CIN, C, 1, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, v);
         }
     }
     return 0;
 }
-template <int CIN, int C>
+template <int CIN, int C, int PX>
 static int tc_run_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
                            float* u, float* v, cudaStream_t st) {
     const int var = (g_tc_variant >> (2 * level)) & 3;
     if constexpr (C == 32) {
-        if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
-        if (var == 2) return tc_launch_branches<CIN, C, 2>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 2) return tc_launch_branches<CIN, C, 2, PX>(xin, w, P, level, g, ntiles, u, v, st);
     }
     if constexpr (C == 64 || C == 128 || C == 256) {
-        if (var == 1) return tc_launch_branches<CIN, C, 1>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, st);
     }
-    return tc_launch_branches<CIN, C, 0>(xin, w, P, level, g, ntiles, u, v, st);
+    return tc_launch_branches<CIN, C, 0, PX>(xin, w, P, level, g, ntiles, u, v, st);
 }
 
-template <int CIN, int C>
+template <int CIN, int C, int PX>
 static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int level, int Bc, int h, int wd,
                         float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
     UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64), 1.0f / (float)(h * wd / 64), 1.0f / (float)(wd / 8), 1.0f / (float)(wd / 8)};
     BALF_REQUIRE(g.total_units < (1 << 23), "internal: %d units in one pass exceed the fast_div range", g.total_units);
     const int ntiles = (g.total_units + 1) / 2;
     int grid = 0;
-    BALF_REQUIRE((plan_matches<BranchG<CIN, C>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C>>(P.branch[level][1]) &&
-                  plan_matches<MergeG<CIN, C>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
-    if (int e = tc_run_branches<CIN, C>(xin, w, P, level, g, ntiles, u, v, st)) return e;
+    BALF_REQUIRE((plan_matches<BranchG<CIN, C, PX>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C, PX>>(P.branch[level][1]) &&
+                  plan_matches<MergeG<CIN, C, PX>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
+    if (int e = tc_run_branches<CIN, C, PX>(xin, w, P, level, g, ntiles, u, v, st)) return e;
     if constexpr (C <= 64) {
         const TcPlan& p = P.merge[level];
         BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
-        const size_t smem = tc_smem_bytes(MergeBulkCfg<CIN, C>::region, p);
-        if (int e = tc_launch_cfg(tc_merge_bulk_kernel<CIN, C>, smem, MergeBulkCfg<CIN, C>::ncols, ntiles, &grid)) return e;
+        const size_t smem = tc_smem_bytes(MergeBulkCfg<CIN, C, PX>::region, p);
+        if (int e = tc_launch_cfg(tc_merge_bulk_kernel<CIN, C, PX>, smem, MergeBulkCfg<CIN, C, PX>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 32 ? "det_merge_c32" : "det_merge_c64", st);
-        tc_merge_bulk_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+        tc_merge_bulk_kernel<CIN, C, PX><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     } else {
         const TcPlan& p = P.merge[level];
-        BALF_REQUIRE(!MergeCfg<C>::bulk_uv || g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
-        const size_t smem = tc_smem_bytes(MergeCfg<C>::region, p);
-        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C>, smem, MergeCfg<C>::ncols, ntiles, &grid)) return e;
+        BALF_REQUIRE((!MergeCfg<C, PX>::bulk_uv || g.total_units % 2 == 0), "internal: odd unit count at stage %d", level);
+        const size_t smem = tc_smem_bytes(MergeCfg<C, PX>::region, p);
+        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C, PX>, smem, MergeCfg<C, PX>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 128 ? "det_merge_c128" : "det_merge_c256", st);
-        tc_merge_kernel<CIN, C><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+        tc_merge_kernel<CIN, C, PX><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     }
     BALF_COUNT_LAUNCH(3);
     BALF_LAUNCH_OK();
@@ -1916,31 +2021,44 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
 }
 
 int tc_run_level_dispatch(int level, const float* xin, bool nchw, const DownW& w, const balf_detector_arch& a, const float* blob,
-                          int Bc, int h, int wd, float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
+                          int Bc, int h, int wd, float* u, float* v, float* r, float* q, float* partial, cudaStream_t st, int px) {
     (void)nchw;
     TcPlans P;
-    tc_build_plans(a, blob, &P);
+    tc_build_plans(a, blob, &P, px);
+    if (px) {
+        switch (level) {
+            case 0: return tc_run_level<3, 32, 1>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
+            case 1: return tc_run_level<32, 64, 1>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
+            case 2: return tc_run_level<64, 128, 1>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
+            default: return tc_run_level<128, 256, 1>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
+        }
+    }
     switch (level) {
-        case 0: return tc_run_level<3, 32>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
-        case 1: return tc_run_level<32, 64>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
-        case 2: return tc_run_level<64, 128>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
-        default: return tc_run_level<128, 256>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
+        case 0: return tc_run_level<3, 32, 0>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
+        case 1: return tc_run_level<32, 64, 0>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
+        case 2: return tc_run_level<64, 128, 0>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
+        default: return tc_run_level<128, 256, 0>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
     }
 }
 
 int tc_run_head(const float* r, const float* q, const float* scale, const DownW& w, const HeadW& hw, const balf_detector_arch& a,
-                const float* blob, int Bc, int hc, int wc, float* logits, float* prob, cudaStream_t st) {
+                const float* blob, int Bc, int hc, int wc, float* logits, float* prob, cudaStream_t st, int px) {
     (void)w; (void)hw;
     TcPlans P;
-    tc_build_plans(a, blob, &P);
+    tc_build_plans(a, blob, &P, px);
     UnitGeom g{hc, wc, hc / 8, wc / 8, hc * wc / 64, Bc * (hc * wc / 64), 1.0f / (float)(hc * wc / 64), 1.0f / (float)(wc / 8), 1.0f / (float)(wc / 8)};
     BALF_REQUIRE(g.total_units < (1 << 23), "internal: %d units in one pass exceed the fast_div range", g.total_units);
     const int ntiles = (g.total_units + 1) / 2;
     const size_t smem = tc_smem_bytes((uint32_t)TM * 256 * 4, P.head);
     int grid = 0;
-    BALF_REQUIRE(plan_matches<HeadG<256>>(P.head), "internal: compile-time and packed GEMM plans differ (head)");
-    if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
-    {
+    if (px) {
+        BALF_REQUIRE((plan_matches<HeadG<256, 1>>(P.head)), "internal: compile-time and packed GEMM plans differ (head, split precision)");
+        if (int e = tc_launch_cfg(tc_head_kernel<256, 1>, smem, 512, ntiles, &grid)) return e;
+        ProfScope ps("det_head", st);
+        tc_head_kernel<256, 1><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob);
+    } else {
+        BALF_REQUIRE(plan_matches<HeadG<256>>(P.head), "internal: compile-time and packed GEMM plans differ (head)");
+        if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
         ProfScope ps("det_head", st);
         tc_head_kernel<256><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob);
     }
