@@ -374,9 +374,9 @@ __global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------ pool (stages 1-3)
 // out[b, py, px, :] = max over the 2x2 window of (r * s + q)
 // swz: 0 = r, q channels-last; 1 = q in swizzled-panel tiles, r in fp16 tiles; 2 = r and q in swizzled-panel tiles (split precision)
-template <int C>
+template <int C, int swz>
 __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict__ q, const float* __restrict__ scale,
-                            int h, int w, float* __restrict__ out, size_t total, int swz) {
+                            int h, int w, float* __restrict__ out, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     constexpr int Q = C / 4;
@@ -400,7 +400,7 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             const size_t cs = swz ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
                                   : ((p * C) >> 2) + c4;
             float4 rv;
-            if (swz == 1) {
+            if constexpr (swz == 1) {
                 // r of those stages is an fp16 tile [C / 8 chunks][128 pixels][8 halves] (tc_merge_bulk_kernel)
                 const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r) + (p - rowi) * C +
                                                                      (size_t)(c4 >> 1) * (128 * 8) + rowi * 8 + (c4 & 1) * 4));
@@ -626,7 +626,10 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
     {
         ProfScope p("det_pool", st);
-        pool_kernel<C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total, swz);
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (swz == 1) pool_kernel<C, 1><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (swz == 2) pool_kernel<C, 2><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else pool_kernel<C, 0><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();

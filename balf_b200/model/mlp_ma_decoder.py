@@ -94,21 +94,24 @@ class MLP_MA_DECODER(nn.Module):
                 self.arch["proj"], self.arch["red"], downsample=i < 3))
         self.detector_head = DetectorHead(input_channel=dims[4], cell_size=self.arch["cell"])
         self._packed = None          # (key, device weight blob) cache, see _weights()
-        # 'tf32': tcgen05 tensor-core kernels, tf32 operands (round-to-nearest) with fp32 accumulation -- score maps
-        #         within rel 1e-3 of the reference;
-        # 'fp32': FFMA kernels, bit-level class of the reference's own fp32 arithmetic (rel ~2e-6);
-        # 'auto' (default): what a drop-in user of the reference expects from each call -- 'fp32' for ``forward`` and for
-        #         the demo path (detect / extract_features / extract_matches: the greedy nms_fast amplifies 1e-4 score
-        #         perturbations into different suppression chains, tf32 measured 98.9 % keypoint agreement there), 'tf32'
-        #         for the batched windowed-NMS throughput path (99.8 % agreement).  See DESIGN.md section 4.1.
+        # 'tf32':  tcgen05 tensor-core kernels, fp16 / tf32 operands (11-bit significand, round-to-nearest) with fp32
+        #          accumulation -- score maps within rel 1e-3 of the reference (measured max 7e-4, mean 1e-4);
+        # 'f16x3': the same kernels in split precision: every operand is an fp16 hi + lo pair, every product runs as three
+        #          MMAs (hi*hi + lo*hi + hi*lo) -- fp32-class score maps (measured max rel 5e-6 against the FFMA path, 100 %
+        #          greedy keypoint agreement on every tested image) at ~0.7x the 'tf32' throughput, 6x the 'fp32' one;
+        # 'fp32':  FFMA kernels, bit-level class of the reference's own fp32 arithmetic (rel ~2e-6);
+        # 'auto' (default): what a drop-in user of the reference expects from each call -- 'f16x3' for ``forward`` and for
+        #          the demo path (detect / extract_features / extract_matches: the greedy nms_fast amplifies 1e-4 score
+        #          perturbations into different suppression chains, 'tf32' measured 98.7-99.8 % keypoint agreement there),
+        #          'tf32' for the batched windowed-NMS throughput path (99.8 % agreement).  See DESIGN.md section 4.1.
         self.precision = "auto"
 
     def resolve_precision(self, nms=None):
         """the arithmetic a call runs in: an explicit ``self.precision`` wins; 'auto' -> 'tf32' for the windowed
-        (validation / throughput) extraction, 'fp32' otherwise."""
+        (validation / throughput) extraction, 'f16x3' (fp32-class results on the tensor cores) otherwise."""
         if self.precision != "auto":
             return self.precision
-        return "tf32" if nms == "windowed" else "fp32"
+        return "tf32" if nms == "windowed" else "f16x3"
 
     # -- weight blob: every floating tensor of the state_dict, concatenated in state_dict order
     def _weights(self, device):

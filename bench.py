@@ -289,16 +289,17 @@ def kernel_work_nms_greedy(images):
 
 def extras_greedy(a, dev, pk, det, args, u8):
     """configs[1] with the demo path's NMS (greedy nms_fast, demo/demo_match.py:44-57): the same batch, device-timed, in the
-    default precision of that path (fp32-class) and with tf32 opted in; per-kernel times of the NMS stage and its HBM
+    default precision of that path ('f16x3': fp32-class results on the tensor cores), on the fp32 FFMA kernels and with tf32
+    opted in; per-kernel times of the NMS stage and its HBM
     fraction (algorithmic bytes: score map read once + 16 bytes per keypoint)."""
     import copy
     import balf_b200._capi as capi
     from balf_b200.demo import demo_match
     out = {}
-    for prec in ("auto", "tf32"):
+    for prec in ("auto", "fp32", "tf32"):
         d = copy.copy(det)
         d.precision = prec
-        ms = cuda_timed(lambda: demo_match.detect_batch_device(args, u8, d, "greedy"), n=3 if prec == "auto" else 5)
+        ms = cuda_timed(lambda: demo_match.detect_batch_device(args, u8, d, "greedy"), n=3 if prec == "fp32" else 5)
         out["detector_%s" % d.resolve_precision("greedy")] = {"ms_per_step": ms, "images_per_s": a.batch / (ms * 1e-3)}
     with torch.inference_mode():
         x, (top, left) = capi.preprocess_u8(u8)
@@ -337,7 +338,7 @@ def extras_pair(dev, det, n_pairs=4):
         b_ = np.clip(a_.astype(np.int64) + rng.integers(-2, 3, (900, 1200, 1)), 0, 255).astype(np.uint8)
         pairs.append((a_, a_[..., 0].copy(), b_, b_[..., 0].copy()))
     res = {}
-    for prec in ("auto", "tf32"):
+    for prec in ("auto", "fp32", "tf32"):
         import copy
         d = copy.copy(det)
         d.precision = prec
@@ -591,7 +592,8 @@ def main():
         "metric": METRIC, "value": images * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tf32": "fp16/tf32 operands (11-bit significand), fp32 accumulate"}.get(det.resolve_precision(a.nms), det.resolve_precision(a.nms)),
+        "dtype": {"tf32": "fp16/tf32 operands (11-bit significand), fp32 accumulate",
+                  "f16x3": "fp16 hi+lo operand pairs (3 MMAs per product), fp32 accumulate"}.get(det.resolve_precision(a.nms), det.resolve_precision(a.nms)),
         "data": "synthetic",
         "config": config_of(a),
         "clocks": clocks,

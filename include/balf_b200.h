@@ -82,13 +82,15 @@ BALF_API int balf_preprocess_u8(const uint8_t* img, int B, int H, int W, int C, 
  * x [B,dims[0],Hp,Wp] fp32 NCHW, Hp and Wp multiples of 64.
  * logits [B,cell^2+1,Hp/8,Wp/8] (may be NULL), prob [B,Hp,Wp].
  * precision: 0 = fp32 FFMA (bit-level class of the reference's fp32 path),
- *            1 = TF32 tensor-core operands with fp32 accumulate (tcgen05). */
+ *            1 = tensor cores (tcgen05) on fp16 / tf32 operands (11-bit significand), fp32 accumulate: rel <= 1e-3,
+ *            2 = tensor cores in split precision ("f16x3"): every operand an fp16 hi + lo pair, every product three MMAs
+ *                (hi*hi + lo*hi + hi*lo): fp32-class score maps (measured max rel 5e-6 against precision 0). */
 BALF_API size_t balf_detector_workspace_bytes(const balf_detector_arch* arch, int B, int Hp, int Wp);
 BALF_API int balf_detector_forward(const balf_detector_arch* arch, const float* packed, const float* x, int B, int Hp,
                           int Wp, float* logits, float* prob, void* workspace, size_t workspace_bytes,
                           int precision, void* stream);
 /* development hook, no reference counterpart: key 0 = bit mask of detector stages that run on the tensor-core
- * kernels when precision = 1 (bits 0-3: the four Down stages, bit 4: the head; default all); key 1 = images per
+ * kernels when precision >= 1 (bits 0-3: the four Down stages, bit 4: the head; default all); key 1 = images per
  * internal pass of balf_detector_forward (default 16; query the workspace size again after changing it). */
 BALF_API int balf_debug_set(int key, int value);
 /* development hook: `buf` = device buffer of 8192 int64 (or NULL to switch off).  While set, CTA 0 of every tensor-core
