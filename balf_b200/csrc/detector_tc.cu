@@ -72,6 +72,7 @@ struct TcPlan {
     uint32_t bytes;       // total bytes of all blocks (resident footprint)
     uint32_t slot_bytes;  // ring slot size (largest block, 128-byte multiple)
     uint32_t nslot;       // ring slots
+    uint32_t ebias_off;   // float offset (inside the tc blob) of the [gemm][row][hi, lo, 0, 0] bias vectors the epilogues add (MergeG::ebias), or 0
     long long* trace;     // development hook (balf_debug_set_trace): clock stamps of CTA 0, or null
 };
 long long* g_tc_trace = nullptr;
@@ -192,12 +193,17 @@ template <int CIN, int C, int PX = 0> struct BranchG {
 template <int CIN, int C, int PX = 0> struct MergeG {
     static constexpr int count = MG_COUNT;
     static constexpr bool x3 = PX != 0;
-    static constexpr bool resident = PX ? C <= 32 : C <= 64;   // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions
+    // C = 64: 64 KB of weights (dense2 in fp16) next to the 128 KB of tile regions.  C = 128 (single-rounded operands): the five
+    // fp16 weight matrices (144 KB) stay resident next to a 64 KB operand region -- the streamed version was bound by the bytes
+    // the ring keeps in flight (the issuing lane waited 2-6 k cycles per GEMM for weights, scripts/tc_trace.py) -- which leaves no
+    // room for the bias blocks: the epilogues add the biases (`ebias`, from the plan's fp32 bias vectors) instead of an MMA.
+    static constexpr bool ebias = C == 128 && PX == 0;
+    static constexpr bool resident = PX ? C <= 32 : C <= 128;
     static constexpr int cap = 32768;
-    static constexpr int nslot = PX ? (C == 64 ? 3 : 2) : (C == 256 ? 2 : 3);   // C = 128: 96 KB of operand regions leave room for three 36 KB slots
+    static constexpr int nslot = PX ? (C == 64 ? 3 : 2) : (C == 256 ? 2 : 3);
     __host__ __device__ static constexpr int rows(int) { return C; }
     __host__ __device__ static constexpr int K(int gi) { return gi == MG_CONV0 ? tc_kin(CIN) : C; }
-    __host__ __device__ static constexpr bool bias(int gi) { return gi != MG_PD2A; }
+    __host__ __device__ static constexpr bool bias(int gi) { return !ebias && gi != MG_PD2A; }
     // stages 1-2: u' / v' cross HBM as fp16 tiles (same 11-bit significand as the tf32 operands they replace, half the
     // bytes of the HBM-bound merge kernels), so dense2 runs as kind::f16 on fp16 weights
     // conv1 / conv2 (A operands written by the epilogues) run on fp16 operands at every stage
@@ -1195,13 +1201,19 @@ __device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int t
 }
 
 // ------------------------------------------------------------------------------------------ merge kernel
+__device__ __forceinline__ int col0_of(int tid, int ch) { return (tid >> 7) * ch; }
 template <int C, int PX = 0> struct MergeCfg {
     static constexpr int CH = C / 2;
     // C = 128: u' and v' (swizzled panel tiles, tf32-rounded by the branch kernels) arrive by bulk copy -- u' into a second
     // region a tile ahead, v' into the first as soon as conv.0 has released it -- and conv.0 shares its phase with dense2(u')
     static constexpr bool bulk_uv = C == 128;
     static constexpr uint32_t uv_bytes = (uint32_t)TM * C * (PX ? 4u : 2u);                 // an fp16 u' / v' tile (hi + lo: PX)
-    static constexpr uint32_t region = (uint32_t)TM * C * 4 + (bulk_uv ? uv_bytes : 0u);   // + the u' tile
+    // compact layout (C = 128, single-rounded operands, resident weights): the u' tile lands in the second half of the fp32-sized
+    // region, which the exact-fp32 staging of r (channel sums) overwrites at the end of the tile -- so the next u' is requested
+    // after the sums and arrives under the next tile's input store and conv.0
+    static constexpr bool two = C == 128 && PX == 0;
+    static constexpr uint32_t r2_off = two ? (uint32_t)TM * C * 2 : (uint32_t)TM * C * 4;
+    static constexpr uint32_t region = two ? (uint32_t)TM * C * 4 : (uint32_t)TM * C * 4 + (bulk_uv ? uv_bytes : 0u);   // + the u' tile
     static constexpr int col_x0 = 0, col_acc = C;
     static constexpr int ncols = tc_cols(2 * C);
     static constexpr int min_ctas = C <= 32 ? 3 : C <= 64 ? 2 : 1;
@@ -1225,9 +1237,16 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const bool w0 = warp0_uniform();
     tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
+    if constexpr (G::ebias) {             // fp32 biases of conv.0, dense2, conv1, conv2 -> vec[g * C + c] (first read after the next barrier)
+        for (int i = tid; i < 4 * C; i += NT2) {
+            const float2 e = __ldg(reinterpret_cast<const float2*>(plan.base + plan.ebias_off + (size_t)i * 4));
+            s.vec[i] = e.x + e.y;
+        }
+    }
+    const float* const eb = s.vec + col0_of(tid, CH);
     const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
-    const uint32_t r2_addr = region_addr + (uint32_t)TM * C * 4;            // bulk_uv: u' tiles land here
+    const uint32_t r2_addr = region_addr + Cfg::r2_off;                     // bulk_uv: u' tiles land here
     uint64_t* const ld_u = s.aux;
     uint64_t* const ld_v = &s.gdone[1];
     constexpr uint32_t kTileBytes = Cfg::uv_bytes;                         // u' / v' tiles are fp16 (chunk-major; hi then lo chunks: PX)
@@ -1288,14 +1307,14 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             if (w0 && elect_one()) {
                 mbar_expect_tx(ld_v, kTileBytes);
                 bulk_load(region_addr, vin + (size_t)t * tile_floats, kTileBytes, ld_v);
-                if (t + (int)gridDim.x < ntiles) {
+                if (!Cfg::two && t + (int)gridDim.x < ntiles) {
                     mbar_expect_tx(ld_u, kTileBytes);
                     bulk_load(r2_addr, uin + (size_t)(t + gridDim.x) * tile_floats, kTileBytes, ld_u);
                 }
             }
             ld_row<CH>(lane_base + Cfg::col_x0 + col0, v);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(G::ebias ? v[i] + eb[i] : v[i], 0.f);
             st_row<CH>(lane_base + Cfg::col_x0 + col0, v);
             // ---- phase 2: dense2(v') accumulates (no thread wrote an operand: the elected lane issues as soon as v' is in)
             if (w0 && elect_one()) {
@@ -1351,7 +1370,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
 #pragma unroll
                 for (int i = 0; i < SC; i += 2) {
                     const unsigned long long xz = pk2(x0[i], x0[i + 1]);
-                    const unsigned long long x1 = add2(pk2(v[c + i], v[c + i + 1]), xz);
+                    unsigned long long x1 = add2(pk2(v[c + i], v[c + i + 1]), xz);
+                    if constexpr (G::ebias) x1 = add2(x1, pk2(eb[C + c + i], eb[C + c + i + 1]));
                     s2 = add2(s2, x1);
                     q2 = fma2(x1, x1, q2);
                     upk2(x1, v[c + i], v[c + i + 1]);
@@ -1374,6 +1394,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
 #pragma unroll
         for (int i = 0; i < CH; i += 2) {          // LeakyReLU(0.2) = max(v, 0.2 v)
+            if constexpr (G::ebias) { v[i] += eb[2 * C + i]; v[i + 1] += eb[2 * C + i + 1]; }
             float l0, l1;
             upk2(mul2(pk2(v[i], v[i + 1]), pk2(0.2f, 0.2f)), l0, l1);
             v[i] = fmaxf(v[i], l0); v[i + 1] = fmaxf(v[i + 1], l1);
@@ -1387,6 +1408,10 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 15);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
+        if constexpr (G::ebias) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] += eb[3 * C + i];
+        }
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
             const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -1395,7 +1420,14 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         pair_store<CH / 4>(rout, row_off, v, valid);
         __syncthreads();
         unit_channel_sums<C>(s.region, t, geo.total_units, partial);
+        if constexpr (Cfg::two) fence_async_smem();                   // generic reads of the staging tile before the async write below
         __syncthreads();
+        if constexpr (Cfg::two) {
+            if (t + (int)gridDim.x < ntiles && w0 && elect_one()) {
+                mbar_expect_tx(ld_u, kTileBytes);
+                bulk_load(r2_addr, uin + (size_t)(t + gridDim.x) * tile_floats, kTileBytes, ld_u);
+            }
+        }
     }
     tc_finish(tm, Cfg::ncols);
 }
@@ -1830,14 +1862,16 @@ static void tc_build_plans_px(const balf_detector_arch& a, const float* base, Tc
         TcPlan& m = P.merge[l];
         m = TcPlan{};
         m.base = base; m.ngemm = MG_COUNT;
-        m.resident = px ? c <= 32 : c <= 64;                           // mirrors MergeG::resident
+        m.resident = px ? c <= 32 : c <= 128;                          // mirrors MergeG::resident
         m.nslot = px ? (c == 64 ? 3 : 2) : (c == 256 ? 2 : 3);         // mirrors MergeG::nslot / MergeG::cap
         const int mcap = 32768;
-        tc_add(m, MG_CONV0, off, c, cin, true, mcap, a.dims[l] >= 8 ? hm : 0);
+        const bool ebias = c == 128 && !px;                            // mirrors MergeG::ebias: biases added by the epilogues
+        tc_add(m, MG_CONV0, off, c, cin, !ebias, mcap, a.dims[l] >= 8 ? hm : 0);
         tc_add(m, MG_PD2A, off, c, c, false, mcap, hm);               // mirrors MergeG::h16
-        tc_add(m, MG_PD2B, off, c, c, true, mcap, hm);
-        tc_add(m, MG_RC1, off, c, c, true, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
-        tc_add(m, MG_RC2, off, c, c, true, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
+        tc_add(m, MG_PD2B, off, c, c, !ebias, mcap, hm);
+        tc_add(m, MG_RC1, off, c, c, !ebias, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
+        tc_add(m, MG_RC2, off, c, c, !ebias, mcap, (px || c > BALF_RC16_MINC) ? hm : 0);
+        if (ebias) { m.ebias_off = (uint32_t)off; off += (size_t)4 * c * 4; }     // [conv.0, dense2, conv1, conv2][row][hi, lo, 0, 0]
     }
     TcPlan& h = P.head;
     h = TcPlan{};
@@ -1883,6 +1917,11 @@ static void tc_pack_one(const TcPlan& p, int gi, const float* wT, int ld, int n0
     if (g.bias)   // two chunk planes after the last block's kb columns; the second stays zero (blob is memset)
         tc_pack_bias_kernel<<<cdiv(g.rows, 128), 128, 0, st>>>(wT, ld, n0, g.rows, k_real, bias, f.beta, f.alpha, f.add,
                                                                blob + g.goff + (size_t)g.rows * k_pad / (g.h16 == 1 ? 2 : 1));
+    else if (p.ebias_off && bias) {   // biases added by the epilogues: the same folded (hi, lo) pairs, in the plan's bias-vector area
+        const int slot = gi == MG_CONV0 ? 0 : gi == MG_PD2B ? 1 : gi == MG_RC1 ? 2 : 3;
+        tc_pack_bias_kernel<<<cdiv(g.rows, 128), 128, 0, st>>>(wT, ld, n0, g.rows, k_real, bias, f.beta, f.alpha, f.add,
+                                                               blob + p.ebias_off + (size_t)slot * g.rows * 4);
+    }
 }
 
 // fp32-path packed weights (DetW) -> tc blob

@@ -19,6 +19,7 @@ dev = torch.device("cuda:0")
 cfg = test_utils.get_cfg_from_yaml_file(config.DEFAULT_CFG)
 torch.manual_seed(0)
 det = get_model.load_model(cfg["model"]).eval().to(dev)
+det.precision = "tf32"
 x = torch.rand(B, 3, 512, 640, device=dev)
 with torch.inference_mode():
     det(x); det(x)
