@@ -45,6 +45,9 @@ using namespace umma;
 #ifndef BALF_MERGE32_CTAS
 #define BALF_MERGE32_CTAS 3
 #endif
+#ifndef BALF_MERGE_TPR
+#define BALF_MERGE_TPR 2      // threads per pixel row of the stage 3-4 merge kernels (4 = 16 epilogue warps per SM: measured no gain, 0.85 -> 0.88 ms at C = 128)
+#endif
 #ifndef BALF_RC16_MINC
 #define BALF_RC16_MINC 32     // conv1 / conv2 of the merge kernels run on fp16 operands for C > this
 #endif
@@ -1176,9 +1179,9 @@ tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom g
 // channel attention).  Every thread takes part: a group of TPP lanes owns one (unit, 4-channel chunk) pair, each lane adds
 // 64 / TPP rows with float4 loads, then an xor butterfly inside the group -- a fixed order, so the result is bit-identical
 // run to run.  (The first version used 2C threads x 64 dependent scalar loads: ~2000 cycles of exposed latency per tile.)
-template <int C>
+template <int C, int NTH = NT2>
 __device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int total_units, float* __restrict__ partial) {
-    constexpr int CQ = C / 4, PAIRS = 2 * CQ, TPP = NT2 / PAIRS, RPT = 64 / TPP;
+    constexpr int CQ = C / 4, PAIRS = 2 * CQ, TPP = NTH / PAIRS, RPT = 64 / TPP;
     static_assert(TPP >= 2 && TPP <= 16, "group must fit in a warp");
     const int tid = threadIdx.x, pair = tid / TPP, sub = tid % TPP;
     const int uu = pair / CQ, ch = pair % CQ;
@@ -1203,7 +1206,13 @@ __device__ __forceinline__ void unit_channel_sums(const float* reg, int t, int t
 // ------------------------------------------------------------------------------------------ merge kernel
 __device__ __forceinline__ int col0_of(int tid, int ch) { return (tid >> 7) * ch; }
 template <int C, int PX = 0> struct MergeCfg {
-    static constexpr int CH = C / 2;
+    // threads per pixel row.  scripts/tc_trace.py at C = 128: the two epilogues that also store q / r take 5.6 k + 7.1 k of a
+    // tile's 22 k cycles; four threads per row (16 warps) did not shorten them -- the 16-byte-per-row global stores touch 16
+    // different 128-byte lines per warp instruction and queue in the L1 (one line per cycle), not in the issue slots
+    static constexpr int TPR = (C >= 128 && PX == 0) ? BALF_MERGE_TPR : 2;
+    static constexpr int NT = TM * TPR;
+    static constexpr uint32_t xch = 2u * TPR * TM * 8u;
+    static constexpr int CH = C / TPR;
     // C = 128: u' and v' (swizzled panel tiles, tf32-rounded by the branch kernels) arrive by bulk copy -- u' into a second
     // region a tile ahead, v' into the first as soon as conv.0 has released it -- and conv.0 shares its phase with dense2(u')
     static constexpr bool bulk_uv = C == 128;
@@ -1220,16 +1229,16 @@ template <int C, int PX = 0> struct MergeCfg {
 };
 
 template <int CIN, int C, int PX = 0>
-__global__ void __launch_bounds__(NT2, MergeCfg<C, PX>::min_ctas)
+__global__ void __launch_bounds__(MergeCfg<C, PX>::NT, MergeCfg<C, PX>::min_ctas)
 tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
                 const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = MergeCfg<C, PX>;
     using G = MergeG<CIN, C, PX>;
-    constexpr int CH = Cfg::CH;
+    constexpr int CH = Cfg::CH, TPR = Cfg::TPR, NTK = Cfg::NT;
     constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;      // operand mode of the loaders, lo-chunk offset of a K = C operand
     (void)w;
-    const TcShared s = carve(smem, Cfg::region, plan);
+    const TcShared s = carve(smem, Cfg::region, plan, 1, Cfg::xch);
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
     const int ntiles = (geo.total_units + 1) / 2;
     const uint32_t my_tiles = blockIdx.x < (unsigned)ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -1238,7 +1247,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     tc_prologue<G::nslot>(s, Cfg::ncols, ring, plan, my_tiles, w0);
     const uint32_t tm = *s.tmem_slot;
     if constexpr (G::ebias) {             // fp32 biases of conv.0, dense2, conv1, conv2 -> vec[g * C + c] (first read after the next barrier)
-        for (int i = tid; i < 4 * C; i += NT2) {
+        for (int i = tid; i < 4 * C; i += NTK) {
             const float2 e = __ldg(reinterpret_cast<const float2*>(plan.base + plan.ebias_off + (size_t)i * 4));
             s.vec[i] = e.x + e.y;
         }
@@ -1257,7 +1266,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
     int it = 0;
-    InputPf<CIN> pf;                       // next tile's level input
+    InputPf<CIN, TPR> pf;                  // next tile's level input
     InputPf<C> pfu;                        // this tile's u' / v' rows, requested one phase ahead (C <= 32)
     auto coords = [&](int tt, bool& vld, int& im, int& px) {
         const int un = 2 * tt + ug;
@@ -1265,10 +1274,10 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         im = vld ? fast_div(un, geo.upi, geo.inv_upi) : 0;
         px = (vld ? un - im * geo.upi : 0) * 64 + tok;
     };
-    if (InputPf<CIN>::enabled && (int)blockIdx.x < ntiles) {
+    if (InputPf<CIN, TPR>::enabled && (int)blockIdx.x < ntiles) {
         bool vld; int im, px;
         coords(blockIdx.x, vld, im, px);
-        fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+        fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
     }
     if (Cfg::bulk_uv && (int)blockIdx.x < ntiles && w0 && elect_one()) {
         mbar_expect_tx(ld_u, kTileBytes);
@@ -1281,15 +1290,15 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         const size_t row_off = ((size_t)img * npix + pix) * C + col0;
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
-        if (InputPf<CIN>::enabled) {
-            store_input_row<CIN, true, 2, HM>(pf, s.region, row, half);
+        if (InputPf<CIN, TPR>::enabled) {
+            store_input_row<CIN, true, TPR, HM>(pf, s.region, row, half);
             if (t + (int)gridDim.x < ntiles) {
                 bool vld; int im, px;
                 coords(t + gridDim.x, vld, im, px);
-                fetch_input_row<CIN>(xin, npix, (size_t)im, px, vld, half, pf);
+                fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
             }
         } else {
-            load_input_row<CIN, 2, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<CIN, TPR, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
@@ -1339,7 +1348,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
             fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
         } else {
-            load_input_row<C, 2, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<C, TPR, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
@@ -1348,7 +1357,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         if (InputPf<C>::enabled) store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
-        else load_input_row<C, 2, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        else load_input_row<C, TPR, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
@@ -1361,7 +1370,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             float rstd, shift;
             ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
             float sum = 0.f, sq = 0.f;
-            constexpr int SC = CH > 64 ? 64 : CH;
+            constexpr int SC = TPR == 4 ? (CH < 32 ? CH : 32) : CH > 64 ? 64 : CH;
             unsigned long long s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < CH; c += SC) {
@@ -1380,7 +1389,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                 pair_store<SC / 4>(qout, row_off + c, x0, valid);
             }
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            row_stats<1, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
             row_to_a16<CH, LOC>(v, s.region, row, col0);
         }
@@ -1419,7 +1428,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         }
         pair_store<CH / 4>(rout, row_off, v, valid);
         __syncthreads();
-        unit_channel_sums<C>(s.region, t, geo.total_units, partial);
+        unit_channel_sums<C, NTK>(s.region, t, geo.total_units, partial);
         if constexpr (Cfg::two) fence_async_smem();                   // generic reads of the staging tile before the async write below
         __syncthreads();
         if constexpr (Cfg::two) {
@@ -2049,10 +2058,10 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     } else {
         const TcPlan& p = P.merge[level];
         BALF_REQUIRE((!MergeCfg<C, PX>::bulk_uv || g.total_units % 2 == 0), "internal: odd unit count at stage %d", level);
-        const size_t smem = tc_smem_bytes(MergeCfg<C, PX>::region, p);
-        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C, PX>, smem, MergeCfg<C, PX>::ncols, ntiles, &grid)) return e;
+        const size_t smem = tc_smem_bytes(MergeCfg<C, PX>::region, p, 1, MergeCfg<C, PX>::xch);
+        if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C, PX>, smem, MergeCfg<C, PX>::ncols, ntiles, &grid, 1, MergeCfg<C, PX>::NT)) return e;
         ProfScope ps(C == 128 ? "det_merge_c128" : "det_merge_c256", st);
-        tc_merge_kernel<CIN, C, PX><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+        tc_merge_kernel<CIN, C, PX><<<grid, MergeCfg<C, PX>::NT, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
     }
     BALF_COUNT_LAUNCH(3);
     BALF_LAUNCH_OK();

@@ -14,7 +14,9 @@ timeout 600 ncu --set full --clock-control none -k regex:"nms15_kernel|select_so
 timeout 600 ncu --set full --clock-control none -k regex:"greedy_cells" -s 24 -c 8 -f -o gpurun_out/prof_greedy $B --nms greedy --precision tf32 > gpurun_out/ncu_greedy.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"hn_tc_" -s 9 -c 9 -f -o gpurun_out/prof_hn python scripts/hn_bench.py > gpurun_out/ncu_hn.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"nn2_tc_kernel|merge_splits_kernel|smnn_select_kernel" -s 4 -c 4 -f -o gpurun_out/prof_smnn python scripts/smnn_bench.py > gpurun_out/ncu_smnn.log 2>&1
-for r in prof prof_nms prof_greedy prof_hn prof_smnn; do
+timeout 1200 ncu --set full --clock-control none -k regex:"tc_branch_kernel|tc_merge_bulk_kernel|tc_merge_kernel|tc_head_kernel" -s 45 -c 15 \
+    -f -o gpurun_out/prof_x3 $B --nms greedy > gpurun_out/ncu_x3.log 2>&1
+for r in prof prof_nms prof_greedy prof_hn prof_smnn prof_x3; do
   ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null
   rm -f gpurun_out/$r.ncu-rep
 done

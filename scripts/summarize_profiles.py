@@ -153,5 +153,6 @@ if __name__ == "__main__":
     full(tag, "prof_hn.ncu-rep", "_ncu_hardnet.md", "the HardNet tensor-core kernels (scripts/hn_bench.py, 4096 patches)")
     full(tag, "prof_greedy.ncu-rep", "_ncu_greedy.md", "the cell-based greedy NMS kernels (bench.py --nms greedy, 64 maps)")
     full(tag, "prof_smnn.ncu-rep", "_ncu_smnn.md", "the SMNN kernels (scripts/smnn_bench.py, 2048 x 2048)")
+    full(tag, "prof_x3.ncu-rep", "_ncu_f16x3.md", "the detector kernels in split precision (bench.py --nms greedy: precision f16x3, 64 images)")
     traffic()
     bench(tag)
