@@ -712,6 +712,64 @@ __device__ __forceinline__ void pair_store(float* __restrict__ out, size_t own_o
         }
     }
 }
+// ---- full-LINE global accesses.  The pair layout above still touches 16 different 128-byte lines per warp instruction, and the
+// L1 processes one line per ~2 cycles (the stage 3-4 kernels, whose rows are 512-1024 bytes apart, spent a quarter to a half of
+// their time queued there while every ncu pipe looked idle).  Groups of 8 lanes (8 consecutive rows) transpose 8 x 8 blocks of
+// 16-byte chunks by shuffle so that each group writes 128 contiguous bytes of ONE row per instruction: 4 lines per instruction.
+__device__ __forceinline__ float4 shfl_xor_f4(float4 v, int m) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                       __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+// a[k] on lane j (of its group of 8) <-> a[j] on lane k
+__device__ __forceinline__ void transpose8(float4 (&a)[8]) {
+    const int j = threadIdx.x & 7;
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+        const bool up = (j & s) != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((k & s) != 0) continue;
+            const float4 recv = shfl_xor_f4(up ? a[k] : a[k | s], s);
+            if (up) a[k] = recv; else a[k | s] = recv;
+        }
+    }
+}
+// store this lane's N consecutive chunks (v[4 * c ..]) of its row at out + own_off (floats); the rows of a group of 8 lanes are
+// `stride` floats apart (consecutive pixels of a channels-last tensor) and share `valid`
+template <int N>
+__device__ __forceinline__ void oct_store(float* __restrict__ out, size_t own_off, int stride, const float* v, bool valid) {
+    static_assert(N % 8 == 0, "blocks of 8 chunks");
+    const int j = threadIdx.x & 7;
+    float* const base = out + own_off - (size_t)j * stride + 4 * j;      // row 0 of the group, this lane's chunk column
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        float4 a[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = make_float4(v[4 * (c0 + c)], v[4 * (c0 + c) + 1], v[4 * (c0 + c) + 2], v[4 * (c0 + c) + 3]);
+        transpose8(a);                                                     // a[k] = chunk c0 + j of row k
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(base + (size_t)k * stride + 4 * c0) = a[k];
+        }
+    }
+}
+// the mirror image: N consecutive chunks of this lane's row, loaded as full lines and transposed back
+template <int N>
+__device__ __forceinline__ void oct_load(const float* __restrict__ in, size_t own_off, int stride, bool valid, float4 (&v)[N]) {
+    static_assert(N % 8 == 0, "blocks of 8 chunks");
+    const int j = threadIdx.x & 7;
+    const float* const base = in + own_off - (size_t)j * stride + 4 * j;
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        float4 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            a[k] = valid ? __ldg(reinterpret_cast<const float4*>(base + (size_t)k * stride + 4 * c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        transpose8(a);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c0 + c] = a[c];
+    }
+}
 // pair layout -> this lane's own chunks k, k+1 (call with the same k on every lane)
 __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
     const bool odd = (threadIdx.x & 1) != 0;
@@ -721,9 +779,10 @@ __device__ __forceinline__ void pair_unswap(float4& c0, float4& c1) {
 
 // this thread's part (1 / TPR) of a pixel row of the level input -> A operand (chunk-major, 128 rows), K padded to >= 8
 // H16: 1 = the operand is fp16 (two 4-channel chunks -> one 16-byte chunk of 8 halves), 2 = fp16 hi + lo (lo chunks CIN / 8 further)
+// ostride > 0: the rows of a group of 8 lanes are `ostride` floats apart -> full-line loads (oct_load) instead of the pair layout
 template <int CIN, int TPR = 2, int H16 = 0>
 __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid,
-                                               float* dst, int row, int half) {
+                                               float* dst, int row, int half, int ostride = 0) {
     if constexpr (CIN < 8) {                       // NCHW network input: part 0 gathers the planes, part 1 zero-fills
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (half == 0 && valid) {
@@ -739,10 +798,16 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
 #pragma unroll 1
         for (int j0 = 0; j0 < N; j0 += NB) {
             float4 v[NB];
-            pair_load<NB>(src + j0, valid, v);
+            const bool oct = NB % 8 == 0 && ostride > 0;        // (uniform)
+            if constexpr (NB % 8 == 0) {
+                if (oct) oct_load<NB>(xin, (img * npix + pix) * CIN + (size_t)(half * N + j0) * 4, ostride, valid, v);
+                else pair_load<NB>(src + j0, valid, v);
+            } else {
+                pair_load<NB>(src + j0, valid, v);
+            }
 #pragma unroll
             for (int j = 0; j < NB; j += 2) {
-                pair_unswap(v[j], v[j + 1]);
+                if (!oct) pair_unswap(v[j], v[j + 1]);
                 if constexpr (H16 != 0) {
                     const float e[8] = {v[j].x, v[j].y, v[j].z, v[j].w, v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
                     uint32_t h[4], l[4];
@@ -920,6 +985,8 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     const int ug = (row & 31) >> 4, tok = (row >> 5) * 16 + (row & 15);   // unit / token of this lane
     const int col0 = half * CH;                                           // this thread's channel range
     const float mix_b1 = __ldg(br.gd_b + tok) + 1.0f;
+    // float distance between the rows of 8 consecutive lanes (8 consecutive tokens: a block row, or 8 grid cells fw pixels apart)
+    const int ostride = (BR == 0 ? geo.fw : 1) * C;
     const size_t npix = (size_t)geo.h * geo.w;
     uint32_t phase = 0, xb = 0;
     int it = 0;
@@ -1001,6 +1068,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
             if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
+            else if constexpr (CH % 32 == 0 && !X3) oct_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, ostride, v, valid);
             else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
@@ -1133,6 +1201,10 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                     // kernel stream them into its operand regions asynchronously, no register pass.  Low bits cleared:
                     // the C >= 128 merge kernels round again when they load, which must be a no-op
                     if ((BR == 1 || Cfg::swz_out) && !X3) o[j] = to_tf32_clean(o[j]);
+                }
+                if constexpr (SC % 32 == 0 && !X3 && !Cfg::swz_out) {      // full-line stores (see oct_store)
+                    oct_store<SC / 4>(out, ((size_t)img * npix + pix) * C + col0 + c, ostride, reinterpret_cast<const float*>(o), valid);
+                    continue;
                 }
 #pragma unroll
                 for (int j = 0; j < SC / 4; j += 2) {
@@ -1298,7 +1370,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                 fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
             }
         } else {
-            load_input_row<CIN, TPR, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<CIN, TPR, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : CIN);
         }
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
@@ -1348,7 +1420,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
             fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
         } else {
-            load_input_row<C, TPR, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half);
+            load_input_row<C, TPR, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : C);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
@@ -1357,7 +1429,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         if (InputPf<C>::enabled) store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
-        else load_input_row<C, TPR, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half);
+        else load_input_row<C, TPR, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : C);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
@@ -1386,7 +1458,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
                     upk2(x1, v[c + i], v[c + i + 1]);
                     upk2(add2(x1, xz), x0[i], x0[i + 1]);
                 }
-                pair_store<SC / 4>(qout, row_off + c, x0, valid);
+                if constexpr (SC % 32 == 0 && PX == 0) oct_store<SC / 4>(qout, row_off + c, C, x0, valid); else pair_store<SC / 4>(qout, row_off + c, x0, valid);
             }
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats<1, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift);
@@ -1426,7 +1498,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
         }
-        pair_store<CH / 4>(rout, row_off, v, valid);
+        if constexpr (CH % 32 == 0 && PX == 0) oct_store<CH / 4>(rout, row_off, C, v, valid); else pair_store<CH / 4>(rout, row_off, v, valid);
         __syncthreads();
         unit_channel_sums<C, NTK>(s.region, t, geo.total_units, partial);
         if constexpr (Cfg::two) fence_async_smem();                   // generic reads of the staging tile before the async write below
@@ -1673,10 +1745,15 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
 #pragma unroll 1
         for (int j0 = 0; j0 < CH / 4; j0 += 8) {            // full-sector pair loads of r and q, 8 chunks at a time
             float4 rv[8], qv[8];
-            pair_load<8>(reinterpret_cast<const float4*>(r + row_off) + j0, valid, rv);
-            pair_load<8>(reinterpret_cast<const float4*>(q + row_off) + j0, valid, qv);
+            if constexpr (PX == 0) {              // full-line loads (see oct_load)
+                oct_load<8>(r, row_off + (size_t)j0 * 4, C, valid, rv);
+                oct_load<8>(q, row_off + (size_t)j0 * 4, C, valid, qv);
+            } else {
+                pair_load<8>(reinterpret_cast<const float4*>(r + row_off) + j0, valid, rv);
+                pair_load<8>(reinterpret_cast<const float4*>(q + row_off) + j0, valid, qv);
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) { pair_unswap(rv[j], rv[j + 1]); pair_unswap(qv[j], qv[j + 1]); }
+                for (int j = 0; j < 8; j += 2) { pair_unswap(rv[j], rv[j + 1]); pair_unswap(qv[j], qv[j + 1]); }
+            }
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {                  // two 4-channel chunks -> one fp16 chunk of 8 channels
                 float e[8];
