@@ -1806,10 +1806,19 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
                     for (int n = 0; n < 65; ++n) logits[((size_t)img * nlog + n) * npix + pix] = z[n];
                 }
                 const float inv = 1.0f / den;
+                if (cell == 8) {                 // 8 x 8 cell: two 16-byte stores per output row (a quarter of the store instructions)
+#pragma unroll
+                    for (int n = 0; n < 64; n += 4) {
+                        const int yy = cy * 8 + (n >> 3), xx = cx * 8 + (n & 7);
+                        *reinterpret_cast<float4*>(prob + ((size_t)img * Hp + yy) * Wp + xx) =
+                            make_float4(expf(z[n] - mx) * inv, expf(z[n + 1] - mx) * inv, expf(z[n + 2] - mx) * inv, expf(z[n + 3] - mx) * inv);
+                    }
+                } else {
 #pragma unroll
                 for (int n = 0; n < 64; ++n) {
                     const int yy = cy * cell + (n >> 3), xx = cx * cell + (n & 7);
                     prob[((size_t)img * Hp + yy) * Wp + xx] = expf(z[n] - mx) * inv;
+                }
                 }
             }
         }

@@ -850,24 +850,6 @@ static int run_greedy_cells(const MapView& mv, const NmsWs& ws, const CellWs& cw
 }
 
 // ------------------------------------------------------------------------------------------ select + sort
-// Warp-aggregated counters.  The selection counts / appends thousands of keys through ONE shared counter and, on the nearly
-// flat score maps of this detector, builds digit histograms in which every key falls into the same bin: same-address
-// shared-memory atomics serialise (measured: half of select_sort_kernel's time).  One atomic per warp (per distinct bin) instead.
-// All 32 lanes must call these (loops below run warp-uniform trip counts).
-__device__ __forceinline__ int warp_slot(int* ctr, bool pred) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return -1;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(ctr, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
-}
-__device__ __forceinline__ void warp_hist_add(unsigned* hist, bool valid, unsigned bin) {
-    const int lane = threadIdx.x & 31;
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? bin : (0x100u | (unsigned)lane));
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
-}
 // k-th largest value of field(key) among keys satisfying pred -- MSB-first byte-wise radix select.
 template <typename Pred, typename Field>
 __device__ u64 radix_select(const u64* keys, int n, int kth, int nbytes, Pred pred, Field field, unsigned* hist,
@@ -877,19 +859,12 @@ __device__ u64 radix_select(const u64* keys, int n, int kth, int nbytes, Pred pr
     for (int shift = (nbytes - 1) * 8; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i0 = threadIdx.x & ~31; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + (threadIdx.x & 31);
-            bool valid = false;
-            unsigned bin = 0;
-            if (i < n) {
-                const u64 k = keys[i];
-                if (pred(k)) {
-                    const u64 f = field(k);
-                    valid = (f & mask) == prefix;
-                    bin = (unsigned)(f >> shift) & 255u;
-                }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 k = keys[i];
+            if (pred(k)) {
+                u64 f = field(k);
+                if ((f & mask) == prefix) atomicAdd(&hist[(unsigned)(f >> shift) & 255u], 1u);
             }
-            warp_hist_add(hist, valid, bin);
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -1024,35 +999,27 @@ __global__ void __launch_bounds__(1024) select_sort_kernel(NmsWs ws, int mode, i
         if (threadIdx.x == 0) n_sel = n;
     } else if (mode == 1) {
         u64 kth = radix_select(keys, n, k, 8, all, [](u64 q) { return q; }, hist, xch);
-        for (int i0 = threadIdx.x & ~31; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + (threadIdx.x & 31);
-            const u64 q = i < n ? keys[i] : 0ull;
-            const int slot = warp_slot(&n_sel, i < n && q >= kth);     // keys are unique -> exactly k
-            if (slot >= 0) sel[slot] = q;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 q = keys[i];
+            if (q >= kth) sel[atomicAdd(&n_sel, 1)] = q;      // keys are unique -> exactly k
         }
     } else {
         // t = k-th largest score; keep score >= t, and if ties at t overflow k keep the k
         // raster-first of them (even over higher scores) -- quirk (i) of find_index_higher_scores
         u64 t = radix_select(keys, n, k, 4, all, [](u64 q) { return q >> 32; }, hist, xch);
-        for (int i0 = threadIdx.x & ~31; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + (threadIdx.x & 31);
-            const u64 s = i < n ? keys[i] >> 32 : 0ull;
-            const unsigned gt = __ballot_sync(0xffffffffu, i < n && s > t), eq = __ballot_sync(0xffffffffu, i < n && s == t);
-            if ((threadIdx.x & 31) == 0) {
-                if (gt) atomicAdd(&c_gt, __popc(gt));
-                if (eq) atomicAdd(&c_eq, __popc(eq));
-            }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 s = keys[i] >> 32;
+            if (s > t) atomicAdd(&c_gt, 1);
+            else if (s == t) atomicAdd(&c_eq, 1);
         }
         __syncthreads();
         u64 low = 0;
         if (c_gt + c_eq > k)
             low = radix_select(keys, n, k, 4, [t](u64 q) { return (q >> 32) >= t; },
                                [](u64 q) { return q & 0xFFFFFFFFull; }, hist, xch);
-        for (int i0 = threadIdx.x & ~31; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + (threadIdx.x & 31);
-            const u64 q = i < n ? keys[i] : 0ull;
-            const int slot = warp_slot(&n_sel, i < n && (q >> 32) >= t && (q & 0xFFFFFFFFull) >= low);
-            if (slot >= 0) sel[slot] = q;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 q = keys[i];
+            if ((q >> 32) >= t && (q & 0xFFFFFFFFull) >= low) sel[atomicAdd(&n_sel, 1)] = q;
         }
     }
     __syncthreads();

@@ -104,13 +104,13 @@ def traffic():
             d = dict(zip(head, r))
             kn = d.get("Kernel Name", "")
             name = None
-            m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)?>", kn)
+            m = re.search(r"tc_branch_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)*>", kn)
             if m:
                 name = "det_branch_%s_c%s" % ("grid" if m.group(3) == "0" else "block", m.group(2))
-            m = re.search(r"tc_merge(?:_bulk)?_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kn)
+            m = re.search(r"tc_merge(?:_bulk)?_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)*>", kn)
             if m:
                 name = "det_merge_c%s" % m.group(2)
-            m = re.search(r"pool_kernel<\(?(?:int\))?(\d+)>", kn)
+            m = re.search(r"pool_kernel<\(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)*>", kn)
             if m:
                 name = "det_pool_c%s" % m.group(1)
             if "tc_head_kernel" in kn:
