@@ -1529,9 +1529,12 @@ template <int CIN, int C, int PX = 0> struct MergeBulkCfg {
     static constexpr bool cc0 = CIN < 8;
     static constexpr uint32_t tile_bytes = (uint32_t)TM * C * 4;      // W / Q staging tiles (fp32)
     static constexpr uint32_t uv_bytes = (uint32_t)TM * C * (PX ? 4u : 2u);   // u' / v' tiles (fp16, chunk-major; hi then lo chunks: PX)
-    static constexpr uint32_t r16_bytes = PX ? 0u : (uint32_t)TM * C * 2;     // r as an fp16 tile (split precision stores the fp32 staging tile W)
+    // r leaves as an fp16 tile staged in the first half of Q (q's own store was issued two phases earlier and has been waited
+    // for); split precision stores the fp32 staging tile W instead.  No region of its own: 3 CTAs per SM fit at C = 32.
+    static constexpr uint32_t r16_bytes = 0u;
     static constexpr uint32_t xbytes = cc0 ? 0u : (uint32_t)TM * tc_kin(CIN) * 4;
-    static constexpr uint32_t region = 2 * uv_bytes + r16_bytes + 2 * tile_bytes + xbytes;   // U, V, R16 (fp16) | W, Q (fp32) | X
+    static constexpr uint32_t region = 2 * uv_bytes + r16_bytes + 2 * tile_bytes + xbytes;   // U, V (fp16) | W, Q (fp32) | X
+    static constexpr uint32_t xch = 2u * TM * 8u;                    // one LayerNorm exchange per tile: a single buffer
     static constexpr int col_acc = 0, col_x0 = C;
     static constexpr int ncols = tc_cols(cc0 ? C : 2 * C);
     static constexpr int min_ctas = C <= 32 ? (PX ? 2 : BALF_MERGE32_CTAS) : 1;
@@ -1546,12 +1549,12 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     constexpr int CH = Cfg::CH;
     using G = MergeG<CIN, C, PX>;
     constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;
-    const TcShared s = carve(smem, Cfg::region, plan);
+    const TcShared s = carve(smem, Cfg::region, plan, 1, Cfg::xch);
     float* const regU = s.region;                                    // fp16 tile: TM * C / 2 floats
     float* const regV = regU + Cfg::uv_bytes / 4;
-    float* const regR = regV + Cfg::uv_bytes / 4;                    // r as an fp16 tile (chunk-major) for its bulk store (not PX)
-    float* const regW = regR + Cfg::r16_bytes / 4;
+    float* const regW = regV + Cfg::uv_bytes / 4;
     float* const regQ = regW + (size_t)TM * C;
+    float* const regR = regQ;                                        // r as an fp16 tile (chunk-major) for its bulk store (not PX): over Q
     float* const regX = regQ + (size_t)TM * C;
     uint64_t* const ld_bar = s.aux;
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
@@ -1633,7 +1636,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
             row_to_sw<CH, false>(x0, regQ, row, col0);
             float sum, sq;
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
-            row_stats(sum, sq, s.xch + (xb++ & 1) * 2 * TM, row, half, C, rstd, shift);
+            row_stats(sum, sq, s.xch, row, half, C, rstd, shift);
             norm_row<CH>(v, rstd, shift);
             if constexpr (G::h16(MG_RC1)) row_to_a16<CH, LOC>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         }
@@ -1657,7 +1660,11 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         if constexpr (G::h16(MG_RC1)) row_to_a16<CH, LOC>(v, regW, row, col0); else row_to_sw<CH, true>(v, regW, row, col0);
         sync_for_mma();
         // ---- phase 3: conv2 = r (exact fp32) -> W (staging) -> global, and the per-unit channel sums (squeeze)
-        if (w0 && elect_one()) { issue_linear_t<G, MG_RC2, !G::h16(MG_RC2)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true); commit(s.done); }
+        if (w0 && elect_one()) {
+            issue_linear_t<G, MG_RC2, !G::h16(MG_RC2)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
+            commit(s.done);
+            if constexpr (!PX) bulk_wait_read();            // q's store (issued in phase 2) has read Q: its first half becomes the r tile
+        }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         ld_row<CH>(lane_base + Cfg::col_acc + col0, v);
         row_to_sw<CH, false>(v, regW, row, col0);              // exact fp32: the squeeze sums below
@@ -2137,7 +2144,7 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     if constexpr (C <= 64) {
         const TcPlan& p = P.merge[level];
         BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
-        const size_t smem = tc_smem_bytes(MergeBulkCfg<CIN, C, PX>::region, p);
+        const size_t smem = tc_smem_bytes(MergeBulkCfg<CIN, C, PX>::region, p, 1, MergeBulkCfg<CIN, C, PX>::xch);
         if (int e = tc_launch_cfg(tc_merge_bulk_kernel<CIN, C, PX>, smem, MergeBulkCfg<CIN, C, PX>::ncols, ntiles, &grid)) return e;
         ProfScope ps(C == 32 ? "det_merge_c32" : "det_merge_c64", st);
         tc_merge_bulk_kernel<CIN, C, PX><<<grid, NT2, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
