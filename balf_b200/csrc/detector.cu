@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------ pool (stages 1-3)
 // out[b, py, px, :] = max over the 2x2 window of (r * s + q)
 // swz: 0 = r, q channels-last; 1 = q in swizzled-panel tiles, r in fp16 tiles; 2 = r and q in swizzled-panel tiles (split precision)
-template <int C, int swz>
+// OH: the output is fp16 (channels-last halves) -- the next stage runs on the single-rounded tensor-core path, whose only use of
+// its level input is the fp16 A operand of conv.0: same values as rounding at load time, half the bytes written once and read 3x
+template <int C, int swz, bool OH>
 __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict__ q, const float* __restrict__ scale,
                             int h, int w, float* __restrict__ out, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,7 +415,14 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             best.x = fmaxf(best.x, rv.x * s.x + qv.x); best.y = fmaxf(best.y, rv.y * s.y + qv.y);
             best.z = fmaxf(best.z, rv.z * s.z + qv.z); best.w = fmaxf(best.w, rv.w * s.w + qv.w);
         }
-    *(reinterpret_cast<float4*>(out + ((b * ho + py) * wo + px) * C) + c4) = best;
+    if constexpr (OH) {
+        uint2 o;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(best.y), "f"(best.x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(best.w), "f"(best.z));
+        *(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + ((b * ho + py) * wo + px) * C) + c4) = o;
+    } else {
+        *(reinterpret_cast<float4*>(out + ((b * ho + py) * wo + px) * C) + c4) = best;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ head (stage 4)
@@ -622,14 +631,16 @@ static int run_se(const Workspace& ws, const DownW& w, int Bc, int npix, int par
 }
 
 template <int C>
-static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st, int swz = 0) {
+static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cudaStream_t st, int swz = 0, bool oh = false) {
     size_t total = (size_t)Bc * (h / 2) * (wd / 2) * (C / 4);
     {
         ProfScope p("det_pool", st);
         const unsigned grid = (unsigned)((total + 255) / 256);
-        if (swz == 1) pool_kernel<C, 1><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
-        else if (swz == 2) pool_kernel<C, 2><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
-        else pool_kernel<C, 0><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        if (swz == 1 && oh) pool_kernel<C, 1, true><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (swz == 1) pool_kernel<C, 1, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (swz == 2) pool_kernel<C, 2, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (oh) pool_kernel<C, 0, true><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else pool_kernel<C, 0, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
@@ -752,17 +763,17 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
             if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<32>(ws, d[0], Bc, Hp * Wp, Hp * Wp / 64, st)) return e;
         } else if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
-        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) ? 1 + px : 0)) return e;
+        if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) ? 1 + px : 0, (tcm & 2) && !px)) return e;
         if (tcm & 2) {
             if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;
         } else if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
-        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) ? 1 + px : 0)) return e;
+        if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) ? 1 + px : 0, (tcm & 4) && !px)) return e;
         if (tcm & 4) {
             if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<128>(ws, d[2], Bc, Hp * Wp / 16, Hp * Wp / 1024, st)) return e;
         } else if (int e = run_level<64, 128, 64, 64>(ws.pooled[1], false, w.down[2], Bc, Hp / 4, Wp / 4, ws, st, &tiles)) return e;
-        if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st)) return e;
+        if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st, 0, (tcm & 8) && !px)) return e;
         if (tcm & 8) {
             if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
             if (int e = run_se<256>(ws, d[3], Bc, hc * wc, hc * wc / 64, st)) return e;

@@ -792,6 +792,16 @@ __device__ __forceinline__ void load_input_row(const float* __restrict__ xin, si
             o = to_tf32(make_float4(v[0], v[1], v[2], v[3]));
         }
         if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = o;
+    } else if constexpr (H16 == 3) {
+        // the level input is already fp16, channels-last [pixel][CIN halves] (written by pool_kernel for this path): its 16-byte
+        // chunks ARE operand chunks -- half the bytes of the fp32 tensor, no conversion (every consumer rounded it to fp16 anyway)
+        constexpr int N16 = CIN / (8 * TPR);
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(xin) + (img * npix + pix) * CIN) + half * N16;
+        uint4 v[N16];
+#pragma unroll
+        for (int j = 0; j < N16; ++j) v[j] = valid ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < N16; ++j) *reinterpret_cast<uint4*>(dst + ((size_t)(half * N16 + j) * TM + row) * 4) = v[j];
     } else {
         constexpr int N = CIN / (4 * TPR), NB = N > 8 ? 8 : N;          // batches of 8 chunks bound the registers in flight
         const float4* src = reinterpret_cast<const float4*>(xin + (img * npix + pix) * CIN) + half * N;
@@ -836,9 +846,19 @@ template <int CIN, int TPR = 2> struct InputPf {
     static constexpr bool enabled = CIN <= 64;
     float4 v[N];
 };
-template <int CIN, bool PAIR = true, int TPR = 2>
+template <int CIN, bool PAIR = true, int TPR = 2, bool XH = false>      // XH: fp16 level input (see load_input_row, mode 3)
 __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, size_t npix, size_t img, int pix, bool valid, int half,
                                                 InputPf<CIN, TPR>& pf) {
+    if constexpr (XH && CIN >= 8) {
+        constexpr int N16 = CIN / (8 * TPR);
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(xin) + (img * npix + pix) * CIN) + half * N16;
+#pragma unroll
+        for (int j = 0; j < N16; ++j) {
+            const uint4 u = valid ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
+            pf.v[j] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+        }
+        return;
+    }
     if constexpr (CIN < 8) {                       // conv.0 runs on the CUDA cores: every part of the row needs the pixel
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid) {
@@ -859,6 +879,12 @@ __device__ __forceinline__ void fetch_input_row(const float* __restrict__ xin, s
 }
 template <int CIN, bool PAIR = true, int TPR = 2, int H16 = 0>
 __device__ __forceinline__ void store_input_row(const InputPf<CIN, TPR>& pf, float* dst, int row, int half) {
+    if constexpr (H16 == 3 && CIN >= 8) {
+        constexpr int N16 = CIN / (8 * TPR);
+#pragma unroll
+        for (int j = 0; j < N16; ++j) *reinterpret_cast<float4*>(dst + ((size_t)(half * N16 + j) * TM + row) * 4) = pf.v[j];
+        return;
+    }
     if constexpr (CIN < 8) {
         if (half < 2) *reinterpret_cast<float4*>(dst + ((size_t)half * TM + row) * 4) = to_tf32(pf.v[0]);
     } else {
@@ -954,6 +980,8 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     constexpr int CH = Cfg::CH, NG = Cfg::groups, TPR = Cfg::TPR, NTG = Cfg::NTG, SC = Cfg::SC;
     constexpr bool X3 = Cfg::PX != 0;
     constexpr int LOC = X3 ? C / 8 : 0;                                   // lo chunks of an A operand follow its C / 8 hi chunks
+    constexpr bool XH = !X3 && CIN >= 8;                                  // the level input arrives as fp16 (pool_kernel, single-rounded path)
+    constexpr int XM = XH ? 3 : X3 ? 2 : 1;
     static_assert(NG == 1 || G::resident, "tile groups share resident weights (no ring state per group)");
     static_assert(CH % SC == 0 && SC % 16 == 0, "sub-chunking");
     TcShared s = carve(smem, Cfg::region, plan, NG, Cfg::xch);
@@ -1011,7 +1039,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     if (InputPf<CIN, TPR>::enabled && vblock < ntiles) {
         bool vld; int im, px;
         coords(vblock, vld, im, px);
-        fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
+        fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
     }
     for (int t = vblock; t < ntiles; t += vgrid, ++it) {
         TC_TRACE(plan, it, 0);
@@ -1025,19 +1053,19 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             if (t + vgrid < ntiles) {
                 bool vld; int im, px;
                 coords(t + vgrid, vld, im, px);
-                fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
+                fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
             }
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
             if (InputPf<CIN, TPR>::enabled) {
-                store_input_row<CIN, true, TPR, X3 ? 2 : 1>(pf, s.region, row, half);
+                store_input_row<CIN, true, TPR, XM>(pf, s.region, row, half);
                 if (t + vgrid < ntiles) {
                     bool vld; int im, px;
                     coords(t + vgrid, vld, im, px);
-                    fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
+                    fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
                 }
             } else {
-                load_input_row<CIN, TPR, X3 ? 2 : 1>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
+                load_input_row<CIN, TPR, XM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
             }
             TC_TRACE(plan, it, 1);
             sync_for_mma<NG, NTG>(grp);
@@ -1309,6 +1337,8 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     using G = MergeG<CIN, C, PX>;
     constexpr int CH = Cfg::CH, TPR = Cfg::TPR, NTK = Cfg::NT;
     constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;      // operand mode of the loaders, lo-chunk offset of a K = C operand
+    constexpr bool XH = PX == 0 && CIN >= 8;                  // fp16 level input (pool_kernel, single-rounded path)
+    constexpr int XM = XH ? 3 : HM;
     (void)w;
     const TcShared s = carve(smem, Cfg::region, plan, 1, Cfg::xch);
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7;
@@ -1349,7 +1379,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
     if (InputPf<CIN, TPR>::enabled && (int)blockIdx.x < ntiles) {
         bool vld; int im, px;
         coords(blockIdx.x, vld, im, px);
-        fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
+        fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
     }
     if (Cfg::bulk_uv && (int)blockIdx.x < ntiles && w0 && elect_one()) {
         mbar_expect_tx(ld_u, kTileBytes);
@@ -1363,14 +1393,14 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         float v[CH];
         // ---- x0 = ReLU(conv.0(x)), parked
         if (InputPf<CIN, TPR>::enabled) {
-            store_input_row<CIN, true, TPR, HM>(pf, s.region, row, half);
+            store_input_row<CIN, true, TPR, XM>(pf, s.region, row, half);
             if (t + (int)gridDim.x < ntiles) {
                 bool vld; int im, px;
                 coords(t + gridDim.x, vld, im, px);
-                fetch_input_row<CIN, true, TPR>(xin, npix, (size_t)im, px, vld, half, pf);
+                fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
             }
         } else {
-            load_input_row<CIN, TPR, HM>(xin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : CIN);
+            load_input_row<CIN, TPR, XM>(xin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : CIN);
         }
         if (InputPf<C>::enabled) fetch_input_row<C>(uin, npix, (size_t)img, pix, valid, half, pfu);
         TC_TRACE(plan, it, 1);
@@ -1549,6 +1579,8 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     constexpr int CH = Cfg::CH;
     using G = MergeG<CIN, C, PX>;
     constexpr int HM = PX ? 2 : 1, LOC = PX ? C / 8 : 0;
+    constexpr bool XH = PX == 0 && CIN >= 8;                  // fp16 level input (pool_kernel, single-rounded path)
+    constexpr int XM = XH ? 3 : HM;
     const TcShared s = carve(smem, Cfg::region, plan, 1, Cfg::xch);
     float* const regU = s.region;                                    // fp16 tile: TM * C / 2 floats
     float* const regV = regU + Cfg::uv_bytes / 4;
@@ -1586,7 +1618,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     if ((int)blockIdx.x < ntiles) {
         int im, px;
         coords(blockIdx.x, im, px);
-        fetch_input_row<CIN, false>(xin, npix, (size_t)im, px, true, half, pfx);
+        fetch_input_row<CIN, false, 2, XH>(xin, npix, (size_t)im, px, true, half, pfx);
         if (w0 && elect_one()) load_tile(blockIdx.x);
     }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -1594,7 +1626,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         float v[CH], x0[CH];
         // ---- phase 1: acc = dense2([u', v']) (+ conv.0(x) at CIN >= 8) on the tensor core | x0 on the CUDA cores at CIN < 8
         if constexpr (!Cfg::cc0) {
-            store_input_row<CIN, false, 2, HM>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
+            store_input_row<CIN, false, 2, XM>(pfx, regX, row, half);     // X was released by the previous tile's phase 1
             sync_for_mma();
         }
         if (w0 && elect_one()) {
@@ -1611,7 +1643,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         if (nt < ntiles) {
             int im, px;
             coords(nt, im, px);
-            fetch_input_row<CIN, false>(xin, npix, (size_t)im, px, true, half, pfx);
+            fetch_input_row<CIN, false, 2, XH>(xin, npix, (size_t)im, px, true, half, pfx);
         }
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         // x1 = acc + x0; q = x1 + x0 -> Q (staging); LayerNorm(x1) (affine folded into conv1) -> W
