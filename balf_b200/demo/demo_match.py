@@ -175,11 +175,49 @@ def extract_features(args, im_rgb, im_gray, detector, descriptor, device):
     return kpts_np[:, 0:2], descs.cpu().numpy()
 
 
+def _features_batch_device(args, rgbs, grays, detector, descriptor, dev):
+    """Same-shape uint8 images -> per image (xy int32 [n,2], dxdy fp32 [n,2] | None, descriptors fp32 [n,128]), all on the device:
+    ONE batched detector + greedy NMS call, per-image patch sampling, ONE HardNet call over all patches.  Per-image results are
+    identical to ``extract_features`` one image at a time (no stage mixes images)."""
+    u8 = torch.from_numpy(np.ascontiguousarray(np.stack(rgbs))).to(dev, non_blocking=True)
+    xy, _, dxdy, cnt = detect_batch_device(args, u8, detector, "greedy")
+    counts = cnt.cpu().tolist()
+    patches = []
+    for b, n in enumerate(counts):
+        kp = xy[b, :n].float()
+        if dxdy is not None:
+            kp = kp + dxdy[b, :n]
+        gray = torch.from_numpy(np.ascontiguousarray(grays[b])).to(dev, non_blocking=True)
+        patches.append(_capi.extract_patches(gray, kp, float(args.s_mult), 32))
+    with torch.inference_mode():
+        descs = descriptor(torch.cat(patches)) if sum(counts) else torch.zeros(0, 128, device=dev)
+    out, o = [], 0
+    for b, n in enumerate(counts):
+        out.append((xy[b, :n], dxdy[b, :n] if dxdy is not None else None, descs[o:o + n]))
+        o += n
+    return out
+
+
 def extract_matches(args, im_rgb1, im_gray1, im_rgb2, im_gray2, detector, descriptor, device):
     """-> (points1 [M,2], points2 [M,2]) of the SMNN(0.99) matches, ordered by the first index."""
+    dev = torch.device(device)
+    if (im_rgb1.dtype == np.uint8 and im_rgb2.dtype == np.uint8 and im_rgb1.shape == im_rgb2.shape
+            and args.order_coord == 'xysr'):
+        # device-resident pair: both images through one batched detector / HardNet call, keypoints and descriptors never
+        # leave the GPU; only the matched points come back
+        (xy1, dx1, d1), (xy2, dx2, d2) = _features_batch_device(args, (im_rgb1, im_rgb2), (im_gray1, im_gray2),
+                                                                 detector, descriptor, dev)
+        if d1.shape[0] >= 2 and d2.shape[0] >= 2:
+            ids = _capi.match_smnn(d1, d2, 0.99)[1].long()
+            pts = []
+            for xy, dx, col in ((xy1, dx1, 0), (xy2, dx2, 1)):
+                p = xy[ids[:, col]].cpu().numpy().astype(np.float64)
+                if dx is not None:
+                    p = p + dx[ids[:, col]].cpu().numpy().astype(np.float64)
+                pts.append(p)
+            return pts[0], pts[1]
     kpts1, desc1 = extract_features(args, im_rgb1, im_gray1, detector, descriptor, device)
     kpts2, desc2 = extract_features(args, im_rgb2, im_gray2, detector, descriptor, device)
-    dev = torch.device(device)
     ids = _capi.match_smnn(torch.from_numpy(desc1).to(dev), torch.from_numpy(desc2).to(dev), 0.99)[1]
     ids = ids.cpu().numpy()
     return kpts1[ids[:, 0], :2], kpts2[ids[:, 1], :2]
