@@ -20,6 +20,10 @@ u8 = torch.randint(0, 256, (3, 120, 186, 1), dtype=torch.uint8, device=dev)
 for nms in ("windowed", "greedy"):
     xy, sc, _, cnt = demo_match.detect_batch_device(args, u8, det, nms)
     print(nms, cnt.tolist())
+det.precision = "f16x3"           # the same kernels in split precision (fp16 hi + lo operand pairs)
+xy, sc, _, cnt = demo_match.detect_batch_device(args, u8, det, "greedy")
+print("greedy f16x3", cnt.tolist())
+det.precision = "tf32"
 xy, sc, lv, cnt = demo_match.detect_multiscale_batch_device(args, u8, det, scale=0.7, levels=2)
 print("multiscale", cnt.tolist())
 d1 = torch.nn.functional.normalize(torch.randn(300, 128, device=dev), dim=1)
