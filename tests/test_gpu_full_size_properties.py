@@ -147,6 +147,10 @@ def test_config3_pair_properties(detector):
     p1, p2 = demo_match.extract_matches(args, rgb1, g1, rgb2, g2, det, hn, DEV)
     assert p1.shape == p2.shape == (len(ids), 2)
     assert np.median(np.abs(p1 - p2).max(1)) < 1.0                              # matched keypoints coincide (same scene)
+    # extract_matches runs the pair device-resident (one batched detector / HardNet call); it must return exactly what the
+    # one-image-at-a-time composition above gives
+    np.testing.assert_array_equal(p1, k1[ids[:, 0]])
+    np.testing.assert_array_equal(p2, k2[ids[:, 1]])
 
 
 def test_config3_pair_vs_reference_and_oracle(detector):
