@@ -1036,33 +1036,33 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
         upk2(s2, a, b); sum = a + b;
         upk2(q2, a, b); sq = a + b;
     };
+    // (the coordinates of the prefetched tile are carried into its iteration: the unit -> pixel arithmetic ran twice per tile)
+    bool nvld = false; int nim = 0, npx = 0;
     if (InputPf<CIN, TPR>::enabled && vblock < ntiles) {
-        bool vld; int im, px;
-        coords(vblock, vld, im, px);
-        fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
+        coords(vblock, nvld, nim, npx);
+        fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)nim, npx, nvld, half, pf);
     }
     for (int t = vblock; t < ntiles; t += vgrid, ++it) {
         TC_TRACE(plan, it, 0);
         bool valid; int img, pix;
-        coords(t, valid, img, pix);
+        if (InputPf<CIN, TPR>::enabled && TPR > 1) { valid = nvld; img = nim; pix = npx; }      // (one thread per row: no registers to spare)
+        else coords(t, valid, img, pix);
         float* orow = out + ((size_t)img * npix + pix) * C + col0;
         float v[CH], rstd, shift;
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
         if constexpr (CIN < 8) {
             const float4 xv = pf.v[0];
             if (t + vgrid < ntiles) {
-                bool vld; int im, px;
-                coords(t + vgrid, vld, im, px);
-                fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
+                coords(t + vgrid, nvld, nim, npx);
+                fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)nim, npx, nvld, half, pf);
             }
             conv0_row<CIN, C, CH>(xv, s.vec, col0, v);
         } else {
             if (InputPf<CIN, TPR>::enabled) {
                 store_input_row<CIN, true, TPR, XM>(pf, s.region, row, half);
                 if (t + vgrid < ntiles) {
-                    bool vld; int im, px;
-                    coords(t + vgrid, vld, im, px);
-                    fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)im, px, vld, half, pf);
+                    coords(t + vgrid, nvld, nim, npx);
+                    fetch_input_row<CIN, true, TPR, XH>(xin, npix, (size_t)nim, npx, nvld, half, pf);
                 }
             } else {
                 load_input_row<CIN, TPR, XM>(xin, npix, (size_t)img, pix, valid, s.region, row, half);
@@ -1197,7 +1197,8 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float lo = a[8 * j + 2 * e] + r[8 * j + 2 * e], hi = a[8 * j + 2 * e + 1] + r[8 * j + 2 * e + 1];
+                            float lo, hi;
+                            upk2(add2(pk2(a[8 * j + 2 * e], a[8 * j + 2 * e + 1]), pk2(r[8 * j + 2 * e], r[8 * j + 2 * e + 1])), lo, hi);
                             if constexpr (X3) split_h2(lo, hi, h[e], l[e]);
                             else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(hi), "f"(lo));
                         }
