@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(kSeThreads) se_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------ pool (stages 1-3)
 // out[b, py, px, :] = max over the 2x2 window of (r * s + q)
-// swz: 0 = r, q channels-last; 1 = q in swizzled-panel tiles, r in fp16 tiles; 2 = r and q in swizzled-panel tiles (split precision)
+// swz: 0 = r, q channels-last; 1 = q in swizzled-panel tiles, r in fp16 tiles; 2 = r and q in swizzled-panel tiles (split precision);
+//      3 = q channels-last, r channels-last fp16 (stage 3 of the single-rounded tensor path)
 // OH: the output is fp16 (channels-last halves) -- the next stage runs on the single-rounded tensor-core path, whose only use of
 // its level input is the fp16 A operand of conv.0: same values as rounding at load time, half the bytes written once and read 3x
 template <int C, int swz, bool OH>
@@ -399,13 +400,17 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             // swz: r / q of the tensor-core merge kernels of the first two stages are tiles of 128 pixels in the swizzled
             // panel layout (detector_tc.cu sw_off): panels of 32 channels, 128-byte rows, chunks permuted by (pixel % 8)
             const size_t rowi = p & 127;
-            const size_t cs = swz ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
+            const size_t cs = (swz == 1 || swz == 2) ? (((p - rowi) * C) >> 2) + (size_t)(c4 >> 3) * (128 * 8) + rowi * 8 + ((c4 & 7) ^ (rowi & 7))
                                   : ((p * C) >> 2) + c4;
             float4 rv;
             if constexpr (swz == 1) {
                 // r of those stages is an fp16 tile [C / 8 chunks][128 pixels][8 halves] (tc_merge_bulk_kernel)
                 const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r) + (p - rowi) * C +
                                                                      (size_t)(c4 >> 1) * (128 * 8) + rowi * 8 + (c4 & 1) * 4));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                rv = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else if constexpr (swz == 3) {
+                const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r) + p * C) + c4);
                 const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
                 rv = make_float4(lo.x, lo.y, hi.x, hi.y);
             } else {
@@ -639,6 +644,8 @@ static int run_pool(const Workspace& ws, int Bc, int h, int wd, float* out, cuda
         if (swz == 1 && oh) pool_kernel<C, 1, true><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
         else if (swz == 1) pool_kernel<C, 1, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
         else if (swz == 2) pool_kernel<C, 2, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (swz == 3 && oh) pool_kernel<C, 3, true><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
+        else if (swz == 3) pool_kernel<C, 3, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
         else if (oh) pool_kernel<C, 0, true><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
         else pool_kernel<C, 0, false><<<grid, 256, 0, st>>>(ws.r, ws.q, ws.scale, h, wd, out, total);
     }
@@ -760,27 +767,27 @@ extern "C" int balf_detector_forward(const balf_detector_arch* arch, const float
         const DownW* d = w.down;
         int tiles = 0;
         if (tcm & 1) {
-            if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
+            if (int e = tc_run_level_dispatch(0, xb, true, d[0], a, tc_blob, Bc, Hp, Wp, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px, 0)) return e;
             if (int e = run_se<32>(ws, d[0], Bc, Hp * Wp, Hp * Wp / 64, st)) return e;
         } else if (int e = run_level<3, 32, 128, 128>(xb, true, w.down[0], Bc, Hp, Wp, ws, st, &tiles)) return e;
         if (int e = run_pool<32>(ws, Bc, Hp, Wp, ws.pooled[0], st, (tcm & 1) ? 1 + px : 0, (tcm & 2) && !px)) return e;
         if (tcm & 2) {
-            if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
+            if (int e = tc_run_level_dispatch(1, ws.pooled[0], false, d[1], a, tc_blob, Bc, Hp / 2, Wp / 2, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px, 0)) return e;
             if (int e = run_se<64>(ws, d[1], Bc, Hp * Wp / 4, Hp * Wp / 256, st)) return e;
         } else if (int e = run_level<32, 64, 128, 128>(ws.pooled[0], false, w.down[1], Bc, Hp / 2, Wp / 2, ws, st, &tiles)) return e;
         if (int e = run_pool<64>(ws, Bc, Hp / 2, Wp / 2, ws.pooled[1], st, (tcm & 2) ? 1 + px : 0, (tcm & 4) && !px)) return e;
         if (tcm & 4) {
-            if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
+            if (int e = tc_run_level_dispatch(2, ws.pooled[1], false, d[2], a, tc_blob, Bc, Hp / 4, Wp / 4, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px, px == 0)) return e;
             if (int e = run_se<128>(ws, d[2], Bc, Hp * Wp / 16, Hp * Wp / 1024, st)) return e;
         } else if (int e = run_level<64, 128, 64, 64>(ws.pooled[1], false, w.down[2], Bc, Hp / 4, Wp / 4, ws, st, &tiles)) return e;
-        if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st, 0, (tcm & 8) && !px)) return e;
+        if (int e = run_pool<128>(ws, Bc, Hp / 4, Wp / 4, ws.pooled[2], st, ((tcm & 4) && !px) ? 3 : 0, (tcm & 8) && !px)) return e;
         if (tcm & 8) {
-            if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px)) return e;
+            if (int e = tc_run_level_dispatch(3, ws.pooled[2], false, d[3], a, tc_blob, Bc, hc, wc, ws.u, ws.v, ws.r, ws.q, ws.partial, st, px, px == 0 && (tcm & 16) != 0)) return e;
             if (int e = run_se<256>(ws, d[3], Bc, hc * wc, hc * wc / 64, st)) return e;
         } else if (int e = run_level<128, 256, 64, 32>(ws.pooled[2], false, w.down[3], Bc, hc, wc, ws, st, &tiles)) return e;
         if (tcm & 16) {
             if (int e = tc_run_head(ws.r, ws.q, ws.scale, d[3], w.head, a, tc_blob, Bc, hc, wc,
-                                    logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp, st, px)) return e;
+                                    logits ? logits + (size_t)b0 * nl * hc * wc : nullptr, prob + (size_t)b0 * Hp * Wp, st, px, px == 0 && (tcm & 8) != 0)) return e;
             continue;
         }
         dim3 gh(hc * wc / 32, Bc);

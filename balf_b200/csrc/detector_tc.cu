@@ -1332,7 +1332,7 @@ template <int C, int PX = 0> struct MergeCfg {
 template <int CIN, int C, int PX = 0>
 __global__ void __launch_bounds__(MergeCfg<C, PX>::NT, MergeCfg<C, PX>::min_ctas)
 tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, const float* __restrict__ uin,
-                const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial) {
+                const float* __restrict__ vin, float* __restrict__ rout, float* __restrict__ qout, float* __restrict__ partial, int r16) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = MergeCfg<C, PX>;
     using G = MergeG<CIN, C, PX>;
@@ -1529,7 +1529,27 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             *reinterpret_cast<float4*>(s.region + ((size_t)(col0 / 4 + j) * TM + row) * 4) = o;
         }
-        if constexpr (CH % 32 == 0 && PX == 0) oct_store<CH / 4>(rout, row_off, C, v, valid); else pair_store<CH / 4>(rout, row_off, v, valid);
+        static_assert(PX != 0 || C < 128 || CH % 64 == 0, "the fp16 r store (r16, decided by the host) assumes two threads per row");
+        if constexpr (CH % 64 == 0 && PX == 0) {
+            if (r16) {
+                // r leaves as fp16 (channels-last halves): it only enters r * s + q, which its consumer (pool_kernel / the head
+                // kernel) rounds to fp16 next -- as at stages 1-2; half the bytes and half the chunk transposes of the store
+                float hv[CH / 2];
+#pragma unroll
+                for (int i = 0; i < CH / 2; ++i) {
+                    uint32_t h;
+                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                    hv[i] = __uint_as_float(h);
+                }
+                oct_store<CH / 8>(rout, row_off / 2, C / 2, hv, valid);
+            } else {
+                oct_store<CH / 4>(rout, row_off, C, v, valid);
+            }
+        } else if constexpr (CH % 32 == 0 && PX == 0) {
+            oct_store<CH / 4>(rout, row_off, C, v, valid);
+        } else {
+            pair_store<CH / 4>(rout, row_off, v, valid);
+        }
         __syncthreads();
         unit_channel_sums<C, NTK>(s.region, t, geo.total_units, partial);
         if constexpr (Cfg::two) fence_async_smem();                   // generic reads of the staging tile before the async write below
@@ -1754,7 +1774,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
 template <int C, int PX = 0>
 __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict__ r, const float* __restrict__ q,
                                                          const float* __restrict__ scale, TcPlan plan, UnitGeom geo, int cell,
-                                                         float* __restrict__ logits, float* __restrict__ prob) {
+                                                         float* __restrict__ logits, float* __restrict__ prob, int r16) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using G = HeadG<C, PX>;
     constexpr int LOC = PX ? C / 8 : 0;
@@ -1786,7 +1806,19 @@ __global__ void __launch_bounds__(NT2, 1) tc_head_kernel(const float* __restrict
         for (int j0 = 0; j0 < CH / 4; j0 += 8) {            // full-sector pair loads of r and q, 8 chunks at a time
             float4 rv[8], qv[8];
             if constexpr (PX == 0) {              // full-line loads (see oct_load)
-                oct_load<8>(r, row_off + (size_t)j0 * 4, C, valid, rv);
+                if (r16) {                         // r as fp16 channels-last (tc_merge_kernel): 4 chunks of 8 halves
+                    const uint4* rh = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(r) + row_off) + j0 / 2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 h = valid ? __ldg(rh + k) : make_uint4(0u, 0u, 0u, 0u);
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                        const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+                        rv[2 * k] = make_float4(a.x, a.y, b.x, b.y);
+                        rv[2 * k + 1] = make_float4(c2.x, c2.y, d.x, d.y);
+                    }
+                } else {
+                    oct_load<8>(r, row_off + (size_t)j0 * 4, C, valid, rv);
+                }
                 oct_load<8>(q, row_off + (size_t)j0 * 4, C, valid, qv);
             } else {
                 pair_load<8>(reinterpret_cast<const float4*>(r + row_off) + j0, valid, rv);
@@ -2166,7 +2198,8 @@ static int tc_run_branches(const float* xin, const DownW& w, const TcPlans& P, i
 
 template <int CIN, int C, int PX>
 static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int level, int Bc, int h, int wd,
-                        float* u, float* v, float* r, float* q, float* partial, cudaStream_t st) {
+                        float* u, float* v, float* r, float* q, float* partial, cudaStream_t st, int r16) {
+    (void)r16;
     UnitGeom g{h, wd, h / 8, wd / 8, h * wd / 64, Bc * (h * wd / 64), 1.0f / (float)(h * wd / 64), 1.0f / (float)(wd / 8), 1.0f / (float)(wd / 8)};
     BALF_REQUIRE(g.total_units < (1 << 23), "internal: %d units in one pass exceed the fast_div range", g.total_units);
     const int ntiles = (g.total_units + 1) / 2;
@@ -2187,7 +2220,7 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
         const size_t smem = tc_smem_bytes(MergeCfg<C, PX>::region, p, 1, MergeCfg<C, PX>::xch);
         if (int e = tc_launch_cfg(tc_merge_kernel<CIN, C, PX>, smem, MergeCfg<C, PX>::ncols, ntiles, &grid, 1, MergeCfg<C, PX>::NT)) return e;
         ProfScope ps(C == 128 ? "det_merge_c128" : "det_merge_c256", st);
-        tc_merge_kernel<CIN, C, PX><<<grid, MergeCfg<C, PX>::NT, smem, st>>>(xin, w, p, g, u, v, r, q, partial);
+        tc_merge_kernel<CIN, C, PX><<<grid, MergeCfg<C, PX>::NT, smem, st>>>(xin, w, p, g, u, v, r, q, partial, r16);
     }
     BALF_COUNT_LAUNCH(3);
     BALF_LAUNCH_OK();
@@ -2195,28 +2228,28 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
 }
 
 int tc_run_level_dispatch(int level, const float* xin, bool nchw, const DownW& w, const balf_detector_arch& a, const float* blob,
-                          int Bc, int h, int wd, float* u, float* v, float* r, float* q, float* partial, cudaStream_t st, int px) {
+                          int Bc, int h, int wd, float* u, float* v, float* r, float* q, float* partial, cudaStream_t st, int px, int r16) {
     (void)nchw;
     TcPlans P;
     tc_build_plans(a, blob, &P, px);
     if (px) {
         switch (level) {
-            case 0: return tc_run_level<3, 32, 1>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
-            case 1: return tc_run_level<32, 64, 1>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
-            case 2: return tc_run_level<64, 128, 1>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
-            default: return tc_run_level<128, 256, 1>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
+            case 0: return tc_run_level<3, 32, 1>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st, r16);
+            case 1: return tc_run_level<32, 64, 1>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st, r16);
+            case 2: return tc_run_level<64, 128, 1>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st, r16);
+            default: return tc_run_level<128, 256, 1>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st, r16);
         }
     }
     switch (level) {
-        case 0: return tc_run_level<3, 32, 0>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st);
-        case 1: return tc_run_level<32, 64, 0>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st);
-        case 2: return tc_run_level<64, 128, 0>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st);
-        default: return tc_run_level<128, 256, 0>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st);
+        case 0: return tc_run_level<3, 32, 0>(xin, w, P, 0, Bc, h, wd, u, v, r, q, partial, st, r16);
+        case 1: return tc_run_level<32, 64, 0>(xin, w, P, 1, Bc, h, wd, u, v, r, q, partial, st, r16);
+        case 2: return tc_run_level<64, 128, 0>(xin, w, P, 2, Bc, h, wd, u, v, r, q, partial, st, r16);
+        default: return tc_run_level<128, 256, 0>(xin, w, P, 3, Bc, h, wd, u, v, r, q, partial, st, r16);
     }
 }
 
 int tc_run_head(const float* r, const float* q, const float* scale, const DownW& w, const HeadW& hw, const balf_detector_arch& a,
-                const float* blob, int Bc, int hc, int wc, float* logits, float* prob, cudaStream_t st, int px) {
+                const float* blob, int Bc, int hc, int wc, float* logits, float* prob, cudaStream_t st, int px, int r16) {
     (void)w; (void)hw;
     TcPlans P;
     tc_build_plans(a, blob, &P, px);
@@ -2229,12 +2262,12 @@ int tc_run_head(const float* r, const float* q, const float* scale, const DownW&
         BALF_REQUIRE((plan_matches<HeadG<256, 1>>(P.head)), "internal: compile-time and packed GEMM plans differ (head, split precision)");
         if (int e = tc_launch_cfg(tc_head_kernel<256, 1>, smem, 512, ntiles, &grid)) return e;
         ProfScope ps("det_head", st);
-        tc_head_kernel<256, 1><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob);
+        tc_head_kernel<256, 1><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob, 0);
     } else {
         BALF_REQUIRE(plan_matches<HeadG<256>>(P.head), "internal: compile-time and packed GEMM plans differ (head)");
         if (int e = tc_launch_cfg(tc_head_kernel<256>, smem, 512, ntiles, &grid)) return e;
         ProfScope ps("det_head", st);
-        tc_head_kernel<256><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob);
+        tc_head_kernel<256><<<grid, NT2, smem, st>>>(r, q, scale, P.head, g, a.cell, logits, prob, r16);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
