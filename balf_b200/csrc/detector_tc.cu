@@ -545,7 +545,7 @@ struct TcShared {
 };
 constexpr int kMaxGroups = 8;
 constexpr uint32_t kSchedEntries = 62;
-constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = 2 * 256 * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 256;
+constexpr uint32_t kOnesBytes = 2 * TM * 16, kXchBytes = 2 * 2 * TM * 8, kVecBytes = (2 * 256 + 64) * 4, kSchedBytes = (kSchedEntries + 2) * 8, kTcTail = 256;
 __host__ __device__ inline uint32_t tc_weight_bytes(const TcPlan& p) {
     return p.resident ? (p.bytes + 127u) / 128u * 128u : p.nslot * p.slot_bytes;
 }
@@ -993,6 +993,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     const DownW::Branch& br = w.br[BR];
     if (grp == 0) {
         for (int i = tid; i < C; i += NTG) { s.vec[i] = __ldg(br.gn_w + i); s.vec[256 + i] = __ldg(br.gn_b + i); }
+        for (int i = tid; i < 64; i += NTG) s.vec[512 + i] = __ldg(br.gd_b + i) + 1.0f;
         if constexpr (CIN < 8) {
             for (int i = tid; i < CIN * C; i += NTG) s.vec[kConv0Off + i] = __ldg(w.conv0_w + i);
             for (int i = tid; i < C; i += NTG) s.vec[kConv0Off + CIN * C + i] = __ldg(w.conv0_b + i);
@@ -1012,7 +1013,9 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     const uint32_t region_addr = smem_u32(s.region), ones_addr = smem_u32(s.ones);
     const int ug = (row & 31) >> 4, tok = (row >> 5) * 16 + (row & 15);   // unit / token of this lane
     const int col0 = half * CH;                                           // this thread's channel range
-    const float mix_b1 = __ldg(br.gd_b + tok) + 1.0f;
+    // mixing bias + 1 of this lane's token, from shared memory (vec[512 + tok]): as a register the compiler re-loaded it from
+    // global memory in every tile (7 % of the stage-2 kernel's stall samples on that one load)
+    const float* const mix_b1p = s.vec + 512 + tok;
     // float distance between the rows of 8 consecutive lanes (8 consecutive tokens: a block row, or 8 grid cells fw pixels apart)
     const int ostride = (BR == 0 ? geo.fw : 1) * C;
     const size_t npix = (size_t)geo.h * geo.w;
@@ -1154,6 +1157,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
                 float y1[SC], y2[SC];
                 ld_row<SC>(lane_base + Cfg::col_y + col0 + c, y1);
                 ld_row<SC>(lane_base + Cfg::col_y + C + col0 + c, y2);
+                const float mix_b1 = *mix_b1p;
                 const unsigned long long b2 = pk2(mix_b1, mix_b1);
 #pragma unroll
                 for (int i = 0; i < SC; i += 2) upk2(mul2(pk2(y1[i], y1[i + 1]), add2(pk2(y2[i], y2[i + 1]), b2)), y2[i], y2[i + 1]);
