@@ -975,12 +975,16 @@ template <int C, int PX = 0> struct BranchCfg : BranchCfgT<C, 2, (C <= 32 ? 4 : 
 
 template <int CIN, int C, int BR, typename Cfg>
 __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, const DownW& w, const TcPlan& plan, const UnitGeom& geo,
-                                               float* __restrict__ out, unsigned char* smem) {
+                                               float* __restrict__ out, float* __restrict__ scratch, unsigned char* smem) {
     using G = BranchG<CIN, C, Cfg::PX>;
     constexpr int CH = Cfg::CH, NG = Cfg::groups, TPR = Cfg::TPR, NTG = Cfg::NTG, SC = Cfg::SC;
     constexpr bool X3 = Cfg::PX != 0;
     constexpr int LOC = X3 ? C / 8 : 0;                                   // lo chunks of an A operand follow its C / 8 hi chunks
     constexpr bool XH = !X3 && CIN >= 8;                                  // the level input arrives as fp16 (pool_kernel, single-rounded path)
+    // stage 4, single-rounded path: u' / v' leave as fp16 channels-last rows (the merge kernel's loaders take their 16-byte chunks as
+    // operand chunks, like the pooled level inputs); the fp32 residual u then round-trips through `scratch`, not through `out`
+    constexpr bool CL16 = !Cfg::h16_out && !Cfg::swz_out && !X3;
+    float* const rt = CL16 ? scratch : out;
     constexpr int XM = XH ? 3 : X3 ? 2 : 1;
     static_assert(NG == 1 || G::resident, "tile groups share resident weights (no ring state per group)");
     static_assert(CH % SC == 0 && SC % 16 == 0, "sub-chunking");
@@ -1050,7 +1054,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
         bool valid; int img, pix;
         if (InputPf<CIN, TPR>::enabled && TPR > 1) { valid = nvld; img = nim; pix = npx; }      // (one thread per row: no registers to spare)
         else coords(t, valid, img, pix);
-        float* orow = out + ((size_t)img * npix + pix) * C + col0;
+        float* orow = rt + ((size_t)img * npix + pix) * C + col0;
         float v[CH], rstd, shift;
         // ---- x -> conv.0 -> ReLU -> LayerNorm (affine folded into dense1)
         if constexpr (CIN < 8) {
@@ -1099,8 +1103,8 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
             if (Cfg::park_u) st_row<CH>(lane_base + Cfg::col_u + col0, v);
-            else if constexpr (CH % 32 == 0 && !X3) oct_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, ostride, v, valid);
-            else pair_store<CH / 4>(out, ((size_t)img * npix + pix) * C + col0, v, valid);
+            else if constexpr (CH % 32 == 0 && !X3) oct_store<CH / 4>(rt, ((size_t)img * npix + pix) * C + col0, ostride, v, valid);
+            else pair_store<CH / 4>(rt, ((size_t)img * npix + pix) * C + col0, v, valid);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
             row_to_a16<CH, LOC>(v, s.region, row, col0);
@@ -1185,6 +1189,34 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             const int oth_sw = __shfl_xor_sync(0xffffffffu, own_sw, 1);
             const size_t base_a = odd ? oth_base : own_base, base_b = odd ? own_base : oth_base;   // rows 2i, 2i+1
             const int sw_a = odd ? oth_sw : own_sw, sw_b = odd ? own_sw : oth_sw;
+            if constexpr (CL16 && CH % 64 == 0) {
+                float hv[CH / 2];                                   // this thread's CH output channels as packed halves
+#pragma unroll
+                for (int c = 0; c < CH; c += SC) {
+                    float a[SC];
+                    ld_row<SC>(lane_base + Cfg::col_y + col0 + c, a);
+#pragma unroll
+                    for (int j0 = 0; j0 < SC / 4; j0 += 8) {
+                        float4 t8[8];
+                        pair_load<8>(reinterpret_cast<const float4*>(orow + c) + j0, valid, t8);
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            pair_unswap(t8[j], t8[j + 1]);
+#pragma unroll
+                            for (int u2 = 0; u2 < 2; ++u2) {
+                                const float4 rr = t8[j + u2];
+                                const int i = 4 * (j0 + j + u2);
+                                uint32_t h0, h1;
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(a[i + 1] + rr.y), "f"(a[i] + rr.x));
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(a[i + 3] + rr.w), "f"(a[i + 2] + rr.z));
+                                hv[(c + i) / 2] = __uint_as_float(h0);
+                                hv[(c + i) / 2 + 1] = __uint_as_float(h1);
+                            }
+                        }
+                    }
+                }
+                oct_store<CH / 8>(out, (((size_t)img * npix + pix) * C + col0) / 2, ostride / 2, hv, valid);
+            } else
 #pragma unroll 1
             for (int c = 0; c < CH; c += SC) {
                 float a[SC], r[SC];
@@ -1274,9 +1306,9 @@ template <int PX> struct BranchSel<256, 1, PX> { using Cfg = BranchCfgT<256, 4, 
 
 template <int CIN, int C, int BR, int V, int PX = 0>
 __global__ void __launch_bounds__(BranchSel<C, V, PX>::Cfg::NTG * BranchSel<C, V, PX>::Cfg::groups, 1)
-tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out) {
+tc_branch_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom geo, float* __restrict__ out, float* __restrict__ scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    tc_branch_body<CIN, C, BR, typename BranchSel<C, V, PX>::Cfg>(xin, w, plan, geo, out, smem);
+    tc_branch_body<CIN, C, BR, typename BranchSel<C, V, PX>::Cfg>(xin, w, plan, geo, out, scratch, smem);
 }
 
 
@@ -1455,7 +1487,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
             store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
             fetch_input_row<C>(vin, npix, (size_t)img, pix, valid, half, pfu);
         } else {
-            load_input_row<C, TPR, HM>(uin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : C);
+            load_input_row<C, TPR, PX ? HM : 3>(uin, npix, (size_t)img, pix, valid, s.region, row, half, 0);
         }
         TC_TRACE(plan, it, 4);
         sync_for_mma();
@@ -1464,7 +1496,7 @@ tc_merge_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGeom ge
         wait_done_ring<G>(s.done, phase, ring, plan, w0);
         TC_TRACE(plan, it, 6);
         if (InputPf<C>::enabled) store_input_row<C, true, 2, HM>(pfu, s.region, row, half);
-        else load_input_row<C, TPR, HM>(vin, npix, (size_t)img, pix, valid, s.region, row, half, PX ? 0 : C);
+        else load_input_row<C, TPR, PX ? HM : 3>(vin, npix, (size_t)img, pix, valid, s.region, row, half, 0);
         TC_TRACE(plan, it, 7);
         sync_for_mma();
         if (w0 && elect_one()) { issue_linear_t<G, MG_PD2B>(ring, plan, region_addr, ones_addr, tm + Cfg::col_acc, false); commit(s.done); }
@@ -2167,7 +2199,7 @@ int g_tc_variant = 0x41;     // debug hook (balf_debug_set key 4): per-stage bra
 
 template <int CIN, int C, int V, int PX>
 static int tc_launch_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
-                              float* u, float* v, cudaStream_t st) {
+                              float* u, float* v, float* su, float* sv, cudaStream_t st) {
     using Cfg = typename BranchSel<C, V, PX>::Cfg;
     constexpr int NG = Cfg::groups;
     int grid = 0;
@@ -2177,27 +2209,27 @@ static int tc_launch_branches(const float* xin, const DownW& w, const TcPlans& P
         if (b == 0) {
             if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 0, V, PX>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
             ProfScope ps(C == 32 ? "det_branch_grid_c32" : C == 64 ? "det_branch_grid_c64" : C == 128 ? "det_branch_grid_c128" : "det_branch_grid_c256", st);
-            tc_branch_kernel<CIN, C, 0, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, u);
+            tc_branch_kernel<CIN, C, 0, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, u, su);
         } else {
             if (int e = tc_launch_cfg(tc_branch_kernel<CIN, C, 1, V, PX>, smem, tc_cols(Cfg::ncols * NG), ntiles, &grid, NG, Cfg::NTG)) return e;
             ProfScope ps(C == 32 ? "det_branch_block_c32" : C == 64 ? "det_branch_block_c64" : C == 128 ? "det_branch_block_c128" : "det_branch_block_c256", st);
-            tc_branch_kernel<CIN, C, 1, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, v);
+            tc_branch_kernel<CIN, C, 1, V, PX><<<grid, Cfg::NTG * NG, smem, st>>>(xin, w, p, g, v, sv);
         }
     }
     return 0;
 }
 template <int CIN, int C, int PX>
 static int tc_run_branches(const float* xin, const DownW& w, const TcPlans& P, int level, const UnitGeom& g, int ntiles,
-                           float* u, float* v, cudaStream_t st) {
+                           float* u, float* v, float* su, float* sv, cudaStream_t st) {
     const int var = (g_tc_variant >> (2 * level)) & 3;
     if constexpr (C == 32) {
-        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, st);
-        if (var == 2) return tc_launch_branches<CIN, C, 2, PX>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, su, sv, st);
+        if (var == 2) return tc_launch_branches<CIN, C, 2, PX>(xin, w, P, level, g, ntiles, u, v, su, sv, st);
     }
     if constexpr (C == 64 || C == 128 || C == 256) {
-        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, st);
+        if (var == 1) return tc_launch_branches<CIN, C, 1, PX>(xin, w, P, level, g, ntiles, u, v, su, sv, st);
     }
-    return tc_launch_branches<CIN, C, 0, PX>(xin, w, P, level, g, ntiles, u, v, st);
+    return tc_launch_branches<CIN, C, 0, PX>(xin, w, P, level, g, ntiles, u, v, su, sv, st);
 }
 
 template <int CIN, int C, int PX>
@@ -2210,7 +2242,8 @@ static int tc_run_level(const float* xin, const DownW& w, const TcPlans& P, int 
     int grid = 0;
     BALF_REQUIRE((plan_matches<BranchG<CIN, C, PX>>(P.branch[level][0]) && plan_matches<BranchG<CIN, C, PX>>(P.branch[level][1]) &&
                   plan_matches<MergeG<CIN, C, PX>>(P.merge[level])), "internal: compile-time and packed GEMM plans differ (level %d)", level);
-    if (int e = tc_run_branches<CIN, C, PX>(xin, w, P, level, g, ntiles, u, v, st)) return e;
+    // (r and q are free until the merge kernel writes them: scratch of the stage-4 branch kernels' residual round trip)
+    if (int e = tc_run_branches<CIN, C, PX>(xin, w, P, level, g, ntiles, u, v, r, q, st)) return e;
     if constexpr (C <= 64) {
         const TcPlan& p = P.merge[level];
         BALF_REQUIRE(g.total_units % 2 == 0, "internal: odd unit count at stage %d", level);
