@@ -24,7 +24,7 @@ def _detect_device(args, im, detector, device):
         x = torch.tensor(pad, dtype=torch.float32).permute(2, 0, 1).unsqueeze(0).contiguous().to(dev)
         _, _, top, left = _capi.pad_geometry(im.shape[0], im.shape[1], 64)
     with torch.inference_mode():
-        prob = detector(x, precision=detector.resolve_precision("greedy"))["prob"]
+        prob = detector(x, precision=detector.resolve_precision("greedy"), want_logits=False)["prob"]
     h, w = im.shape[0], im.shape[1]
     xy, sc, dxdy, cnt = _capi.greedy_nms_topk(
         prob, args.num_features, border=args.border_size, thr=args.heatmap_confidence_threshold,
@@ -40,7 +40,7 @@ def detect_batch_device(args, u8, detector, nms="greedy"):
     B, h, w, _ = u8.shape
     x, (top, left) = _capi.preprocess_u8(u8)
     with torch.inference_mode():
-        prob = detector(x, precision=detector.resolve_precision(nms))["prob"]
+        prob = detector(x, precision=detector.resolve_precision(nms), want_logits=False)["prob"]
     if nms == "windowed":
         xy, sc, cnt = _capi.windowed_nms_topk(prob, args.num_features, border=args.border_size,
                                               nms_size=args.nms_size, crop=(top, left, h, w))
@@ -70,7 +70,7 @@ def detect_multiscale_batch_device(args, u8, detector, scale=0.7, levels=3, nms=
         else:
             x, (top, left) = _capi.resize_preprocess_u8(u8, hs, ws)
         with torch.inference_mode():
-            prob = detector(x, precision=detector.resolve_precision(nms))["prob"]
+            prob = detector(x, precision=detector.resolve_precision(nms), want_logits=False)["prob"]
         if nms == "windowed":
             xy, sc, cnt = _capi.windowed_nms_topk(prob, args.num_features, border=args.border_size,
                                                   nms_size=args.nms_size, crop=(top, left, hs, ws))

@@ -122,7 +122,9 @@ class MLP_MA_DECODER(nn.Module):
             self._packed = (key, _capi.detector_pack_weights(raw, self.arch))
         return self._packed[1]
 
-    def forward(self, x, precision=None):
+    def forward(self, x, precision=None, want_logits=True):
+        """reference contract: {'logits': [B,65,H/8,W/8], 'prob': [B,H,W]}; ``want_logits=False`` (the extraction pipelines of this
+        package, which only read 'prob') skips the logits tensor -- 'logits' is then None."""
         if self.training:
             raise RuntimeError("balf_b200 implements the inference path only: call .eval() first")
         if not x.is_cuda:
@@ -130,5 +132,5 @@ class MLP_MA_DECODER(nn.Module):
         if x.dim() != 4 or x.shape[1] != self.arch["dims"][0]:
             raise ValueError("expected input [B, %d, H, W], got %s" % (self.arch["dims"][0], tuple(x.shape)))
         precision = precision or self.resolve_precision()
-        logits, prob = _capi.detector_forward(x, self._weights(x.device), self.arch, precision)
+        logits, prob = _capi.detector_forward(x, self._weights(x.device), self.arch, precision, want_logits=want_logits)
         return {"logits": logits, "prob": prob}

@@ -38,7 +38,7 @@ def extract_detections(image_RGB_norm, model, device, cell_size=8, nms_size=15, 
     img = torch.as_tensor(np.ascontiguousarray(image_RGB_norm), dtype=torch.float32).to(dev)[None]
     h, w = img.shape[1], img.shape[2]
     x, (top, left) = _capi.preprocess_f32(img)
-    prob = model(x, precision=model.resolve_precision("windowed"))["prob"]
+    prob = model(x, precision=model.resolve_precision("windowed"), want_logits=False)["prob"]
     xy, sc, cnt = _capi.windowed_nms_topk(prob, num_points, border=border_size, nms_size=nms_size, crop=(top, left, h, w))
     n = int(cnt[0])
     return _points(xy[0].cpu().numpy(), sc[0].cpu().numpy(), n), prob[:, top:top + h, left:left + w]
@@ -55,7 +55,7 @@ def extract_detections_batch(images_u8, model, nms="nms_fast", nms_size=15, num_
     _, h, w, _ = images_u8.shape
     x, (top, left) = _capi.preprocess_u8(images_u8)
     kind = NMS_BACKENDS[nms]
-    prob = model(x, precision=model.resolve_precision("windowed" if kind == "windowed" else "greedy"))["prob"]
+    prob = model(x, precision=model.resolve_precision("windowed" if kind == "windowed" else "greedy"), want_logits=False)["prob"]
     if kind == "box":
         # repeatability_tools.box_nms(prob, size=4, iou=0.1, min_prob, keep_top_k) on the border-masked crop, then the
         # surviving pixels as points (get_point_coordinates): a 1 x 1 "window" keeps every positive pixel
