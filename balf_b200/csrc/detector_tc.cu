@@ -299,9 +299,19 @@ __device__ __forceinline__ void issue_linear_t(Ring& r, const TcPlan& p, uint32_
     }
 }
 
-// Thread 0: token mixing of both units (see issue_mix), GEMM GI = the 64 x 64 mixing matrix.
-template <typename G, int GI, int C, int CP>
-__device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y_addr, uint32_t y_stride, uint32_t d_tmem) {
+// Thread 0: token mixing of both units, GEMM GI = the 64 x 64 mixing matrix (A operand, K-major).  B = the tile's LayerNorm'ed
+// activations exactly as row_to_a16 wrote them -- [channel / 8][tile row][8 halves], i.e. an MN-major operand (instruction
+// descriptor bit 16): 16 bytes = 8 channels of one token, tile rows (tokens) 16 bytes apart, channel chunks TM * 16 bytes apart;
+// for an MN-major SWIZZLE_NONE operand LBO is the K-direction stride between 8-row core matrices (128) and SBO the MN-direction
+// stride between chunk planes (probed: scripts/umma_probe_mn.cu, profiles/r02_umma_probe_mn.txt).  Tokens 16 g .. 16 g + 15 of
+// unit u are tile rows 32 g + 16 u .. + 15 (TMEM lane = tile row), so K step g of unit u starts (32 g + 16 u) * 16 bytes in.
+// (The first version stored a transposed [channel][token] copy with one 2-byte shared-memory store per value.)
+constexpr uint32_t kDescHiMn = ((uint32_t)(TM * 16u) >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t desc_mn_of(uint32_t addr) {
+    return ((uint64_t)kDescHiMn << 32) | (uint64_t)(((128u >> 4) << 16) | ((addr >> 4) & 0x3FFFu));
+}
+template <typename G, int GI, int C>
+__device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y_addr, uint32_t d_tmem) {
     uint32_t w_addr, slot = 0;
     if (G::resident) {
         w_addr = r.wsm + g_off<G>(GI);
@@ -312,19 +322,19 @@ __device__ __forceinline__ void issue_mix_t(Ring& r, const TcPlan& p, uint32_t y
         w_addr = r.wsm + slot * p.slot_bytes;
     }
     fence_after_sync();
-    // fp16 operands: A = the 64 x 64 mixing matrix, B = the unit's activations [channel][token], 8 tokens per 16-byte chunk
-    constexpr uint32_t idesc = make_idesc_f16(64, C);
-    constexpr uint32_t b_lbo = (uint32_t)CP * 16u;
+    constexpr uint32_t idesc = make_idesc_f16(64, C) | (1u << 16);          // B MN-major
+    constexpr uint32_t lo_off = (uint32_t)(C / 8) * TM * 16u;                // split precision: the lo chunk planes follow the hi ones
     const uint64_t w_desc = desc_of(w_addr, 1024u);
+    const uint64_t y_desc = desc_mn_of(y_addr);
 #pragma unroll
     for (uint32_t u = 0; u < 2; ++u) {
-        const uint64_t y_desc = desc_of(y_addr + u * y_stride, b_lbo);
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) {
-            mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((ks * 2u * b_lbo) >> 4), idesc, ks > 0);
-            if constexpr (G::x3) {      // lo copies: the mixing matrix 8 KB (64 x 64 halves) further, the activations after both units' hi copies
-                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((2u * y_stride + ks * 2u * b_lbo) >> 4), idesc, true);
-                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((8192u + ks * 2u * 1024u) >> 4), y_desc + ((ks * 2u * b_lbo) >> 4), idesc, true);
+            const uint32_t yo = (32u * ks + 16u * u) * 16u;
+            mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + (yo >> 4), idesc, ks > 0);
+            if constexpr (G::x3) {      // lo copies: the mixing matrix 8 KB (64 x 64 halves) further
+                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((ks * 2u * 1024u) >> 4), y_desc + ((lo_off + yo) >> 4), idesc, true);
+                mma_f16(d_tmem + ((u * 16u) << 16), w_desc + ((8192u + ks * 2u * 1024u) >> 4), y_desc + (yo >> 4), idesc, true);
             }
         }
     }
@@ -958,8 +968,7 @@ template <int C, int TPR_, int NG_, bool WW_ = false, int PX_ = 0> struct Branch
     static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
     static constexpr uint32_t y_stride = (CP * 64 + 16) * 2;       // bytes between the two units' (fp16) mixing operands
     // operand region of a group: the [128 x C] A operand (hi chunks, then lo chunks: PX) or the two units' mixing operands (hi, hi, lo, lo)
-    static constexpr uint32_t yb = (PX ? 4u : 2u) * y_stride, ab = (uint32_t)TM * C * (PX ? 4u : 2u);
-    static constexpr uint32_t region = ((yb > ab ? yb : ab) + 127u) / 128u * 128u;
+    static constexpr uint32_t region = (uint32_t)TM * C * (PX ? 4u : 2u);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
     static constexpr bool swz_out = false;                         // (round-1 layout: fp32 tiles in the swizzled panel layout)
     static constexpr bool h16_out = C <= 128;                      // u' / v' leave as fp16 tiles [C / 8 chunks][128 pixels][8 halves]: the operand
@@ -1128,30 +1137,18 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             float sum = 0.f, sq = 0.f;
             gelu_row<CH, true>(v, sum, sq);
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
-            __half* yt = reinterpret_cast<__half*>(s.region) + (size_t)ug * (Cfg::y_stride / 2) + (size_t)(tok >> 3) * (Cfg::CP * 8) + (tok & 7) + (size_t)col0 * 8;
             norm_row<CH>(v, rstd, shift);
 #pragma unroll
             for (int i = 0; i < CH; i += 2) {
                 const float2 gw = *reinterpret_cast<const float2*>(s.vec + col0 + i), gb = *reinterpret_cast<const float2*>(s.vec + 256 + col0 + i);
-                float o0, o1;
-                upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), o0, o1);
-                if (!(BALF_EXP & 2) || o0 == 12345.678f) {
-                    uint32_t h, l;
-                    if constexpr (X3) split_h2(o0, o1, h, l);
-                    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(o1), "f"(o0));
-                    reinterpret_cast<unsigned short*>(yt)[(size_t)i * 8] = (unsigned short)(h & 0xFFFFu);
-                    reinterpret_cast<unsigned short*>(yt)[(size_t)(i + 1) * 8] = (unsigned short)(h >> 16);
-                    if constexpr (X3) {                                  // lo copies of both units follow the two hi copies
-                        reinterpret_cast<unsigned short*>(yt)[(size_t)Cfg::y_stride + (size_t)i * 8] = (unsigned short)(l & 0xFFFFu);
-                        reinterpret_cast<unsigned short*>(yt)[(size_t)Cfg::y_stride + (size_t)(i + 1) * 8] = (unsigned short)(l >> 16);
-                    }
-                }
+                upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), v[i], v[i + 1]);
             }
+            row_to_a16<CH, LOC>(v, s.region, row, col0);          // the mixing MMA reads it as an MN-major B operand (issue_mix_t)
         }
         TC_TRACE(plan, it, 10);
         sync_for_mma<NG, NTG>(grp);
         // ---- token mixing, gating y1 * (y2' + 1)
-        if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_mix_t<G, BG_WM, C, Cfg::CP>(ring, plan, region_addr, Cfg::y_stride, tm + Cfg::col_y + C); commit(s.done); }
+        if (!(BALF_EXP & 16) && w0 && elect_one()) { issue_mix_t<G, BG_WM, C>(ring, plan, region_addr, tm + Cfg::col_y + C); commit(s.done); }
         TC_TRACE(plan, it, 11);
         wait_done_ring<G, NG, NTG, Cfg::WW>(s.done, phase, ring, plan, w0, grp);
         TC_TRACE(plan, it, 12);
