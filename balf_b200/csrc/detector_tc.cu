@@ -1061,7 +1061,7 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
     for (int t = vblock; t < ntiles; t += vgrid, ++it) {
         TC_TRACE(plan, it, 0);
         bool valid; int img, pix;
-        if (InputPf<CIN, TPR>::enabled && TPR > 1) { valid = nvld; img = nim; pix = npx; }      // (one thread per row: no registers to spare)
+        if (InputPf<CIN, TPR>::enabled && (TPR > 1 || !X3)) { valid = nvld; img = nim; pix = npx; }   // (split precision at one thread per row: no registers to spare)
         else coords(t, valid, img, pix);
         float* orow = rt + ((size_t)img * npix + pix) * C + col0;
         float v[CH], rstd, shift;
