@@ -606,7 +606,7 @@ def main():
         "detector": {"ms_per_step": det_ms, "tflops": det_tf,
                      "frac_of_tf32_peak": det_tf / (pk["tensor"] / 2) if det_tf else None,
                      "frac_of_f16_peak": det_tf / pk["tensor"] if det_tf else None,
-                     "note": "most GEMMs run as kind::f16 (fp16 operands), conv.0 / token mixing / biases as kind::tf32",
+                     "note": "every GEMM and the token mixing run as kind::f16 (fp16 operands); stage-1 conv.0 on the CUDA cores, bias columns as kind::tf32",
                      "peak_source": pk["src"]},
         "kernels": kernels,
         "cfg3": {"workload": "configs[3]: 1024 synthetic 1024x1024 images strong-scaled over %d rank(s), detector + windowed NMS + "
