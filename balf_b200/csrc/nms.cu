@@ -1024,6 +1024,39 @@ __global__ void __launch_bounds__(1024) select_sort_kernel(NmsWs ws, int mode, i
     }
     __syncthreads();
     // bitonic sort, descending
+    if (npow2 == 2048 && blockDim.x == 1024) {
+        // Two keys per thread (elements 2t, 2t + 1) in registers: stride 1 is a compare-exchange inside the thread, strides 2-32
+        // are 64-bit shuffles inside the warp, and only strides >= 64 (15 of the 66 stages) go through shared memory with a CTA
+        // barrier each -- the all-shared-memory version spent two thirds of this kernel's time in its 66 barrier-separated stages.
+        const int t = threadIdx.x;
+        u64 k0 = sel[2 * t], k1 = sel[2 * t + 1];
+        for (int size = 2; size <= 2048; size <<= 1) {
+            const bool desc = ((2 * t) & size) == 0;
+            int stride = size >> 1;
+            if (stride >= 64) {
+                sel[2 * t] = k0; sel[2 * t + 1] = k1;
+                __syncthreads();
+                for (; stride >= 64; stride >>= 1) {
+                    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool d2 = (lo & size) == 0;
+                    const u64 a = sel[lo], c = sel[hi];
+                    if ((a < c) == d2) { sel[lo] = c; sel[hi] = a; }
+                    __syncthreads();
+                }
+                k0 = sel[2 * t]; k1 = sel[2 * t + 1];
+            }
+            for (; stride >= 2; stride >>= 1) {
+                const int d = stride >> 1;
+                const bool keep_max = ((t & d) == 0) == desc;
+                const u64 o0 = __shfl_xor_sync(0xffffffffu, k0, d), o1 = __shfl_xor_sync(0xffffffffu, k1, d);
+                k0 = keep_max ? (k0 > o0 ? k0 : o0) : (k0 < o0 ? k0 : o0);
+                k1 = keep_max ? (k1 > o1 ? k1 : o1) : (k1 < o1 ? k1 : o1);
+            }
+            if ((k0 < k1) == desc) { const u64 x = k0; k0 = k1; k1 = x; }
+        }
+        sel[2 * t] = k0; sel[2 * t + 1] = k1;
+        __syncthreads();
+    } else {
     for (int size = 2; size <= npow2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = threadIdx.x; i < npow2 / 2; i += blockDim.x) {
@@ -1034,6 +1067,7 @@ __global__ void __launch_bounds__(1024) select_sort_kernel(NmsWs ws, int mode, i
             }
             __syncthreads();
         }
+    }
     }
     const int m = min(n_sel, k);
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
