@@ -1,34 +1,38 @@
-// BALF detector forward on the sm_100a tensor cores: precision 1 ("tf32").
+// BALF detector forward on the sm_100a tensor cores: precision 1 ("tf32": single-rounded fp16 / tf32 operands) and precision 2
+// ("f16x3": every operand an fp16 hi + lo pair, three MMAs per product -- template flag PX, see BranchG).
 //
 // Same semantics and kernel decomposition as the fp32 path in detector.cu (reference:
 // balf/model/mlp_ma_decoder.py:201-244 Down, :119-149 multi-axis gMLP, :25-117 grid / block gMLP,
 // :151-199 channel attention; balf/model/decoder.py:16-30 head), but every Linear layer and both
-// token-mixing products are tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) and the whole chain of
-// a tile stays on chip:
+// token-mixing products are tcgen05.mma (kind::f16 on fp16 operands -- the same 11-bit significand as tf32 --
+// with fp32 accumulation in TMEM; kind::tf32 for the bias columns) and the whole chain of a tile stays on chip:
 //
 //   shared memory (A operand, chunk-major) --tcgen05.mma--> TMEM accumulator --tcgen05.ld--> registers
 //        ^                                                                          |
-//        +---- activation / LayerNorm / gating, two threads per pixel row  <--------+
+//        +---- activation / LayerNorm / gating, 1 / 2 / 4 threads per pixel row  <--+
 //
 // A tile is 128 pixels = 2 "units" of 64 tokens (grid branch: the 64 cells of one in-cell offset;
-// block branch: one 8x8 block; merge / head: 64 consecutive pixels).  A CTA has 256 threads: thread
-// (row = tid % 128, half = tid / 128) owns one half of the channels of pixel row `row`; TMEM lane ==
-// row, so GELU, gating and softmax are thread-local and LayerNorm needs one (sum, sum of squares)
-// exchange between the two halves of a row through shared memory.
+// block branch: one 8x8 block; merge / head: 64 consecutive pixels).  Thread (row = tid % 128, part = tid / 128)
+// owns one part (1 / TPR) of the channels of pixel row `row`; TMEM lane == row, so GELU, gating and softmax are
+// thread-local and LayerNorm needs one (sum, sum of squares) exchange between the parts of a row through shared
+// memory.  Stage 1 runs one thread per row in five independent tile groups per CTA (BranchCfgT).
 //
 // What the epilogues do NOT do: biases ride in the GEMM (one extra K = 8 MMA whose A operand is a
 // constant [1 1 0 ...] column block and whose B rows hold the bias split into tf32 hi + lo parts), and
 // the LayerNorm affine parameters that feed a Linear layer are folded into that layer's weights and bias
 // when the weights are packed (W' = W diag(gamma), b' = b + W beta).  GELU is the exact erf form,
-// evaluated as v * Phi(v) with erfc(t) = exp2(t * P(t)) (degree-5 fit, |err| < 3.7e-6, scripts/fit_gelu.py).
+// evaluated as relu(v) - |v| * 0.5 erfc(|v| / sqrt 2) with erfc through exp2 of a degree-5 fit (|err| < 3.7e-6,
+// scripts/fit_gelu.py).
 //
-// The 64x64 token mixing runs as two M=64 MMAs (A = mixing matrix, B = the unit's activations stored
-// [channel][token]); their accumulators interleave in the two 16-lane halves of every 32-lane TMEM
-// quadrant, which fixes the lane <-> pixel mapping of the branch kernels:
+// The 64x64 token mixing runs as M = 64 MMAs (A = mixing matrix, B = the tile's activations in the A-operand layout,
+// read as an MN-major operand, see issue_mix_t); the accumulators of the two units interleave in the two 16-lane
+// halves of every 32-lane TMEM quadrant, which fixes the lane <-> pixel mapping of the branch kernels:
 //        unit g = (lane % 32) / 16,   token = (lane / 32) * 16 + lane % 16.
 // Weights are pre-packed into the exact shared-memory image of the B operands and brought in by TMA
 // bulk copies (cp.async.bulk + mbarrier) -- once per CTA when the whole set fits next to the operand
-// region (level 1), otherwise through a 2-slot ring that runs ahead of the MMAs.
+// region (stages 1-3), otherwise through a 2-3 slot ring that runs ahead of the MMAs.  Tensors that cross HBM between
+// the kernels of a stage are fp16 wherever their consumer rounds them to fp16 anyway (u', v', r, the pooled level
+// inputs); DESIGN.md section 3.
 #include <cuda_fp16.h>
 #include "detector.cuh"
 #include "umma.cuh"
@@ -965,9 +969,7 @@ template <int C, int TPR_, int NG_, bool WW_ = false, int PX_ = 0> struct Branch
     static constexpr int TPR = TPR_;
     static constexpr int NTG = TM * TPR;                           // threads per tile group
     static constexpr int CH = C / TPR;
-    static constexpr int CP = C + 1;                               // padded rows of the [channel][token] operand
-    static constexpr uint32_t y_stride = (CP * 64 + 16) * 2;       // bytes between the two units' (fp16) mixing operands
-    // operand region of a group: the [128 x C] A operand (hi chunks, then lo chunks: PX) or the two units' mixing operands (hi, hi, lo, lo)
+    // operand region of a group: the [128 x C] A operand (hi chunks, then lo chunks: PX); the token mixing reads the same layout
     static constexpr uint32_t region = (uint32_t)TM * C * (PX ? 4u : 2u);
     static constexpr bool park_u = C <= 128;                       // u stays in TMEM (else it round-trips through `out`)
     static constexpr bool swz_out = false;                         // (round-1 layout: fp32 tiles in the swizzled panel layout)
@@ -1139,9 +1141,10 @@ __device__ __forceinline__ void tc_branch_body(const float* __restrict__ xin, co
             row_stats<NG, TPR>(sum, sq, s.xch + (xb++ & 1) * TPR * TM, row, half, C, rstd, shift, grp);
             norm_row<CH>(v, rstd, shift);
 #pragma unroll
-            for (int i = 0; i < CH; i += 2) {
-                const float2 gw = *reinterpret_cast<const float2*>(s.vec + col0 + i), gb = *reinterpret_cast<const float2*>(s.vec + 256 + col0 + i);
+            for (int i = 0; i < CH; i += 4) {
+                const float4 gw = *reinterpret_cast<const float4*>(s.vec + col0 + i), gb = *reinterpret_cast<const float4*>(s.vec + 256 + col0 + i);
                 upk2(fma2(pk2(v[i], v[i + 1]), pk2(gw.x, gw.y), pk2(gb.x, gb.y)), v[i], v[i + 1]);
+                upk2(fma2(pk2(v[i + 2], v[i + 3]), pk2(gw.z, gw.w), pk2(gb.z, gb.w)), v[i + 2], v[i + 3]);
             }
             row_to_a16<CH, LOC>(v, s.region, row, col0);          // the mixing MMA reads it as an MN-major B operand (issue_mix_t)
         }
