@@ -181,14 +181,14 @@ def _features_batch_device(args, rgbs, grays, detector, descriptor, dev):
     identical to ``extract_features`` one image at a time (no stage mixes images)."""
     u8 = torch.from_numpy(np.ascontiguousarray(np.stack(rgbs))).to(dev, non_blocking=True)
     xy, _, dxdy, cnt = detect_batch_device(args, u8, detector, "greedy")
+    gray_dev = [torch.from_numpy(np.ascontiguousarray(g)).to(dev, non_blocking=True) for g in grays]   # uploads under the detector
     counts = cnt.cpu().tolist()
     patches = []
     for b, n in enumerate(counts):
         kp = xy[b, :n].float()
         if dxdy is not None:
             kp = kp + dxdy[b, :n]
-        gray = torch.from_numpy(np.ascontiguousarray(grays[b])).to(dev, non_blocking=True)
-        patches.append(_capi.extract_patches(gray, kp, float(args.s_mult), 32))
+        patches.append(_capi.extract_patches(gray_dev[b], kp, float(args.s_mult), 32))
     with torch.inference_mode():
         descs = descriptor(torch.cat(patches)) if sum(counts) else torch.zeros(0, 128, device=dev)
     out, o = [], 0
