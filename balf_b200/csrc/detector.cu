@@ -416,7 +416,20 @@ __global__ void pool_kernel(const float* __restrict__ r, const float* __restrict
             } else {
                 rv = __ldg(reinterpret_cast<const float4*>(r) + cs);
             }
-            float4 qv = __ldg(reinterpret_cast<const float4*>(q) + cs);
+            float4 qv;
+            if constexpr (swz == 1) {
+                // q of those stages: 24 bits per value in two planes per tile of 128 pixels (tc_merge_bulk_kernel): [C / 8][128][8 x u16]
+                // = the top halves of the fp32 patterns, then [C / 16][128][16 x u8] = the next byte
+                const unsigned char* qt = reinterpret_cast<const unsigned char*>(q) + (p - rowi) * C * 3;
+                const uint2 t16 = __ldg(reinterpret_cast<const uint2*>(qt + ((size_t)(c4 >> 1) * 128 + rowi) * 16 + (c4 & 1) * 8));
+                const uint32_t m8 = __ldg(reinterpret_cast<const uint32_t*>(qt + (size_t)128 * C * 2 + ((size_t)(c4 >> 2) * 128 + rowi) * 16 + (c4 & 3) * 4));
+                qv.x = __uint_as_float(((t16.x & 0xFFFFu) << 16) | ((m8 & 0xFFu) << 8));
+                qv.y = __uint_as_float((t16.x & 0xFFFF0000u) | (m8 & 0xFF00u));
+                qv.z = __uint_as_float(((t16.y & 0xFFFFu) << 16) | ((m8 >> 8) & 0xFF00u));
+                qv.w = __uint_as_float((t16.y & 0xFFFF0000u) | ((m8 >> 16) & 0xFF00u));
+            } else {
+                qv = __ldg(reinterpret_cast<const float4*>(q) + cs);
+            }
             best.x = fmaxf(best.x, rv.x * s.x + qv.x); best.y = fmaxf(best.y, rv.y * s.y + qv.y);
             best.z = fmaxf(best.z, rv.z * s.z + qv.z); best.w = fmaxf(best.w, rv.w * s.w + qv.w);
         }

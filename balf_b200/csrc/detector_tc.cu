@@ -1722,7 +1722,36 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
                 upk2(x1, v[i], v[i + 1]);
                 upk2(add2(x1, xz), x0[i], x0[i + 1]);
             }
-            row_to_sw<CH, false>(x0, regQ, row, col0);
+            if constexpr (PX == 0) {
+                // q crosses HBM as 24 bits per value -- the top 16 bits of the fp32 pattern (rounded to 16 mantissa bits, RN on
+                // the bit pattern) in a [C / 8][128][8 x u16] plane and the next 8 bits in a [C / 16][128][16 x u8] plane: its only
+                // consumer (pool_kernel) rounds max(r s + q) to fp16, 2^-17 on q is noise there; 96 instead of 128 bytes per pixel
+                // at C = 32 on the two HBM-bound kernels of the stage.  (fp16 q was measured at +15 % score-map error.)
+                uint32_t bq[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) bq[i] = __float_as_uint(x0[i]) + 0x80u;
+                unsigned char* const qb = reinterpret_cast<unsigned char*>(regQ);
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) {          // top halves: bytes 2, 3 of each value
+                    uint4 o;
+                    o.x = __byte_perm(bq[8 * j], bq[8 * j + 1], 0x7632); o.y = __byte_perm(bq[8 * j + 2], bq[8 * j + 3], 0x7632);
+                    o.z = __byte_perm(bq[8 * j + 4], bq[8 * j + 5], 0x7632); o.w = __byte_perm(bq[8 * j + 6], bq[8 * j + 7], 0x7632);
+                    *reinterpret_cast<uint4*>(qb + ((size_t)(col0 / 8 + j) * TM + row) * 16) = o;
+                }
+#pragma unroll
+                for (int j = 0; j < CH / 16; ++j) {         // middle bytes: byte 1 of each value
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t lo = __byte_perm(bq[16 * j + 4 * e], bq[16 * j + 4 * e + 1], 0x0051);
+                        const uint32_t hi = __byte_perm(bq[16 * j + 4 * e + 2], bq[16 * j + 4 * e + 3], 0x0051);
+                        w4[e] = __byte_perm(lo, hi, 0x5410);
+                    }
+                    *reinterpret_cast<uint4*>(qb + (size_t)TM * C * 2 + ((size_t)(col0 / 16 + j) * TM + row) * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            } else {
+                row_to_sw<CH, false>(x0, regQ, row, col0);
+            }
             float sum, sq;
             { float a, b; upk2(s2, a, b); sum = a + b; upk2(q2, a, b); sq = a + b; }
             row_stats(sum, sq, s.xch, row, half, C, rstd, shift);
@@ -1734,7 +1763,8 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
         if (w0 && elect_one()) {
             issue_linear_t<G, MG_RC1, !G::h16(MG_RC1)>(ring, plan, w_addr, ones_addr, tm + Cfg::col_acc, true);
             commit(s.done);
-            bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
+            if constexpr (PX == 0) bulk_store(qout + (size_t)t * (tile_floats * 3 / 4), q_addr, Cfg::tile_bytes / 4 * 3);   // 24-bit planes
+            else bulk_store(qout + (size_t)t * tile_floats, q_addr, Cfg::tile_bytes);
             bulk_commit();
             if (nt < ntiles) load_tile(nt);
         }

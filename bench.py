@@ -206,17 +206,18 @@ def kernel_work(name, images):
             cin, ch, px = level_dims()[lv[c]]
             n = images * px
             uv = 2 if ch <= 128 else 4                   # bytes per element of u' / v' in HBM (fp16 tiles at stages 1-3)
-            rb = 2                                       # ... of r (fp16 at every stage); q is fp32
+            rb = 2                                       # ... of r (fp16 at every stage)
+            qb = 3 if ch <= 64 else 4                    # ... of q (24-bit planes at stages 1-2, fp32 above)
             xb = 4 if cin < 8 else 2                     # ... of the level input (the network input is fp32, pooled outputs fp16)
             if "branch" in name:                       # half of dense1, branch dense1, token mix, dense2; x in, u' out
                 return n * (2 * cin * ch + 2 * ch * ch + 4 * ch * ch + 128 * ch + 2 * ch * ch), n * (xb * cin + uv * ch)
             if "merge" in name:                        # conv.0, dense2 (2C->C), conv1, conv2; x, u', v' in, r, q out
-                return n * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch), n * (xb * cin + 2 * uv * ch + rb * ch + 4 * ch)
+                return n * (2 * cin * ch + 4 * ch * ch + 4 * ch * ch), n * (xb * cin + 2 * uv * ch + rb * ch + qb * ch)
         if name == "det_head":                         # r (fp16), q in; prob out (64 values per 8x8 cell)
             n = images * level_dims()[3][2]
             return n * (2 * 256 * 256 + 2 * 256 * 65), n * (2 * 256 + 4 * 256 + 4 * 64)
         if name == "det_pool":                         # r (fp16), q in, pooled out (fp16, a quarter of the pixels), stages 1-3
-            return 0, sum(images * px * (2 * ch + 4 * ch + ch // 2) for _, ch, px in level_dims()[:3])
+            return 0, sum(images * px * (2 * ch + (3 if ch <= 64 else 4) * ch + ch // 2) for _, ch, px in level_dims()[:3])
         return 0, 0
     if name.startswith("nms_windowed"):
         return 0, images * (4 * H * W)
