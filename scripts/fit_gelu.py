@@ -32,7 +32,7 @@ for deg in (4, 5, 6, 7):
     print("deg %d: max abs %.3e (at v=%.3f)  max rel(|exact|>1e-6) %.3e" % (deg, abs_err.max(), v[abs_err.argmax()], rel[np.abs(exact) > 1e-6].max()))
     print("   coeffs:", ", ".join("%.9ef" % x for x in c32))
 
-# ---- the form the kernels evaluate (csrc/detector_tc.cu: gelu_erf): constants absorbed so that the epilogue needs
+# ---- the form the kernels evaluate (csrc/detector_tc.cuh: gelu_erf): constants absorbed so that the epilogue needs
 # no FMUL:  a = min(|v|, 4 sqrt 2),  R(a) = -1 + sum_i c_i s^(i+1) a^(i+1)  (s = 1/sqrt 2, c = the degree-6 fit above),
 # gelu(v) = max(v, 0) - a * exp2(R(a)).
 c6 = np.array([-1.627962232e+00, -9.178448915e-01, -1.506087184e-01, 3.200358897e-02, -4.260182846e-03, 2.576425322e-04])

@@ -1,6 +1,6 @@
 """Development helper: per-phase SM-clock timeline of CTA 0 of one tensor-core branch kernel.
     python scripts/tc_trace.py [level 0..3] [batch]
-Stamps (csrc/detector_tc.cu, TC_TRACE): 0 tile start; then per phase k: 3k+1 epilogue/loads done (before the MMA
+Stamps (csrc/detector_tc.cuh, TC_TRACE): 0 tile start; then per phase k: 3k+1 epilogue/loads done (before the MMA
 sync), 3k+2 MMA issued + committed (thread 0) / passed the sync (epilogue thread), 3k+3 accumulator ready."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

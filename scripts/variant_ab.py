@@ -1,5 +1,5 @@
 """Development helper (GPU): A/B of the branch-kernel variants selected by balf_debug_set(4, mask)
-(2 bits per stage, see BranchSel in csrc/detector_tc.cu): score-map difference against variant 0 and per-kernel times.
+(2 bits per stage, see BranchSel in csrc/detector_tc.cuh): score-map difference against variant 0 and per-kernel times.
     python scripts/variant_ab.py [B] [mask ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
