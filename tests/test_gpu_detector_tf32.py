@@ -1,4 +1,4 @@
-"""Parity of the tensor-core detector path (precision 'tf32': balf_b200/csrc/detector_tc.cu, tcgen05
+"""Parity of the tensor-core detector path (precision 'tf32': balf_b200/csrc/detector_tc.cuh, tcgen05
 kind::tf32 with fp32 accumulation in TMEM) with the reference's golden vectors and the CPU oracle.
 
 Bound (BASELINE.json north_star): score maps within rel <= 1e-3 for fp32-accumulate paths, and
