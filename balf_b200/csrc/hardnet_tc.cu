@@ -28,6 +28,9 @@ using namespace umma;
 
 constexpr int kHnSlots = 3;
 constexpr int kHnThreads = 128;
+// conv kernels: two warp groups of 128 threads share the epilogue (tile idx = g * T + t goes to group idx % 2): the layers spend
+// most of their time in the TMEM -> ReLU -> fp16 -> next-layer-image epilogue (tensor pipe 16-39 % busy with one group)
+constexpr int kHnConvThreads = 256;
 // final layer (8x8 "valid" conv = [patches x 8192] x [8192 x 128]): K blocks of 32 = (position, 32 channels)
 constexpr int kFinalKB = 32, kFinalBlocks = 8192 / kFinalKB, kFinalBlockFloats = 128 * kFinalKB, kFinalSplit = 4;
 
@@ -97,7 +100,7 @@ __device__ __forceinline__ void hn_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
 }
 
 template <int CIN, int COUT, int STRIDE, int HOUT, int G, int KB, int NEXT, int RN, int EB>
-__global__ void __launch_bounds__(kHnThreads, 1)
+__global__ void __launch_bounds__(kHnConvThreads, 1)
 hn_tc_conv_kernel(const float* __restrict__ in_, const float* __restrict__ wblk_, const float* __restrict__ shift,
                   float* __restrict__ out_, int n) {
     using Ge = HnGeom<CIN, COUT, STRIDE, HOUT, G, KB, EB>;
@@ -115,7 +118,7 @@ hn_tc_conv_kernel(const float* __restrict__ in_, const float* __restrict__ wblk_
     uint64_t* in_full = bars + 2 * kHnSlots;
     uint64_t* done = bars + 2 * kHnSlots + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kHnSlots + 2);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, row = tid & 127, wg = tid >> 7;     // accumulator row / epilogue warp group of this thread
     const bool w0 = warp0_uniform();
 
     if (tid < 32) tmem_alloc(tmem_slot, Ge::ncols);
@@ -125,12 +128,12 @@ hn_tc_conv_kernel(const float* __restrict__ in_, const float* __restrict__ wblk_
         mbar_init(done, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < COUT; i += kHnThreads) s_shift[i] = __ldg(shift + i);
+    for (int i = tid; i < COUT; i += kHnConvThreads) s_shift[i] = __ldg(shift + i);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = *tmem_slot;
-    const uint32_t lane_base = tm + ((uint32_t)(tid & ~31) << 16);
+    const uint32_t lane_base = tm + ((uint32_t)(row & ~31) << 16);
 
     const int ngroups = (n + G - 1) / G;
     const int my_groups = (int)blockIdx.x < ngroups ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -162,7 +165,7 @@ hn_tc_conv_kernel(const float* __restrict__ in_, const float* __restrict__ wblk_
         __syncthreads();
         {
             constexpr int NH = Ge::NPL == 1 ? 2 * Ge::PW + 2 * (Ge::PH - 2) : 4 * (Ge::PW + Ge::PH - 1);
-            for (int i = tid; i < NH * (CIN / EPC) * G; i += kHnThreads) {
+            for (int i = tid; i < NH * (CIN / EPC) * G; i += kHnConvThreads) {
                 const int h = i % NH, c = (i / NH) % (CIN / EPC), g = i / (NH * (CIN / EPC));
                 int row;
                 if (Ge::NPL == 1) {
@@ -231,7 +234,8 @@ hn_tc_conv_kernel(const float* __restrict__ in_, const float* __restrict__ wblk_
             if (p0 + g >= n) break;                         // uniform over the CTA
 #pragma unroll
             for (int t = 0; t < Ge::T; ++t) {
-                const int q = Ge::qs(t) + tid;
+                if (((g * Ge::T + t) & 1) != wg) continue;          // this tile belongs to the other warp group (uniform per warp)
+                const int q = Ge::qs(t) + row;
                 const int gy = q / Ge::PW, gx = q - gy * Ge::PW;
                 const int oy = gy - 1, ox = gx - 1;
                 bool valid = q <= Ge::QLAST && ox >= 0 && ox < HOUT && oy >= 0 && oy < HOUT;
@@ -562,7 +566,7 @@ static int hn_tc_launch(const char* name, const float* in, const float* wblk, co
     const int grid = ngroups < hn_num_sms() ? ngroups : hn_num_sms();
     {
         ProfScope p(name, st);
-        kernel<<<grid, kHnThreads, Ge::smem, st>>>(in, wblk, shift, out, n);
+        kernel<<<grid, kHnConvThreads, Ge::smem, st>>>(in, wblk, shift, out, n);
     }
     BALF_COUNT_LAUNCH(1);
     BALF_LAUNCH_OK();
