@@ -131,3 +131,13 @@ def test_preprocess_matches_reference_padding():
         np.testing.assert_array_equal(x.cpu().numpy(), postproc.preprocess(im))
         xg, _ = c.preprocess_u8(torch.from_numpy(im[:, :, :1].copy()).to("cuda:0")[None])     # gray -> 3 planes
         np.testing.assert_array_equal(xg.cpu().numpy(), x.cpu().numpy())
+
+
+def test_forward_without_logits(det_gpu):
+    """the extraction pipelines call forward(want_logits=False): same score map bit for bit, 'logits' is None"""
+    x = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(9)).to("cuda:0")
+    with torch.inference_mode():
+        a = det_gpu(x)
+        b = det_gpu(x, want_logits=False)
+    assert b["logits"] is None and a["logits"] is not None
+    assert torch.equal(a["prob"], b["prob"])
