@@ -1668,7 +1668,7 @@ tc_merge_bulk_kernel(const float* __restrict__ xin, DownW w, TcPlan plan, UnitGe
     const int col0 = half * CH;
     const size_t npix = (size_t)geo.h * geo.w;
     const size_t tile_floats = (size_t)TM * C;              // tile t of the batch chunk starts at float t * tile_floats in u', v', r, q
-    uint32_t phase = 0, ld_phase = 0, xb = 0;
+    uint32_t phase = 0, ld_phase = 0;
     auto coords = [&](int tt, int& im, int& px) {
         const int un = 2 * tt + (row >> 6);
         im = fast_div(un, geo.upi, geo.inv_upi);
