@@ -175,13 +175,41 @@ def extract_features(args, im_rgb, im_gray, detector, descriptor, device):
     return kpts_np[:, 0:2], descs.cpu().numpy()
 
 
+_PAIR_STAGING = {}      # (device, shape) -> pinned uint8 staging buffers of the device-resident pair path, reused across calls
+
+
+def _pinned_upload(key, arrays, dev):
+    """Same-shape uint8 host arrays -> ONE device tensor [len(arrays), ...]: each array is copied into its slice of a cached
+    pinned staging buffer and leaves on an asynchronous DMA right away -- the copy of array i+1 into pinned memory runs while
+    array i crosses PCIe, and no stacked pageable copy is built first.  The buffer may be rewritten only once its last DMA has
+    finished: the event recorded after the copies is waited on at the next use."""
+    shape = (len(arrays),) + tuple(arrays[0].shape)
+    slot = _PAIR_STAGING.get((key, dev, shape))
+    if slot is None:
+        slot = _PAIR_STAGING[(key, dev, shape)] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True), None]
+    pin, last = slot
+    if last is not None:
+        last.synchronize()
+    out = torch.empty(shape, dtype=torch.uint8, device=dev)
+    view = pin.numpy()
+    for i, a in enumerate(arrays):
+        np.copyto(view[i], a)
+        out[i].copy_(pin[i], non_blocking=True)
+    slot[1] = torch.cuda.Event()
+    slot[1].record(torch.cuda.current_stream(dev))
+    return out
+
+
 def _features_batch_device(args, rgbs, grays, detector, descriptor, dev):
     """Same-shape uint8 images -> per image (xy int32 [n,2], dxdy fp32 [n,2] | None, descriptors fp32 [n,128]), all on the device:
     ONE batched detector + greedy NMS call, per-image patch sampling, ONE HardNet call over all patches.  Per-image results are
     identical to ``extract_features`` one image at a time (no stage mixes images)."""
-    u8 = torch.from_numpy(np.ascontiguousarray(np.stack(rgbs))).to(dev, non_blocking=True)
+    u8 = _pinned_upload("rgb", rgbs, dev)
     xy, _, dxdy, cnt = detect_batch_device(args, u8, detector, "greedy")
-    gray_dev = [torch.from_numpy(np.ascontiguousarray(g)).to(dev, non_blocking=True) for g in grays]   # uploads under the detector
+    if all(g.dtype == np.uint8 and g.shape == grays[0].shape for g in grays):
+        gray_dev = _pinned_upload("gray", grays, dev)                                    # uploads under the detector
+    else:
+        gray_dev = [torch.from_numpy(np.ascontiguousarray(g)).to(dev, non_blocking=True) for g in grays]
     counts = cnt.cpu().tolist()
     patches = []
     for b, n in enumerate(counts):
@@ -211,11 +239,13 @@ def extract_matches(args, im_rgb1, im_gray1, im_rgb2, im_gray2, detector, descri
             ids = _capi.match_smnn(d1, d2, 0.99)[1].long()
             pts = []
             for xy, dx, col in ((xy1, dx1, 0), (xy2, dx2, 1)):
-                p = xy[ids[:, col]].cpu().numpy().astype(np.float64)
+                # int32 pixel + fp32 offset, added in float64 as the reference does on the host (both convert exactly)
+                p = xy[ids[:, col]].double()
                 if dx is not None:
-                    p = p + dx[ids[:, col]].cpu().numpy().astype(np.float64)
+                    p = p + dx[ids[:, col]].double()
                 pts.append(p)
-            return pts[0], pts[1]
+            both = torch.stack(pts).cpu().numpy()          # one device->host copy of the matched points of both images
+            return both[0], both[1]
     kpts1, desc1 = extract_features(args, im_rgb1, im_gray1, detector, descriptor, device)
     kpts2, desc2 = extract_features(args, im_rgb2, im_gray2, detector, descriptor, device)
     ids = _capi.match_smnn(torch.from_numpy(desc1).to(dev), torch.from_numpy(desc2).to(dev), 0.99)[1]
