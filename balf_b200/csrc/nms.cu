@@ -202,50 +202,143 @@ __device__ __forceinline__ Interior interior_of(const MapView& mv) {
     return Interior{mv.border, (unsigned)max(mv.H - 2 * mv.border, 0), (unsigned)max(mv.W - 2 * mv.border, 0)};
 }
 
-// Tiles whose 80 x 80 input window lies inside the border-masked interior (80 % of them at 480 x 640) are loaded by the TMA:
-// one cp.async.bulk.tensor of the [80 x 80] box of a 3-D tensor map over the score maps [B, Hs, Ws] -- no thread instruction, no
-// index arithmetic, completion on an mbarrier.  (Phase 1 was two thirds of this issue-bound kernel's instructions.)  The raw
-// fp32 bits are used as they are: scores are >= 0 (softmax probabilities), and a negative value orders below zero as an
-// integer, i.e. it can never survive -- the same outcome as the max(bits, 0) of the manual path.
-__device__ __forceinline__ uint32_t nms_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared state of one tile's phases 2-5 (everything but the pixels)
+struct Nms15Tile {
+    int cmax[kNmsNB][kNmsNB + 1];
+    uint32_t cand[kNmsInner * kNmsInner];       // lby | lbx << 8 | sure << 16
+    u64 surv[kNmsListCap];
+    int n_cand, n_surv, g_base;
+};
 
-__global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int vec_ok, const __grid_constant__ CUtensorMap tmap, int use_tma) {
-    __shared__ __align__(128) int px[kNmsIn][kNmsIn];
-    __shared__ __align__(8) unsigned long long tma_bar;
-    __shared__ int cmax[kNmsNB][kNmsNB + 1];
-    __shared__ uint32_t cand[kNmsInner * kNmsInner];       // lby | lbx << 8 | sure << 16
-    __shared__ u64 surv[kNmsListCap];
-    __shared__ int n_cand, n_surv, g_base;
-    const int b = blockIdx.z, tx0 = blockIdx.x * kNmsTile, ty0 = blockIdx.y * kNmsTile;
+// Phases 2-5 of the one-tile-per-CTA kernel on the tile at (ty0, tx0) of image b whose masked 80 x 80 window sits in px.  The
+// caller has zeroed t.n_cand / t.n_surv and ended phase 1 with a CTA barrier.
+__device__ __forceinline__ void nms15_phases(int (*px)[kNmsIn], Nms15Tile& t, const MapView& mv, const NmsWs& ws, int b, int ty0, int tx0) {
     const int tid = threadIdx.x, sub = tid & 3;
+    // ---- 2: block maxima
+    for (int i = tid; i < kNmsNB * kNmsNB; i += 256) {
+        const int by = i / kNmsNB, bx = i - by * kNmsNB;
+        const int4 r0 = *reinterpret_cast<const int4*>(&px[4 * by][4 * bx]);
+        const int4 r1 = *reinterpret_cast<const int4*>(&px[4 * by + 1][4 * bx]);
+        const int4 r2 = *reinterpret_cast<const int4*>(&px[4 * by + 2][4 * bx]);
+        const int4 r3 = *reinterpret_cast<const int4*>(&px[4 * by + 3][4 * bx]);
+        int m = __vimax3_s32(r0.x, r0.y, r0.z);
+        m = __vimax3_s32(m, r0.w, r1.x);
+        m = __vimax3_s32(m, r1.y, r1.z);
+        m = __vimax3_s32(m, r1.w, r2.x);
+        m = __vimax3_s32(m, r2.y, r2.z);
+        m = __vimax3_s32(m, r2.w, r3.x);
+        m = __vimax3_s32(m, r3.y, r3.z);
+        t.cmax[by][bx] = max(m, r3.w);
+    }
+    __syncthreads();
+    // ---- 3: coarse test, one thread per inner block
+    {
+        const int ly = (tid >> 4) + 2, lx = (tid & 15) + 2;
+        const int own = t.cmax[ly][lx];
+        if (own > 0) {
+            int m3 = __vimax3_s32(t.cmax[ly - 1][lx - 1], t.cmax[ly - 1][lx], t.cmax[ly - 1][lx + 1]);
+            m3 = __vimax3_s32(m3, t.cmax[ly][lx - 1], t.cmax[ly][lx + 1]);
+            m3 = __vimax3_s32(m3, t.cmax[ly + 1][lx - 1], t.cmax[ly + 1][lx]);
+            m3 = max(m3, t.cmax[ly + 1][lx + 1]);
+            if (own >= m3) {
+                int m5 = 0;
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx) m5 = __vimax3_s32(m5, t.cmax[ly - 2][lx + dx], t.cmax[ly + 2][lx + dx]);
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) m5 = __vimax3_s32(m5, t.cmax[ly + dy][lx - 2], t.cmax[ly + dy][lx + 2]);
+                t.cand[atomicAdd(&t.n_cand, 1)] = (uint32_t)ly | ((uint32_t)lx << 8) | (own >= m5 ? 0x10000u : 0u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 4: finish the candidates, four lanes each (sub-lane s owns row s of a block)
+    const int nc = t.n_cand;
+    u64* gkeys = ws.keys + (size_t)b * ws.cap;
+    for (int base = 0; base < nc; base += 64) {
+        const int ci = base + (tid >> 2);
+        if ((ci & ~7) >= nc) continue;                      // this warp's eight candidate slots are empty (warp-uniform)
+        const bool live = ci < nc;
+        const uint32_t c = live ? t.cand[ci] : 0u;
+        const bool sure = (c & 0x10000u) != 0;
+        const int ly = live ? (int)(c & 0xFFu) : 2, lx = live ? (int)((c >> 8) & 0xFFu) : 2;
+        const int own = live ? t.cmax[ly][lx] : -1;
+        unsigned peaks = 0;
+        {
+            const int4 v = *reinterpret_cast<const int4*>(&px[4 * ly + sub][4 * lx]);
+            peaks = ((v.x == own ? 1u : 0u) | (v.y == own ? 2u : 0u) | (v.z == own ? 4u : 0u) | (v.w == own ? 8u : 0u)) << (4 * sub);
+        }
+        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 1);
+        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 2);
+        while (__any_sync(0xffffffffu, peaks != 0)) {
+            const bool act = peaks != 0;
+            const int j = act ? __ffs(peaks) - 1 : 0;
+            peaks &= peaks - 1;
+            const int r = j >> 2, cc = j & 3;
+            int wmax = 0;
+            if (act && !sure) {
+                // ring blocks whose maximum exceeds own; inside the window lie rows >= r+1 of block row -2, rows <= r-1
+                // of block row +2, columns >= cc+1 of block column -2, columns <= cc-1 of block column +2
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int dy = k < 5 ? -2 : k < 10 ? 2 : (k - 10) / 2 - 1;
+                    const int dx = k < 10 ? (k % 5) - 2 : ((k & 1) ? 2 : -2);
+                    if (t.cmax[ly + dy][lx + dx] > own) {
+                        const bool row_in = dy == -2 ? sub >= r + 1 : dy == 2 ? sub <= r - 1 : true;
+                        if (row_in) {
+                            const int4 v = *reinterpret_cast<const int4*>(&px[4 * (ly + dy) + sub][4 * (lx + dx)]);
+                            const int lo = dx == -2 ? cc + 1 : 0, hi = dx == 2 ? cc - 1 : 3;
+                            if (lo <= 0 && 0 <= hi) wmax = max(wmax, v.x);
+                            if (lo <= 1 && 1 <= hi) wmax = max(wmax, v.y);
+                            if (lo <= 2 && 2 <= hi) wmax = max(wmax, v.z);
+                            if (lo <= 3 && 3 <= hi) wmax = max(wmax, v.w);
+                        }
+                    }
+                }
+            }
+            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
+            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
+            if (act && sub == 0 && own >= wmax) {
+                const int y = ty0 - kNmsHalo + 4 * ly + r, x = tx0 - kNmsHalo + 4 * lx + cc;
+                const u64 key = make_key(__int_as_float(own), (uint32_t)(y * mv.W + x));   // own > 0: its bits are the score
+                const int slot = atomicAdd(&t.n_surv, 1);
+                if (slot < kNmsListCap) t.surv[slot] = key;
+                else {                                       // plateau: more survivors than the staging list holds
+                    const unsigned gs = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+                    if (gs < ws.cap) gkeys[gs] = key; else atomicOr(ws.flags + b, 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 5: one append per CTA
+    const int ns = min(t.n_surv, kNmsListCap);
+    if (tid == 0 && ns > 0) t.g_base = (int)atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), (unsigned)ns);
+    __syncthreads();
+    for (int i = tid; i < ns; i += 256) {
+        const size_t gs = (size_t)t.g_base + i;
+        if (gs < ws.cap) gkeys[gs] = t.surv[i]; else atomicOr(ws.flags + b, 1);
+    }
+}
+
+// One CTA per tile, the window loaded with per-thread 128-bit loads: maps the TMA cannot describe (row pitch or base not a
+// multiple of 16 bytes, maps smaller than a window) and the development switch (balf_debug_set key 7).
+__global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int vec_ok) {
+    __shared__ __align__(128) int px[kNmsIn][kNmsIn];
+    __shared__ Nms15Tile t;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kNmsTile, ty0 = blockIdx.y * kNmsTile;
+    const int tid = threadIdx.x;
     const Interior in = interior_of(mv);
-    if (tid == 0) { n_cand = 0; n_surv = 0; }
+    if (tid == 0) { t.n_cand = 0; t.n_surv = 0; }
     // ---- 1: tile + halo -> shared memory
     const int* img = reinterpret_cast<const int*>(mv.score) + ((size_t)b * mv.Hs + mv.top) * mv.Ws + mv.left;   // crop origin, raw bits
     // (all of a thread's loads are issued before the first one is consumed: one HBM round trip per CTA, not seven)
     constexpr int kQuads = kNmsIn * (kNmsIn / 4), kIter = (kQuads + 255) / 256;
     int4 v[kIter];
     // Tiles whose 80 x 80 input window lies inside the border-masked interior (80 % of them at 480 x 640) skip every
-    // per-pixel bounds / border test: phase 1 is two thirds of this kernel's instructions, and the kernel is issue-bound.
+    // per-pixel bounds / border test
     const bool inner = vec_ok && in.yok(ty0 - kNmsHalo) && in.yok(ty0 - kNmsHalo + kNmsIn - 1) &&
                        in.xok(tx0 - kNmsHalo) && in.xok(tx0 - kNmsHalo + kNmsIn - 1);
-    if (inner && use_tma) {
-        const uint32_t bar = nms_smem_u32(&tma_bar);
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)(kNmsIn * kNmsIn * 4)) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         :: "r"(nms_smem_u32(&px[0][0])), "l"(&tmap), "r"(mv.left + tx0 - kNmsHalo), "r"(mv.top + ty0 - kNmsHalo), "r"(b), "r"(bar)
-                         : "memory");
-        }
-        __syncthreads();                                   // the barrier is initialised before anybody polls it
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar) : "memory");
-        }
-    } else if (inner) {
+    if (inner) {
         const int* base = img + (size_t)(ty0 - kNmsHalo) * mv.Ws + (tx0 - kNmsHalo);
 #pragma unroll
         for (int k = 0; k < kIter; ++k) {
@@ -293,109 +386,224 @@ __global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int ve
     }
     }
     __syncthreads();
-    // ---- 2: block maxima
-    for (int i = tid; i < kNmsNB * kNmsNB; i += 256) {
-        const int by = i / kNmsNB, bx = i - by * kNmsNB;
-        const int4 r0 = *reinterpret_cast<const int4*>(&px[4 * by][4 * bx]);
-        const int4 r1 = *reinterpret_cast<const int4*>(&px[4 * by + 1][4 * bx]);
-        const int4 r2 = *reinterpret_cast<const int4*>(&px[4 * by + 2][4 * bx]);
-        const int4 r3 = *reinterpret_cast<const int4*>(&px[4 * by + 3][4 * bx]);
-        int m = __vimax3_s32(r0.x, r0.y, r0.z);
-        m = __vimax3_s32(m, r0.w, r1.x);
-        m = __vimax3_s32(m, r1.y, r1.z);
-        m = __vimax3_s32(m, r1.w, r2.x);
-        m = __vimax3_s32(m, r2.y, r2.z);
-        m = __vimax3_s32(m, r2.w, r3.x);
-        m = __vimax3_s32(m, r3.y, r3.z);
-        cmax[by][bx] = max(m, r3.w);
+    nms15_phases(px, t, mv, ws, b, ty0, tx0);
+}
+
+// The TMA form (every map whose rows the tensor map can describe): PERSISTENT CTAs of eight AUTONOMOUS warps.
+//  * The 80 x 80 window of a tile arrives by one cp.async.bulk.tensor of the box of a 3-D tensor map over the score maps
+//    [B, Hs, Ws] into one of two shared-memory buffers, completion on that buffer's mbarrier -- no thread instruction, no index
+//    arithmetic; the window of the CTA's next tile is in flight while the current one is worked on.  Windows that reach over the
+//    border-masked interior, the crop or the map come in as raw values (zeros outside the map: the TMA's out-of-bounds fill) and
+//    are masked in place while the block maxima are taken.  The raw fp32 bits are used as they are: scores are >= 0 (softmax
+//    probabilities), and a negative value orders below zero as an integer, i.e. it can never survive -- the same outcome as the
+//    max(bits, 0) of the manual path.
+//  * ONE CTA barrier per tile.  The one-tile-per-CTA form is a chain of five barrier-separated phases, most of them a few dozen
+//    instructions deep, and spent 40 % of its stall samples at those barriers (ncu, round 2).  Here the CTA takes the block maxima
+//    together (phase 2, one barrier), then every warp works alone on the two inner block rows 2w+2, 2w+3 it owns: coarse test
+//    with one lane per block, its candidates finished four lanes each, __syncwarp only -- and moves on to the next tile while other
+//    warps are still busy.  Survivors are staged per tile; the LAST warp to leave a tile (a shared-memory counter) appends them to
+//    the image's key list with one global atomic and requests the window of the tile after next into the buffer just freed.
+//    (Measured alternatives: warps that also take their own block maxima of the six block rows they read -- no barrier at all, 2.4x
+//    the phase-2 work -- 45 us against 37; sixteen lanes per candidate with warp-group reductions instead of the serial walk over
+//    the ring blocks: 50 us.)
+constexpr int kNmsPxBytes = kNmsIn * kNmsIn * 4;
+constexpr int kNmsSurvCap = 64;               // survivors staged per tile (a 64 x 64 tile holds at most 64 without plateaus)
+struct Nms15W {
+    int cmax[2][kNmsNB][kNmsNB + 1];          // per window buffer: a warp may be one tile ahead of the slowest one
+    u64 surv[2][kNmsSurvCap];
+    unsigned char cl[8][32];                  // per warp: lane (| 0x80: sure) of each candidate block
+    int n_surv[2], done[2];
+    int info[2][4];                           // tile in a buffer: image, ty0, tx0, window inside the interior
+    unsigned long long full[2];
+};
+__device__ __forceinline__ uint32_t nms_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) nms15_tma_kernel(MapView mv, NmsWs ws, const __grid_constant__ CUtensorMap tmap,
+                                                        int tiles_x, int tiles_y, int ntiles) {
+    extern __shared__ __align__(128) unsigned char nms_dyn[];
+    __shared__ __align__(16) Nms15W S;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, sub = lane & 3;
+    const Interior in = interior_of(mv);
+    const int per_img = tiles_x * tiles_y, stride = (int)gridDim.x;
+    auto request = [&](int tile, int buf) {                 // one thread: the window of `tile` -> buffer `buf`
+        const int b = tile / per_img, r = tile - b * per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int ty0 = ty * kNmsTile, tx0 = tx * kNmsTile;
+        S.info[buf][0] = b; S.info[buf][1] = ty0; S.info[buf][2] = tx0;
+        S.info[buf][3] = in.yok(ty0 - kNmsHalo) && in.yok(ty0 - kNmsHalo + kNmsIn - 1) &&
+                         in.xok(tx0 - kNmsHalo) && in.xok(tx0 - kNmsHalo + kNmsIn - 1);
+        const uint32_t bar = nms_smem_u32(&S.full[buf]);
+        // (the arrive releases the info words to the warps that acquire the phase in their try_wait)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)kNmsPxBytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     :: "r"(nms_smem_u32(nms_dyn + buf * kNmsPxBytes)), "l"(&tmap), "r"(mv.left + tx0 - kNmsHalo),
+                        "r"(mv.top + ty0 - kNmsHalo), "r"(b), "r"(bar)
+                     : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(nms_smem_u32(&S.full[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(nms_smem_u32(&S.full[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.n_surv[0] = S.n_surv[1] = 0; S.done[0] = S.done[1] = 0;
+        if ((int)blockIdx.x < ntiles) request((int)blockIdx.x, 0);
+        if ((int)blockIdx.x + stride < ntiles) request((int)blockIdx.x + stride, 1);
     }
-    __syncthreads();
-    // ---- 3: coarse test, one thread per inner block
-    {
-        const int ly = (tid >> 4) + 2, lx = (tid & 15) + 2;
-        const int own = cmax[ly][lx];
-        if (own > 0) {
-            int m3 = __vimax3_s32(cmax[ly - 1][lx - 1], cmax[ly - 1][lx], cmax[ly - 1][lx + 1]);
-            m3 = __vimax3_s32(m3, cmax[ly][lx - 1], cmax[ly][lx + 1]);
-            m3 = __vimax3_s32(m3, cmax[ly + 1][lx - 1], cmax[ly + 1][lx]);
-            m3 = max(m3, cmax[ly + 1][lx + 1]);
-            if (own >= m3) {
-                int m5 = 0;
-#pragma unroll
-                for (int dx = -2; dx <= 2; ++dx) m5 = __vimax3_s32(m5, cmax[ly - 2][lx + dx], cmax[ly + 2][lx + dx]);
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) m5 = __vimax3_s32(m5, cmax[ly + dy][lx - 2], cmax[ly + dy][lx + 2]);
-                cand[atomicAdd(&n_cand, 1)] = (uint32_t)ly | ((uint32_t)lx << 8) | (own >= m5 ? 0x10000u : 0u);
+    __syncthreads();                                        // the only CTA barrier: mbarriers and counters are initialised
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += stride, ++it) {
+        const int buf = it & 1;
+        int (*px)[kNmsIn] = reinterpret_cast<int (*)[kNmsIn]>(nms_dyn + buf * kNmsPxBytes);
+        int (*cm)[kNmsNB + 1] = S.cmax[buf];
+        {
+            const uint32_t bar = nms_smem_u32(&S.full[buf]), parity = (uint32_t)(it >> 1) & 1u;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
             }
         }
-    }
-    __syncthreads();
-    // ---- 4: finish the candidates, four lanes each (sub-lane s owns row s of a block)
-    const int nc = n_cand;
-    u64* gkeys = ws.keys + (size_t)b * ws.cap;
-    for (int base = 0; base < nc; base += 64) {
-        const int ci = base + (tid >> 2);
-        if ((ci & ~7) >= nc) continue;                      // this warp's eight candidate slots are empty (warp-uniform)
-        const bool live = ci < nc;
-        const uint32_t c = live ? cand[ci] : 0u;
-        const bool sure = (c & 0x10000u) != 0;
-        const int ly = live ? (int)(c & 0xFFu) : 2, lx = live ? (int)((c >> 8) & 0xFFu) : 2;
-        const int own = live ? cmax[ly][lx] : -1;
-        unsigned peaks = 0;
-        {
-            const int4 v = *reinterpret_cast<const int4*>(&px[4 * ly + sub][4 * lx]);
-            peaks = ((v.x == own ? 1u : 0u) | (v.y == own ? 2u : 0u) | (v.z == own ? 4u : 0u) | (v.w == own ? 8u : 0u)) << (4 * sub);
+        const int b = S.info[buf][0], ty0 = S.info[buf][1], tx0 = S.info[buf][2];
+        const bool inner = S.info[buf][3] != 0;
+        // ---- 2: maxima of the 20 x 20 blocks, the whole CTA (masking the window in place where it leaves the interior)
+        for (int i = tid; i < kNmsNB * kNmsNB; i += 256) {
+            const int by = i / kNmsNB, bx = i - by * kNmsNB;
+            int4 r0 = *reinterpret_cast<const int4*>(&px[4 * by][4 * bx]);
+            int4 r1 = *reinterpret_cast<const int4*>(&px[4 * by + 1][4 * bx]);
+            int4 r2 = *reinterpret_cast<const int4*>(&px[4 * by + 2][4 * bx]);
+            int4 r3 = *reinterpret_cast<const int4*>(&px[4 * by + 3][4 * bx]);
+            if (!inner) {
+                const int gy = ty0 - kNmsHalo + 4 * by, gx = tx0 - kNmsHalo + 4 * bx;
+                const bool y0 = in.yok(gy), y1 = in.yok(gy + 1), y2 = in.yok(gy + 2), y3 = in.yok(gy + 3);
+                const bool x0 = in.xok(gx), x1 = in.xok(gx + 1), x2 = in.xok(gx + 2), x3 = in.xok(gx + 3);
+                if (!(y0 & y1 & y2 & y3 & x0 & x1 & x2 & x3)) {        // a block on (or beyond) the interior's boundary
+                    r0 = make_int4(y0 & x0 ? r0.x : 0, y0 & x1 ? r0.y : 0, y0 & x2 ? r0.z : 0, y0 & x3 ? r0.w : 0);
+                    r1 = make_int4(y1 & x0 ? r1.x : 0, y1 & x1 ? r1.y : 0, y1 & x2 ? r1.z : 0, y1 & x3 ? r1.w : 0);
+                    r2 = make_int4(y2 & x0 ? r2.x : 0, y2 & x1 ? r2.y : 0, y2 & x2 ? r2.z : 0, y2 & x3 ? r2.w : 0);
+                    r3 = make_int4(y3 & x0 ? r3.x : 0, y3 & x1 ? r3.y : 0, y3 & x2 ? r3.z : 0, y3 & x3 ? r3.w : 0);
+                    *reinterpret_cast<int4*>(&px[4 * by][4 * bx]) = r0;
+                    *reinterpret_cast<int4*>(&px[4 * by + 1][4 * bx]) = r1;
+                    *reinterpret_cast<int4*>(&px[4 * by + 2][4 * bx]) = r2;
+                    *reinterpret_cast<int4*>(&px[4 * by + 3][4 * bx]) = r3;
+                }
+            }
+            int m = __vimax3_s32(r0.x, r0.y, r0.z);
+            m = __vimax3_s32(m, r0.w, r1.x);
+            m = __vimax3_s32(m, r1.y, r1.z);
+            m = __vimax3_s32(m, r1.w, r2.x);
+            m = __vimax3_s32(m, r2.y, r2.z);
+            m = __vimax3_s32(m, r2.w, r3.x);
+            m = __vimax3_s32(m, r3.y, r3.z);
+            cm[by][bx] = max(m, r3.w);
         }
-        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 1);
-        peaks |= __shfl_xor_sync(0xffffffffu, peaks, 2);
-        while (__any_sync(0xffffffffu, peaks != 0)) {
-            const bool act = peaks != 0;
-            const int j = act ? __ffs(peaks) - 1 : 0;
-            peaks &= peaks - 1;
-            const int r = j >> 2, cc = j & 3;
-            int wmax = 0;
-            if (act && !sure) {
-                // ring blocks whose maximum exceeds own; inside the window lie rows >= r+1 of block row -2, rows <= r-1
-                // of block row +2, columns >= cc+1 of block column -2, columns <= cc-1 of block column +2
+        __syncthreads();                                    // the tile's only CTA barrier
+        // ---- 3: coarse test, one lane per inner block; warp w owns the inner block rows 2w + 2, 2w + 3
+        unsigned cmask;
+        {
+            const int rr = 2 * w + 2 + (lane >> 4), lx = 2 + (lane & 15);
+            const int own = cm[rr][lx];
+            bool is_c = false, sure = false;
+            if (own > 0) {
+                int m3 = __vimax3_s32(cm[rr - 1][lx - 1], cm[rr - 1][lx], cm[rr - 1][lx + 1]);
+                m3 = __vimax3_s32(m3, cm[rr][lx - 1], cm[rr][lx + 1]);
+                m3 = __vimax3_s32(m3, cm[rr + 1][lx - 1], cm[rr + 1][lx]);
+                m3 = max(m3, cm[rr + 1][lx + 1]);
+                if (own >= m3) {
+                    int m5 = 0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int dy = k < 5 ? -2 : k < 10 ? 2 : (k - 10) / 2 - 1;
-                    const int dx = k < 10 ? (k % 5) - 2 : ((k & 1) ? 2 : -2);
-                    if (cmax[ly + dy][lx + dx] > own) {
-                        const bool row_in = dy == -2 ? sub >= r + 1 : dy == 2 ? sub <= r - 1 : true;
-                        if (row_in) {
-                            const int4 v = *reinterpret_cast<const int4*>(&px[4 * (ly + dy) + sub][4 * (lx + dx)]);
-                            const int lo = dx == -2 ? cc + 1 : 0, hi = dx == 2 ? cc - 1 : 3;
-                            if (lo <= 0 && 0 <= hi) wmax = max(wmax, v.x);
-                            if (lo <= 1 && 1 <= hi) wmax = max(wmax, v.y);
-                            if (lo <= 2 && 2 <= hi) wmax = max(wmax, v.z);
-                            if (lo <= 3 && 3 <= hi) wmax = max(wmax, v.w);
+                    for (int dx = -2; dx <= 2; ++dx) m5 = __vimax3_s32(m5, cm[rr - 2][lx + dx], cm[rr + 2][lx + dx]);
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) m5 = __vimax3_s32(m5, cm[rr + dy][lx - 2], cm[rr + dy][lx + 2]);
+                    is_c = true;
+                    sure = own >= m5;
+                }
+            }
+            cmask = __ballot_sync(0xffffffffu, is_c);
+            if (is_c) S.cl[w][__popc(cmask & ((1u << lane) - 1u))] = (unsigned char)(lane | (sure ? 0x80 : 0));
+        }
+        __syncwarp();
+        // ---- 4: finish the candidates, four lanes each (sub-lane s owns row s of a block)
+        const int nc = __popc(cmask);
+        u64* gkeys = ws.keys + (size_t)b * ws.cap;
+        for (int base = 0; base < nc; base += 8) {
+            const int ci = base + (lane >> 2);
+            const bool live = ci < nc;
+            const unsigned c = live ? S.cl[w][ci] : 0u;
+            const bool sure = (c & 0x80u) != 0;
+            const int rr = 2 * w + 2 + (int)((c >> 4) & 1u), lx = 2 + (int)(c & 15u), ly = rr;     // block row / column of the tile
+            const int own = live ? cm[rr][lx] : -1;
+            unsigned peaks = 0;
+            {
+                const int4 v = *reinterpret_cast<const int4*>(&px[4 * ly + sub][4 * lx]);
+                peaks = ((v.x == own ? 1u : 0u) | (v.y == own ? 2u : 0u) | (v.z == own ? 4u : 0u) | (v.w == own ? 8u : 0u)) << (4 * sub);
+            }
+            peaks |= __shfl_xor_sync(0xffffffffu, peaks, 1);
+            peaks |= __shfl_xor_sync(0xffffffffu, peaks, 2);
+            while (__any_sync(0xffffffffu, peaks != 0)) {
+                const bool act = peaks != 0;
+                const int j = act ? __ffs(peaks) - 1 : 0;
+                peaks &= peaks - 1;
+                const int r = j >> 2, cc = j & 3;
+                int wmax = 0;
+                if (act && !sure) {
+                    // ring blocks whose maximum exceeds own; inside the window lie rows >= r+1 of block row -2, rows <= r-1
+                    // of block row +2, columns >= cc+1 of block column -2, columns <= cc-1 of block column +2
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int dy = k < 5 ? -2 : k < 10 ? 2 : (k - 10) / 2 - 1;
+                        const int dx = k < 10 ? (k % 5) - 2 : ((k & 1) ? 2 : -2);
+                        if (cm[rr + dy][lx + dx] > own) {
+                            const bool row_in = dy == -2 ? sub >= r + 1 : dy == 2 ? sub <= r - 1 : true;
+                            if (row_in) {
+                                const int4 v = *reinterpret_cast<const int4*>(&px[4 * (ly + dy) + sub][4 * (lx + dx)]);
+                                const int lo = dx == -2 ? cc + 1 : 0, hi = dx == 2 ? cc - 1 : 3;
+                                if (lo <= 0 && 0 <= hi) wmax = max(wmax, v.x);
+                                if (lo <= 1 && 1 <= hi) wmax = max(wmax, v.y);
+                                if (lo <= 2 && 2 <= hi) wmax = max(wmax, v.z);
+                                if (lo <= 3 && 3 <= hi) wmax = max(wmax, v.w);
+                            }
                         }
                     }
                 }
-            }
-            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
-            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
-            if (act && sub == 0 && own >= wmax) {
-                const int y = ty0 - kNmsHalo + 4 * ly + r, x = tx0 - kNmsHalo + 4 * lx + cc;
-                const u64 key = make_key(__int_as_float(own), (uint32_t)(y * mv.W + x));   // own > 0: its bits are the score
-                const int slot = atomicAdd(&n_surv, 1);
-                if (slot < kNmsListCap) surv[slot] = key;
-                else {                                       // plateau: more survivors than the staging list holds
-                    const unsigned gs = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
-                    if (gs < ws.cap) gkeys[gs] = key; else atomicOr(ws.flags + b, 1);
+                wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
+                wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 2));
+                if (act && sub == 0 && own >= wmax) {
+                    const int y = ty0 - kNmsHalo + 4 * ly + r, x = tx0 - kNmsHalo + 4 * lx + cc;
+                    const u64 key = make_key(__int_as_float(own), (uint32_t)(y * mv.W + x));   // own > 0: its bits are the score
+                    const int slot = atomicAdd(&S.n_surv[buf], 1);
+                    if (slot < kNmsSurvCap) S.surv[buf][slot] = key;
+                    else {                                   // plateau: more survivors than the staging list holds
+                        const unsigned gs = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), 1u);
+                        if (gs < ws.cap) gkeys[gs] = key; else atomicOr(ws.flags + b, 1);
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
-    // ---- 5: one append per CTA
-    const int ns = min(n_surv, kNmsListCap);
-    if (tid == 0 && ns > 0) g_base = (int)atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), (unsigned)ns);
-    __syncthreads();
-    for (int i = tid; i < ns; i += 256) {
-        const size_t gs = (size_t)g_base + i;
-        if (gs < ws.cap) gkeys[gs] = surv[i]; else atomicOr(ws.flags + b, 1);
+        __syncwarp();
+        // ---- 5: the last warp to leave the tile appends its survivors (one global atomic) and refills the buffer
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();                          // this warp's survivors and its reads of the window come first
+            last = atomicAdd(&S.done[buf], 1) == 7;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence_block();
+            const int ns = min(*reinterpret_cast<volatile int*>(&S.n_surv[buf]), kNmsSurvCap);
+            unsigned gb = 0;
+            if (lane == 0 && ns > 0) gb = atomicAdd(reinterpret_cast<unsigned*>(ws.count + b), (unsigned)ns);
+            gb = __shfl_sync(0xffffffffu, gb, 0);
+            for (int i = lane; i < ns; i += 32) {
+                const size_t gs = (size_t)gb + i;
+                const u64 key = *reinterpret_cast<volatile u64*>(&S.surv[buf][i]);
+                if (gs < ws.cap) gkeys[gs] = key; else atomicOr(ws.flags + b, 1);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                S.n_surv[buf] = 0; S.done[buf] = 0;
+                // the generic-proxy accesses of the window (every warp has left it) are ordered before the TMA's write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (tile + 2 * stride < ntiles) request(tile + 2 * stride, buf);
+            }
+        }
     }
 }
 
@@ -1133,12 +1341,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStream_t st) {
     const int vec_ok = (mv.left % 4 == 0) && (mv.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(mv.score) % 16 == 0);
-    dim3 grid(cdiv(mv.W, kNmsTile), cdiv(mv.H, kNmsTile), B);
-    // 3-D tensor map over the score maps [B, Hs, Ws] fp32, box = one 80 x 80 input window (row pitch a multiple of 16 bytes)
+    const int tiles_x = cdiv(mv.W, kNmsTile), tiles_y = cdiv(mv.H, kNmsTile);
+    // 3-D tensor map over the score maps [B, Hs, Ws] fp32, box = one 80 x 80 input window (row pitch and base multiples of 16 bytes)
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     int use_tma = 0;
-    if (vec_ok && g_nms_tma && mv.Ws >= kNmsIn && mv.Hs >= kNmsIn) {
+    if (g_nms_tma && mv.Ws % 4 == 0 && reinterpret_cast<uintptr_t>(mv.score) % 16 == 0 && mv.Ws >= kNmsIn && mv.Hs >= kNmsIn) {
         if (EncodeTiledFn enc = encode_tiled_fn()) {
             const cuuint64_t dims[3] = {(cuuint64_t)mv.Ws, (cuuint64_t)mv.Hs, (cuuint64_t)B};
             const cuuint64_t strides[2] = {(cuuint64_t)mv.Ws * 4, (cuuint64_t)mv.Ws * mv.Hs * 4};
@@ -1149,9 +1357,27 @@ static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStre
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
     }
-    {
+    if (use_tma) {
+        // persistent CTAs, two window buffers each (50 KB of dynamic shared memory): four CTAs per SM
+        static int per_sm = 0, sms = 0;
+        const int smem = 2 * kNmsPxBytes;
+        if (!per_sm) {
+            BALF_CUDA_OK(cudaFuncSetAttribute(nms15_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int dev = 0, occ = 0;
+            BALF_CUDA_OK(cudaGetDevice(&dev));
+            BALF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            BALF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms15_tma_kernel, 256, smem));
+            BALF_REQUIRE(occ > 0, "internal: nms15_tma_kernel does not fit an SM");
+            per_sm = occ;
+        }
+        const int ntiles = tiles_x * tiles_y * B;
+        const int grid = std::min(ntiles, sms * per_sm);
         ProfScope p("nms_windowed", st);
-        nms15_kernel<<<grid, 256, 0, st>>>(mv, ws, vec_ok, tmap, use_tma);
+        nms15_tma_kernel<<<grid, 256, smem, st>>>(mv, ws, tmap, tiles_x, tiles_y, ntiles);
+    } else {
+        dim3 grid(tiles_x, tiles_y, B);
+        ProfScope p("nms_windowed", st);
+        nms15_kernel<<<grid, 256, 0, st>>>(mv, ws, vec_ok);
     }
     BALF_COUNT_LAUNCH(1);
     return 0;
