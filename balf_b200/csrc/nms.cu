@@ -405,7 +405,10 @@ __global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int ve
 //    the image's key list with one global atomic and requests the window of the tile after next into the buffer just freed.
 //    (Measured alternatives: warps that also take their own block maxima of the six block rows they read -- no barrier at all, 2.4x
 //    the phase-2 work -- 45 us against 37; sixteen lanes per candidate with warp-group reductions instead of the serial walk over
-//    the ring blocks: 50 us.)
+//    the ring blocks: 50 us; four ring blocks per sub-lane (a four-step instead of a sixteen-step walk): 42 us -- every variant
+//    that shortens a dependency chain at the price of more instructions lost.  Phase-skipping runs put the kernel's time at:
+//    block maxima + barrier 9 us, coarse test 3, candidates 10, append 2, loop / hand-over 7; the window loads alone take
+//    19 us and hide behind the rest.)
 constexpr int kNmsPxBytes = kNmsIn * kNmsIn * 4;
 constexpr int kNmsSurvCap = 64;               // survivors staged per tile (a 64 x 64 tile holds at most 64 without plateaus)
 struct Nms15W {
@@ -1342,11 +1345,13 @@ static EncodeTiledFn encode_tiled_fn() {
 static int launch_windowed15(const MapView& mv, const NmsWs& ws, int B, cudaStream_t st) {
     const int vec_ok = (mv.left % 4 == 0) && (mv.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(mv.score) % 16 == 0);
     const int tiles_x = cdiv(mv.W, kNmsTile), tiles_y = cdiv(mv.H, kNmsTile);
-    // 3-D tensor map over the score maps [B, Hs, Ws] fp32, box = one 80 x 80 input window (row pitch and base multiples of 16 bytes)
+    // 3-D tensor map over the score maps [B, Hs, Ws] fp32, box = one 80 x 80 input window (row pitch, base and box start multiples of 16 bytes)
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     int use_tma = 0;
-    if (g_nms_tma && mv.Ws % 4 == 0 && reinterpret_cast<uintptr_t>(mv.score) % 16 == 0 && mv.Ws >= kNmsIn && mv.Hs >= kNmsIn) {
+    // (the box must start on a 16-byte boundary of its row as well: a crop whose left edge is not a multiple of four pixels
+    // faults in the TMA unit -- "illegal instruction" -- so those maps take the per-thread loads)
+    if (g_nms_tma && vec_ok && mv.Ws >= kNmsIn && mv.Hs >= kNmsIn) {
         if (EncodeTiledFn enc = encode_tiled_fn()) {
             const cuuint64_t dims[3] = {(cuuint64_t)mv.Ws, (cuuint64_t)mv.Hs, (cuuint64_t)B};
             const cuuint64_t strides[2] = {(cuuint64_t)mv.Ws * 4, (cuuint64_t)mv.Ws * mv.Hs * 4};

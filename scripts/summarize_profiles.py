@@ -115,7 +115,7 @@ def traffic():
                 name = "det_pool_c%s" % m.group(1)
             if "tc_head_kernel" in kn:
                 name = "det_head"
-            if "nms15_kernel" in kn:
+            if "nms15_kernel" in kn or "nms15_tma_kernel" in kn:
                 name = "nms_windowed"
             if "select_sort_kernel" in kn:
                 name = "nms_select_sort"

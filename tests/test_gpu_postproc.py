@@ -240,6 +240,32 @@ def test_windowed15_two_level_edge_cases():
     np.testing.assert_array_equal(gpu_windowed(m, 64, 0, 15)[0], postproc.windowed_detect(m[0], 0, 15, 64))
 
 
+def test_windowed15_tma_and_fallback_paths():
+    """nms_size 15 on maps the TMA can describe (row pitch a multiple of 16 bytes, at least one 80 x 80 window): the persistent
+    double-buffered kernel (windows that leave the interior are masked in place) against the oracle and against the per-thread-load
+    kernel (balf_debug_set key 7), for crops whose left edge is / is not a multiple of four pixels (the TMA faults on a box that
+    does not start on a 16-byte boundary: those crops must take the fallback), partial tiles, every border class, negative scores."""
+    rng = np.random.default_rng(29)
+    base = (rng.random((5, 176, 336), dtype=np.float32) - 0.1).astype(np.float32)           # ~10 % negative
+    base[1] = np.round(base[1] * 16) / 16                                                    # plateaus / ties
+    base[2] *= (rng.random((176, 336)) > 0.97)                                               # sparse, many zeros
+    c = capi()
+    try:
+        for (top, left, H, W) in ((0, 0, 176, 336), (3, 4, 160, 320), (2, 5, 150, 300), (25, 25, 129, 257), (8, 8, 100, 200)):
+            for border in (0, 7, 15):
+                k = 2048
+                outs = []
+                for tma in (1, 0):
+                    c.debug_set(7, tma)
+                    outs.append(gpu_windowed(base, k, border, 15, (top, left, H, W)))
+                for b in range(base.shape[0]):
+                    want = postproc.windowed_detect(base[b, top:top + H, left:left + W], border, 15, k)
+                    np.testing.assert_array_equal(outs[0][b], want, err_msg="crop %s border %d image %d" % ((top, left, H, W), border, b))
+                    np.testing.assert_array_equal(outs[1][b], want, err_msg="fallback: crop %s border %d image %d" % ((top, left, H, W), border, b))
+    finally:
+        c.debug_set(7, 1)
+
+
 # ----------------------------------------------------------------------------- cell-based greedy NMS (round 2) and box_nms
 def test_greedy_cells_vs_whole_image_kernel_and_oracle():
     """the multi-CTA cell rounds, the one-CTA-per-image finisher (long monotone ramps need one round per kept pixel, far
