@@ -19,7 +19,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
 timeout 1200 ncu --set full --clock-control none -k regex:"${NCU_KERNEL:-tc_branch_kernel|tc_merge_bulk_kernel|tc_merge_kernel|tc_head_kernel|pool_kernel}" -s ${NCU_SKIP:-48} -c ${NCU_COUNT:-16} \
     -f -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"nms15_kernel|select_sort_kernel" -s 6 -c 2 \
+timeout 600 ncu --set full --clock-control none -k regex:"nms15_(tma_)?kernel|select_sort_kernel" -s 6 -c 2 \
     -f -o gpurun_out/prof_nms python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_nms.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"greedy_cells" -s 24 -c 8 \
     -f -o gpurun_out/prof_greedy python bench.py --steps 1 --warmup 3 --nms greedy --precision tf32 --no-cpu-baseline --no-extras > gpurun_out/ncu_greedy.log 2>&1

@@ -10,7 +10,7 @@ B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_bench.log 2>&1
 timeout 1200 ncu --set full --clock-control none -k regex:"tc_branch_kernel|tc_merge_bulk_kernel|tc_merge_kernel|tc_head_kernel|pool_kernel" -s 48 -c 16 \
     -f -o gpurun_out/prof $B > gpurun_out/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"nms15_kernel|select_sort_kernel" -s 6 -c 2 -f -o gpurun_out/prof_nms $B > gpurun_out/ncu_nms.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"nms15_(tma_)?kernel|select_sort_kernel" -s 6 -c 2 -f -o gpurun_out/prof_nms $B > gpurun_out/ncu_nms.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"greedy_cells" -s 24 -c 8 -f -o gpurun_out/prof_greedy $B --nms greedy --precision tf32 > gpurun_out/ncu_greedy.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"hn_tc_(conv|first|final)_kernel" -s 7 -c 7 -f -o gpurun_out/prof_hn python scripts/hn_bench.py > gpurun_out/ncu_hn.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"nn2_tc_kernel|merge_splits_kernel|smnn_select_kernel" -s 4 -c 4 -f -o gpurun_out/prof_smnn python scripts/smnn_bench.py > gpurun_out/ncu_smnn.log 2>&1
