@@ -175,7 +175,8 @@ def extract_features(args, im_rgb, im_gray, detector, descriptor, device):
     return kpts_np[:, 0:2], descs.cpu().numpy()
 
 
-_PAIR_STAGING = {}      # (device, shape) -> pinned uint8 staging buffers of the device-resident pair path, reused across calls
+_PAIR_STAGING = {}      # (key, device, shape) -> [pinned uint8 staging buffer, event of its last DMA]; the device-resident pair
+_PAIR_STAGING_MAX = 4   # path reuses them across calls, at most this many shapes (least recently used first out)
 
 
 def _pinned_upload(key, arrays, dev):
@@ -184,9 +185,14 @@ def _pinned_upload(key, arrays, dev):
     array i crosses PCIe, and no stacked pageable copy is built first.  The buffer may be rewritten only once its last DMA has
     finished: the event recorded after the copies is waited on at the next use."""
     shape = (len(arrays),) + tuple(arrays[0].shape)
-    slot = _PAIR_STAGING.get((key, dev, shape))
+    slot = _PAIR_STAGING.pop((key, dev, shape), None)
     if slot is None:
-        slot = _PAIR_STAGING[(key, dev, shape)] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True), None]
+        while len(_PAIR_STAGING) >= _PAIR_STAGING_MAX:          # images of many sizes (HPatches): do not hoard pinned memory
+            _, old_event = _PAIR_STAGING.pop(next(iter(_PAIR_STAGING)))
+            if old_event is not None:
+                old_event.synchronize()
+        slot = [torch.empty(shape, dtype=torch.uint8, pin_memory=True), None]
+    _PAIR_STAGING[(key, dev, shape)] = slot                   # (re-)inserted last: dict order = least recently used first
     pin, last = slot
     if last is not None:
         last.synchronize()
