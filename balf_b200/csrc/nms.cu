@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int ve
     nms15_phases(px, t, mv, ws, b, ty0, tx0);
 }
 
-// The TMA form (every map whose rows the tensor map can describe): PERSISTENT CTAs of eight AUTONOMOUS warps.
+// The TMA form (every map whose rows and crop the tensor map can describe): PERSISTENT CTAs, two window buffers each.
 //  * The 80 x 80 window of a tile arrives by one cp.async.bulk.tensor of the box of a 3-D tensor map over the score maps
 //    [B, Hs, Ws] into one of two shared-memory buffers, completion on that buffer's mbarrier -- no thread instruction, no index
 //    arithmetic; the window of the CTA's next tile is in flight while the current one is worked on.  Windows that reach over the
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) nms15_kernel(MapView mv, NmsWs ws, int ve
 //    seven on a named barrier (bar.arrive / bar.sync), appends them to the image's key list with one global atomic and requests
 //    the window of the tile after next into the buffer just freed.
 //    (Measured alternatives: warps that also take their own block maxima of the six block rows they read -- no barrier at all, 2.4x
-//    the phase-2 work -- 45 us against 37; sixteen lanes per candidate with warp-group reductions instead of the serial walk over
+//    the phase-2 work -- 45 us against 37 (scripts/nms_bench.py); sixteen lanes per candidate with warp-group reductions instead of the serial walk over
 //    the ring blocks: 50 us; four ring blocks per sub-lane (a four-step instead of a sixteen-step walk): 42 us -- every variant
 //    that shortens a dependency chain at the price of more instructions lost.  Phase-skipping runs put the kernel's time at:
 //    block maxima + barrier 9 us, coarse test 3, candidates 10, append 2, loop / hand-over 7; the window loads alone take
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256, 5) nms15_tma_kernel(MapView mv, NmsWs ws,
         if ((int)blockIdx.x < ntiles) request((int)blockIdx.x, 0);
         if ((int)blockIdx.x + stride < ntiles) request((int)blockIdx.x + stride, 1);
     }
-    __syncthreads();                                        // the only CTA barrier: mbarriers and counters are initialised
+    __syncthreads();                                        // mbarriers and counters are initialised
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += stride, ++it) {
         const int buf = it & 1;
